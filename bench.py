@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py — scan-to-map registrations/sec (100k-pt scan vs 1M-pt map) on B200, per BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload headline|c2|c1|c4]
+
+One "step" = one NDT registration (pcl::Registration::align semantics) of a synthetic 64-ring scan (~100k points)
+against a 1M-point map, resolution 2.0, DIRECT7, transformation_epsilon 0.01, max 35 iterations, identity guess —
+the steady state apps/align.cpp:32-36 calls "10times" (target already set).
+
+ * value     : registrations/s with the scans already resident in HBM (setInputSourceDevice + align per step)
+ * e2e       : the same through the public API with HOST buffers: setInputSource(numpy) + align + 4x4 read-back
+ * roofline  : the solver kernel's algorithmic bytes (per evaluation N_src*16 + N_src*7*8 +
+               N_hit*48 + 224) / its CUDA-event duration on the launching stream, vs MEASURED_PEAKS.json hbm_gbs
+ * cpu_baseline: the CPU oracle (restatement of the reference's OpenMP path) on the same workload, bounded sample
+ * --impl reference: times that CPU path alone (the reference needs PCL/Eigen/FLANN and cannot be built here)
+N > 1: one process per GPU (torchrun), each rank registers its own K scans (replicas — a single alignment does not
+shard) and ONE NCCL all-gather of the K 4x4 poses closes the timed region; value = N*K / max time.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (synth config, resolution, description)
+    "headline": ("headline", 2.0, "NDT align, 64-ring scan (~100k pts) vs 1M-pt map, res 2.0, DIRECT7, eps 0.01, max_iter 35"),
+    "c2": ("c2", 2.0, "NDT align, 32-ring scan (~60k pts) vs 500k-pt map, res 2.0, DIRECT7, eps 0.01, max_iter 35"),
+    "c1": ("c1", 5.0, "NDT align, 16-ring scan (~10k pts) vs 50k-pt map, res 5.0, DIRECT7, eps 0.01, max_iter 35"),
+}
+N_SCANS = 4  # distinct scans rotated through the steps
+
+
+def make_workload(name: str, rank: int):
+    from lidarslam_ros2_b200 import synth
+
+    cfg, res, desc = WORKLOADS[name]
+    src0, tgt, T_gt = synth.registration_pair(cfg, res)
+    rings, azim = {"headline": (64, 1563), "c2": (32, 1875), "c1": (16, 625)}[name]
+    scene = synth.make_scene()
+    scans = [src0]
+    d = np.pi / 180.0
+    for k in range(1, N_SCANS):  # nearby sensor poses → different scans, same map
+        s = 1.0 + 0.15 * k + 0.07 * rank
+        T = synth.pose_matrix((0.40 * s, -0.25 * s, 0.06), (0.4 * d, -0.3 * d * s, 1.5 * d * s))
+        scans.append(synth.make_scan(scene, rings, azim, synth.sensor_pose(T), stream=9000 + 10 * k + 100 * rank))
+    return scans, tgt, res, desc
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+def time_cpu(scans, tgt, res, max_seconds: float, max_aligns: int, threads: int | None = None):
+    """CPU oracle on the same workload. Returns (registrations/s, n_aligns, threads, poses)."""
+    import oracle
+
+    oracle.build()
+    nt = threads or oracle.max_threads()
+    n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=nt)
+    n.set_target(tgt)
+    n.set_source(scans[0])
+    n.align()  # warm-up (also builds the lazy target kd-tree like PCL's first align)
+    poses, t_total, k = [], 0.0, 0
+    while k < max_aligns and (k < 2 or t_total < max_seconds):
+        n.set_source(scans[k % len(scans)])
+        t0 = time.perf_counter()
+        poses.append(n.align())
+        t_total += time.perf_counter() - t0
+        k += 1
+    return k / t_total, k, nt, poses
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU (OpenMP) path for this hot path, timed on the box's host cores."""
+    if rank != 0:
+        return
+    scans, tgt, res, desc = make_workload(args.workload, 0)
+    import oracle
+
+    oracle.build()
+    nt = oracle.max_threads()
+    n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=nt)
+    n.set_target(tgt)
+    for w in range(min(args.warmup, 3)):
+        n.set_source(scans[w % len(scans)])
+        n.align()
+    t_total = 0.0
+    for k in range(args.steps):
+        n.set_source(scans[k % len(scans)])
+        t0 = time.perf_counter()
+        n.align()
+        t_total += time.perf_counter() - t0
+    v = args.steps / t_total
+    line = {
+        "impl": "reference", "metric": "scan-to-map registrations/sec", "value": v, "unit": "registrations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math / f64 accumulation",
+        "data": "synthetic",
+        "config": {"workload": desc, "n_source": int(len(scans[0])), "n_target": int(len(tgt)),
+                   "note": "reference cannot be compiled here (PCL/Eigen/FLANN absent): CPU restatement oracle/ (kind=port)"},
+        "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": nt, "kind": "port",
+                         "sample": f"{args.steps} full align() calls, {nt} OpenMP threads, host has {os.cpu_count()} cpus"},
+        "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the registration engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import lidarslam_ros2_b200 as m
+
+    args.warmup = max(args.warmup, 3)
+    scans, tgt, res, desc = make_workload(args.workload, rank)
+    K, W = args.steps, args.warmup
+
+    ndt = m.NormalDistributionsTransform(device=local_rank)
+    ndt.setResolution(res)
+    ndt.setTransformationEpsilon(0.01)
+    ndt.setMaximumIterations(35)
+    ndt.setNeighborhoodSearchMethod(m.DIRECT7)
+    t0 = time.perf_counter()
+    ndt.setInputTarget(tgt)  # H2D + voxel map build (reported separately)
+    set_target_ms = 1e3 * (time.perf_counter() - t0)
+    target_build_ms = ndt.stats()["target_build_ms"]
+
+    # scans resident in HBM as float4 (plumbing: torch owns the device memory)
+    dev_scans = []
+    for s in scans:
+        a = np.concatenate([s, np.ones((len(s), 1), dtype=np.float32)], axis=1)
+        dev_scans.append(torch.from_numpy(a).cuda())
+    pinned_scans = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in scans]
+    flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+    poses_dev = torch.zeros((K, 16), dtype=torch.float32, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident(k):
+        d = dev_scans[k % N_SCANS]
+        ndt.setInputSourceDevice(d.data_ptr(), d.shape[0])
+        return ndt.align()
+
+    def step_e2e(k):
+        ndt.setInputSource(pinned_scans[k % N_SCANS].numpy())
+        return ndt.align()
+
+    for k in range(W):
+        step_resident(k)
+        step_e2e(k)
+
+    # ---- timed: HBM-resident -------------------------------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ndt.stats()["kernel_launches"]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    solve_ms, evals, hits_tot, alg_bytes = [], [], [], []
+    poses = []
+    barrier()
+    wall0 = time.perf_counter()
+    for k in range(K):
+        if not args.no_flush:
+            flush_buf.zero_()  # evict L2 (126 MB) between steps; excluded from the per-step timing
+            torch.cuda.synchronize()
+        ev[k][0].record()
+        T = step_resident(k)
+        ev[k][1].record()
+        poses.append(T)
+        st = ndt.stats()
+        solve_ms.append(st["solve_ms"])
+        evals.append(st["evaluations"])
+        hits_tot.append(st["hits_total"])
+        n_src = st["n_source"]
+        alg_bytes.append(st["evaluations"] * (n_src * 16 + n_src * 7 * 8 + 224) + st["hits_total"] * 48)
+    poses_dev.copy_(torch.from_numpy(np.stack(poses).reshape(K, 16)))
+    if world > 1:  # the one collective of the batched sweep: all-gather of the 4x4 poses (NCCL over NVLink)
+        gathered = [torch.empty_like(poses_dev) for _ in range(world)]
+        dist.all_gather(gathered, poses_dev)
+    barrier()
+    wall = time.perf_counter() - wall0
+    launches = ndt.stats()["kernel_launches"] - launches0
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = float(np.sum(step_ms))
+    clocks = sampler.stop()
+    t_total = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t_total.item())
+
+    # ---- timed: end to end with host buffers -------------------------------------------------------------
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    barrier()
+    for k in range(K):
+        if not args.no_flush:
+            flush_buf.zero_()
+            torch.cuda.synchronize()
+        ev2[k][0].record()
+        T = step_e2e(k)
+        ev2[k][1].record()
+    barrier()
+    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ev2]))
+    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms_max = float(t2.item())
+
+    if rank == 0:
+        peak, which = hbm_peak()
+        kern_s = float(np.sum(solve_ms)) * 1e-3
+        achieved = float(np.sum(alg_bytes)) / kern_s / 1e9 if kern_s > 0 else 0.0
+        line = {
+            "metric": "scan-to-map registrations/sec", "value": world * K / (total_ms_max * 1e-3), "unit": "registrations/s",
+            "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math / f64 reduction", "data": "synthetic",
+            "config": {"workload": desc, "n_source": int(len(scans[0])), "n_target": int(len(tgt)),
+                       "n_voxels": int(ndt.stats()["n_voxels"]), "guess": "identity",
+                       "l2": "working set < L2: L2 flushed (256 MiB memset) between steps, flush excluded from timing"
+                       if not args.no_flush else "L2 warm (no flush)",
+                       "parallelism": f"replicas x{world} + 1 NCCL all-gather of poses" if world > 1 else "1 GPU",
+                       "grid_ctas": ndt.stats()["grid_ctas"], "block_threads": ndt.stats()["block_threads"],
+                       "index_in_smem": ndt.stats()["index_in_smem"]},
+            "e2e": {"value": world * K / (e2e_ms_max * 1e-3), "unit": "registrations/s",
+                    "h2d_bytes_per_step": int(len(scans[0]) * 16), "d2h_bytes_per_step": 64 + 456,
+                    "ms_per_step": e2e_ms_max / K},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "ndt_solver_kernel<DIRECT7> (persistent: all evaluations of one align)",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
+                         "traffic": None, "alg_bytes_per_launch": float(np.mean(alg_bytes)),
+                         "launch_ms": float(np.mean(solve_ms)), "evaluations_per_launch": float(np.mean(evals)),
+                         "us_per_evaluation": 1e3 * float(np.sum(solve_ms)) / max(1, int(np.sum(evals))),
+                         "hits_per_point": float(np.sum(hits_tot)) / max(1, int(np.sum(evals))) / max(1, len(scans[0]))},
+            "target_build": {"set_input_target_ms": set_target_ms, "voxel_build_device_ms": target_build_ms},
+            "wall_s_timed_region": wall,
+        }
+        if not args.no_cpu_baseline and world >= 1:
+            v, k_done, nt, cpu_poses = time_cpu(scans, tgt, res, max_seconds=20.0, max_aligns=min(K, 40))
+            from lidarslam_ros2_b200 import synth
+
+            errs = [synth.pose_error(poses[i], cpu_poses[i]) for i in range(min(len(cpu_poses), K))]
+            line["cpu_baseline"] = {"value": v, "unit": "registrations/s", "cores": nt, "kind": "port",
+                                    "sample": f"{k_done} full align() calls of the same workload, {nt} OpenMP threads "
+                                              f"(host reports {os.cpu_count()} cpus)",
+                                    "pose_parity_max": {"dt_m": max(e[0] for e in errs), "dr_rad": max(e[1] for e in errs)}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

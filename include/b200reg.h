@@ -1,0 +1,146 @@
+/* b200reg.h — C-ABI of the B200-native scan-registration engine.
+ *
+ * Drop-in boundary: the pcl::Registration<PointXYZI,PointXYZI> surface that lidarslam_ros2's nodes hold
+ * (scanmatcher/include/scanmatcher/scanmatcher_component.h:93, graph_based_slam/include/graph_based_slam/
+ * graph_based_slam_component.h:106) and through which they drive pclomp::NormalDistributionsTransform and
+ * pclomp::GeneralizedIterativeClosestPoint. Every entry point below names the reference interface it
+ * replaces (paths relative to the reference root; "ndt.h" = Thirdparty/ndt_omp_ros2/include/pclomp/ndt_omp.h,
+ * "gicp.h" = .../gicp_omp.h, "sm.cpp" = scanmatcher/src/scanmatcher_component.cpp,
+ * "gbs.cpp" = graph_based_slam/src/graph_based_slam_component.cpp).
+ *
+ * Conventions
+ *  - plain C, opaque handle, no exceptions; every call returns 0 (B200REG_OK) or a negative error code,
+ *    b200reg_last_error() gives the text. PCL-style soft failure: an empty cloud is rejected and ignored.
+ *  - 4x4 matrices are 16 floats COLUMN-MAJOR — exactly Eigen::Matrix4f::data().
+ *  - clouds are (const float* base, size_t n, size_t stride_bytes) with x,y,z at byte offsets 0,4,8 of every
+ *    point: pass pcl::PointCloud<PointXYZI>::points.data() with stride 32 (PointXYZ: 16).
+ *  - the library copies what it needs to the GPU inside set_input_*; caller memory may be freed on return.
+ *  - one handle = one CUDA stream + its device buffers; a handle is used from one host thread at a time,
+ *    different handles may be used concurrently from different threads (lidarslam/src/lidarslam.cpp:12-17).
+ *  - there is NO CPU fallback: without a CUDA device b200reg_create fails with B200REG_ERR_CUDA.
+ */
+#ifndef B200REG_H_
+#define B200REG_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b200reg_engine* b200reg_t;
+
+enum b200reg_kind { B200REG_NDT = 0, B200REG_GICP = 1 };
+
+/* pclomp::NeighborSearchMethod (ndt.h:52-57), same numeric order */
+enum b200reg_search { B200REG_KDTREE = 0, B200REG_DIRECT26 = 1, B200REG_DIRECT7 = 2, B200REG_DIRECT1 = 3 };
+
+enum b200reg_status {
+  B200REG_OK = 0,
+  B200REG_ERR_ARG = -1,       /* bad argument / wrong engine kind                                    */
+  B200REG_ERR_NO_TARGET = -2, /* align/fitness without setInputTarget (PCL: initCompute() fails)      */
+  B200REG_ERR_NO_SOURCE = -3, /* align without setInputSource                                          */
+  B200REG_ERR_CUDA = -4,      /* CUDA runtime error, or no device                                      */
+  B200REG_ERR_TIMEOUT = -5,   /* device-side watchdog fired inside the persistent solver               */
+  B200REG_ERR_GRID = -6       /* voxel grid would overflow int32 (voxel_grid_covariance_omp_impl.hpp:79) */
+};
+
+/* ---- lifetime --------------------------------------------------------------------------------------- */
+/* replaces `new pclomp::NormalDistributionsTransform<...>()` / `new pclomp::GeneralizedIterativeClosestPoint
+ * <...>()` (sm.cpp:105-106,116-117; gbs.cpp:64-65,74-75). Defaults are the reference constructors'
+ * (ndt_omp_impl.hpp:47-76: resolution 1.0, step 0.1, outlier 0.55, eps 0.1, 35 iterations, DIRECT7;
+ * gicp.h:108-128: k=20, gicp_eps 1e-3, rot_eps 2e-3, 20 inner, 200 outer, eps 5e-4, corr-dist 5). */
+int b200reg_create(int kind, int device, b200reg_t* out);
+int b200reg_destroy(b200reg_t h);
+const char* b200reg_last_error(b200reg_t h);
+
+/* ---- pcl::Registration setters (sm.cpp:109,118-119; gbs.cpp:66-69,76-81) ---------------------------- */
+int b200reg_set_transformation_epsilon(b200reg_t h, double eps);      /* setTransformationEpsilon      */
+int b200reg_set_maximum_iterations(b200reg_t h, int n);               /* setMaximumIterations          */
+int b200reg_set_max_correspondence_distance(b200reg_t h, double d);   /* setMaxCorrespondenceDistance  */
+int b200reg_set_euclidean_fitness_epsilon(b200reg_t h, double eps);   /* stored; unused by both engines */
+int b200reg_set_ransac_iterations(b200reg_t h, int n);                /* stored; unused by both engines */
+
+/* ---- pclomp::NormalDistributionsTransform setters / getters (ndt.h:110-233) ------------------------- */
+int b200reg_ndt_set_resolution(b200reg_t h, float resolution);        /* ndt.h:127-137                 */
+int b200reg_ndt_set_step_size(b200reg_t h, double step);              /* ndt.h:162-166                 */
+int b200reg_ndt_set_outlier_ratio(b200reg_t h, double ratio);         /* ndt.h:180-184 (setOulierRatio) */
+int b200reg_ndt_set_neighborhood_search_method(b200reg_t h, int m);   /* ndt.h:186-188                 */
+int b200reg_ndt_set_num_threads(b200reg_t h, int n);                  /* ndt.h:110-112; accepted, no-op */
+int b200reg_ndt_get_transformation_probability(b200reg_t h, double* out); /* ndt.h:193-197             */
+int b200reg_ndt_get_final_num_iteration(b200reg_t h, int* out);       /* ndt.h:202-206                 */
+/* ndt.h:233 calculateScore(cloud): cloud is an already-transformed source */
+int b200reg_ndt_calculate_score(b200reg_t h, const float* base, size_t n, size_t stride_bytes, double* out);
+
+/* ---- pclomp::GeneralizedIterativeClosestPoint setters (gicp.h:156-252) ------------------------------- */
+int b200reg_gicp_set_rotation_epsilon(b200reg_t h, double eps);       /* setRotationEpsilon            */
+int b200reg_gicp_set_correspondence_randomness(b200reg_t h, int k);   /* setCorrespondenceRandomness   */
+int b200reg_gicp_set_maximum_optimizer_iterations(b200reg_t h, int n);/* setMaximumOptimizerIterations */
+int b200reg_gicp_set_epsilon(b200reg_t h, double gicp_epsilon);       /* gicp_epsilon_ (gicp.h:110)    */
+
+/* ---- clouds ----------------------------------------------------------------------------------------- */
+/* setInputTarget (ndt.h:117-122 → init() ndt.h:271-278 → VoxelGridCovariance::filter; gicp.h:156-170):
+ * uploads the cloud and, for NDT, builds the voxel map (mean / regularised inverse covariance) on the GPU. */
+int b200reg_set_input_target(b200reg_t h, const float* base, size_t n, size_t stride_bytes);
+/* setInputSource (pcl::Registration; gicp.h:133-149) */
+int b200reg_set_input_source(b200reg_t h, const float* base, size_t n, size_t stride_bytes);
+/* Same, from a DEVICE buffer of n float4 (x,y,z,ignored) already resident in HBM on the handle's device. */
+int b200reg_set_input_target_device(b200reg_t h, const void* dev_float4, size_t n);
+int b200reg_set_input_source_device(b200reg_t h, const void* dev_float4, size_t n);
+
+/* ---- align ------------------------------------------------------------------------------------------ */
+/* pcl::Registration::align(output, guess) (sm.cpp:353, gbs.cpp:230, apps/align.cpp:27,33) →
+ * computeTransformation (ndt_omp_impl.hpp:80-171 / gicp_omp_impl.hpp:369-515). guess == NULL means identity.
+ * Synchronous: on return final_out (may be NULL) holds getFinalTransformation(). */
+int b200reg_align(b200reg_t h, const float* guess, float* final_out);
+int b200reg_get_final_transformation(b200reg_t h, float* out16);      /* sm.cpp:356; gbs.cpp:244,253   */
+int b200reg_has_converged(b200reg_t h, int* out);                     /* sm.cpp:375                    */
+/* getFitnessScore(max_range) (gbs.cpp:231, sm.cpp:376): mean squared 1-NN distance of the aligned source
+ * to the target, over points with d^2 <= max_range; DBL_MAX if none. */
+int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out);
+/* the `output` cloud of align(): source transformed by the final transformation; out has n_source points */
+int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes);
+
+/* Batched loop-closure sweep (generalises gbs.cpp:187-233 from the arg-min candidate to all candidates):
+ * runs align() on `count` independent handles of ONE device concurrently (one stream each) and returns when
+ * all are done. guesses may be NULL (identity); finals = 16*count floats. */
+int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, float* finals);
+
+/* ---- pcl::VoxelGrid<PointXYZI>::filter (sm.cpp:266-269,311-314,325-328,444-447; gbs.cpp:225-226) ------ */
+/* Centroid downsample of all fields (x,y,z,intensity). intensity_offset_bytes < 0: no intensity field.
+ * out: same point layout as in (stride_bytes), capacity in points; *m = number of output points (ascending
+ * leaf index). If the grid would overflow int32 the input is returned unchanged (PCL behaviour). */
+int b200reg_voxelgrid(int device, const float* in, size_t n, size_t stride_bytes, long intensity_offset_bytes,
+                      float leaf, float* out, size_t out_capacity, size_t* m);
+
+/* ---- introspection (parity tests, roofline accounting) ---------------------------------------------- */
+typedef struct b200reg_stats {
+  int evaluations;        /* computeDerivatives passes of the last align (ndt_omp_impl.hpp:179)          */
+  int iterations;         /* nr_iterations_                                                              */
+  long long hits;         /* (point, voxel) pairs visited in the last evaluation                         */
+  long long hits_total;   /* ... summed over all evaluations of the last align                           */
+  float solve_ms;         /* device time of the last align's solver kernel (CUDA events, handle stream)  */
+  float target_build_ms;  /* device time of the last setInputTarget                                      */
+  int kernel_launches;    /* kernels launched by this handle since creation                              */
+  int grid_ctas, block_threads, index_in_smem;
+  long long n_voxels, n_cells, n_source, n_target;
+} b200reg_stats;
+int b200reg_get_stats(b200reg_t h, b200reg_stats* out);
+
+/* one fused derivative pass (ndt_omp_impl.hpp:179-284) at a given transform T (col-major) with the angle
+ * tables taken at p6[3..5]; out: score, g[6], H[36] row-major. */
+int b200reg_ndt_derivatives(b200reg_t h, const float* T, const double* p6, int compute_hessian, double* score,
+                            double* g6, double* H36);
+/* Hessian-only pass over the radius neighbourhood in f64 (ndt_omp_impl.hpp:538-629) */
+int b200reg_ndt_hessian_radius(b200reg_t h, const float* T, const double* p6, double* H36);
+/* voxel map read-back, voxels with >= 6 points in ascending leaf index (voxel_grid_covariance_omp_impl.hpp:
+ * 282-367). Any pointer may be NULL. mean3/icov9 doubles, centroid3 floats. */
+int b200reg_ndt_num_voxels(b200reg_t h, size_t* out);
+int b200reg_ndt_get_voxels(b200reg_t h, int* leaf_idx, int* npts, double* mean3, double* icov9, float* centroid3);
+/* exact 1-NN of n query points against the target cloud (building block of getFitnessScore / GICP) */
+int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, int* idx, float* d2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REG_H_ */

@@ -1,0 +1,707 @@
+// extern "C" implementation of include/b200reg.h. No CPU fallback: every compute entry point launches CUDA
+// kernels; if no device is present b200reg_create fails.
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/b200reg.h"
+#include "engine.hpp"
+#include "gicp.hpp"
+
+using namespace b200;
+
+struct b200reg_engine {
+  int kind = B200REG_NDT;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+
+  // pcl::Registration parameters
+  double corr_dist = std::sqrt(DBL_MAX);  // PCL default corr_dist_threshold_
+  double euclid_eps = -DBL_MAX;
+  int ransac_iters = 0;
+  NdtConfig ndt;
+  int min_points_per_voxel = 6;           // voxel_grid_covariance_omp.h:204
+  double min_covar_eigvalue_mult = 0.01;  // voxel_grid_covariance_omp.h:205
+  GicpConfig gicp;
+
+  DeviceBuffer<float4> d_target, d_source, d_aligned;
+  PinnedBuffer<float4> staging;
+  size_t n_target = 0, n_source = 0;
+  bool have_target = false, have_source = false;
+  bool map_valid = false, nn_valid = false;
+  float map_resolution = 0;
+
+  VoxelMap map;
+  NnGrid nn;
+  NdtSolver solver;
+  GicpSolver gicp_solver;
+
+  DeviceBuffer<int> nn_idx;
+  DeviceBuffer<float> nn_d2;
+  DeviceBuffer<double> scratch_d;   // >= 64 doubles
+  DeviceBuffer<float> scratch_f;    // >= 16 floats
+  DeviceBuffer<float4> query_buf;
+
+  // results of the last align (row-major)
+  float final_T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  int converged = 0, iterations = 0, evaluations = 0;
+  double trans_probability = 0;
+  long long hits_last = 0, hits_total = 0;
+  float solve_ms = 0, target_build_ms = 0;
+  bool align_pending = false;
+  int other_launches = 0;
+};
+
+namespace {
+
+void set_identity(float* T) {
+  for (int k = 0; k < 16; k++) T[k] = (k % 5 == 0) ? 1.0f : 0.0f;
+}
+void col_to_row(const float* c, float* r) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) r[i * 4 + j] = c[j * 4 + i];
+}
+void row_to_col(const float* r, float* c) {
+  for (int i = 0; i < 4; i++)
+    for (int j = 0; j < 4; j++) c[j * 4 + i] = r[i * 4 + j];
+}
+
+template <typename F>
+int guarded(b200reg_t h, F&& f) {
+  if (!h) return B200REG_ERR_ARG;
+  try {
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) {
+      h->err = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+      return B200REG_ERR_CUDA;
+    }
+    return f();
+  } catch (const CudaError& e) {
+    h->err = e.what();
+    cudaGetLastError();
+    return B200REG_ERR_CUDA;
+  } catch (const std::exception& e) {
+    h->err = e.what();
+    return B200REG_ERR_ARG;
+  }
+}
+
+int fail(b200reg_t h, int code, const char* msg) {
+  h->err = msg;
+  return code;
+}
+
+void ensure_map(b200reg_t h) {
+  if (h->map_valid && h->map_resolution == h->ndt.resolution) return;
+  B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+  bool ok = h->map.build(h->d_target.ptr, h->n_target, h->ndt.resolution, h->min_points_per_voxel,
+                         h->min_covar_eigvalue_mult, h->stream);
+  B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+  B200_CUDA(cudaEventSynchronize(h->ev1));
+  B200_CUDA(cudaEventElapsedTime(&h->target_build_ms, h->ev0, h->ev1));
+  h->map_valid = true;
+  h->map_resolution = h->ndt.resolution;
+  if (!ok) h->err = "voxel grid would overflow int32: leaf size too small for the target cloud (map left empty)";
+}
+
+void ensure_nn(b200reg_t h) {
+  if (h->nn_valid) return;
+  h->nn.build(h->d_target.ptr, h->n_target, h->stream);
+  h->nn_valid = true;
+}
+
+// ---- NDT align: enqueue / complete ------------------------------------------------------------------------
+int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
+  h->converged = 0;
+  set_identity(h->final_T);
+  if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "align: no input target");
+  if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "align: no input source");
+  ensure_map(h);
+  float T[16];
+  if (guess_colmajor) col_to_row(guess_colmajor, T);
+  else set_identity(T);
+  if (h->map.n_voxels == 0) {
+    // no voxel holds >= 6 points: the reference's first solve returns delta_p == 0 → converged, final = guess
+    std::memcpy(h->final_T, T, sizeof(T));
+    h->converged = 1;
+    h->iterations = 0;
+    h->evaluations = 1;
+    h->trans_probability = 0;
+    h->hits_last = h->hits_total = 0;
+    h->align_pending = false;
+    return B200REG_OK;
+  }
+  B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+  h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
+  h->align_pending = true;
+  return B200REG_OK;
+}
+
+int ndt_align_end(b200reg_t h) {
+  if (!h->align_pending) return B200REG_OK;
+  h->align_pending = false;
+  for (int rounds = 0; rounds < 4096; rounds++) {
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    const NdtResult& r = h->solver.result();
+    if (r.error == 100) {
+      // the More-Thuente loop ran (only when step_max <= step_min): f64 radius Hessian (K2), then resume
+      h->scratch_d.ensure(64);
+      ndt_hessian_radius(h->map, h->d_source.ptr, h->n_source, h->ndt, h->solver.control_T(), h->solver.state_jd(),
+                         h->solver.state_hd(), h->scratch_d.ptr, h->stream);
+      ndt_hessian_into_state(h->scratch_d.ptr, h->solver.work(), h->stream);
+      h->other_launches += 2;
+      float dummyT[16];
+      set_identity(dummyT);
+      h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, dummyT, nullptr, 1, 1);
+      continue;
+    }
+    if (r.error != 0) {
+      h->solver.reset_barrier();
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      return fail(h, B200REG_ERR_TIMEOUT, "NDT solver kernel watchdog fired (grid barrier timeout)");
+    }
+    B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+    B200_CUDA(cudaEventSynchronize(h->ev1));
+    B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
+    std::memcpy(h->final_T, r.final_T, sizeof(h->final_T));
+    h->converged = r.converged;
+    h->iterations = r.iterations;
+    h->evaluations = r.evaluations;
+    h->trans_probability = r.trans_probability;
+    h->hits_last = r.hits_last;
+    h->hits_total = r.hits_total;
+    return B200REG_OK;
+  }
+  return fail(h, B200REG_ERR_TIMEOUT, "NDT solver did not finish");
+}
+
+int gicp_align(b200reg_t h, const float* guess_colmajor) {
+  h->converged = 0;
+  set_identity(h->final_T);
+  if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "align: no input target");
+  if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "align: no input source");
+  ensure_nn(h);
+  float T[16];
+  if (guess_colmajor) col_to_row(guess_colmajor, T);
+  else set_identity(T);
+  h->gicp.corr_dist = h->corr_dist;
+  B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+  GicpOutcome out = h->gicp_solver.align(h->nn, h->d_target.ptr, h->n_target, h->d_source.ptr, h->n_source, h->gicp, T,
+                                         h->stream);
+  B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+  B200_CUDA(cudaEventSynchronize(h->ev1));
+  B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
+  std::memcpy(h->final_T, out.final_T, sizeof(h->final_T));
+  h->converged = out.converged;
+  h->iterations = out.iterations;
+  h->evaluations = out.evaluations;
+  return B200REG_OK;
+}
+
+int set_cloud(b200reg_t h, bool target, const float* base, size_t n, size_t stride, const void* dev) {
+  // PCL: empty cloud → PCL_ERROR and the call is ignored (gicp_omp.h:137-141; Registration::setInputTarget)
+  if (n == 0 || (!base && !dev)) return fail(h, B200REG_ERR_ARG, "empty input cloud ignored");
+  if (!dev && stride < 12) return fail(h, B200REG_ERR_ARG, "stride_bytes must be >= 12");
+  DeviceBuffer<float4>& dst = target ? h->d_target : h->d_source;
+  if (dev) {
+    dst.ensure(n);
+    B200_CUDA(cudaMemcpyAsync(dst.ptr, dev, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+  } else {
+    upload_cloud(base, n, stride, dst, h->staging, h->stream);
+    // the staging buffer is reused by the next upload: wait for the copy engine
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+  }
+  if (target) {
+    h->n_target = n;
+    h->have_target = true;
+    h->map_valid = false;
+    h->nn_valid = false;
+    h->gicp_solver.invalidate_target();
+    if (h->kind == B200REG_NDT) ensure_map(h);  // setInputTarget → init() builds the voxel structure eagerly
+  } else {
+    h->n_source = n;
+    h->have_source = true;
+    h->gicp_solver.invalidate_source();
+  }
+  return B200REG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200reg_create(int kind, int device, b200reg_t* out) {
+  if (!out || (kind != B200REG_NDT && kind != B200REG_GICP)) return B200REG_ERR_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) {
+    cudaGetLastError();
+    return B200REG_ERR_CUDA;  // no CPU fallback
+  }
+  b200reg_engine* h = new b200reg_engine();
+  h->kind = kind;
+  h->device = device;
+  try {
+    B200_CUDA(cudaSetDevice(device));
+    B200_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    B200_CUDA(cudaEventCreate(&h->ev0));
+    B200_CUDA(cudaEventCreate(&h->ev1));
+    h->solver.init(device, h->stream);
+    h->gicp_solver.init(device, h->stream);
+    if (kind == B200REG_GICP) {
+      h->corr_dist = 5.0;  // gicp_omp.h:119
+    }
+    h->scratch_d.ensure(64);
+    h->scratch_f.ensure(16);
+  } catch (const std::exception&) {
+    delete h;
+    cudaGetLastError();
+    return B200REG_ERR_CUDA;
+  }
+  *out = h;
+  return B200REG_OK;
+}
+
+int b200reg_destroy(b200reg_t h) {
+  if (!h) return B200REG_ERR_ARG;
+  cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  cudaStream_t s = h->stream;
+  delete h;
+  if (s) cudaStreamDestroy(s);
+  return B200REG_OK;
+}
+
+const char* b200reg_last_error(b200reg_t h) { return h ? h->err.c_str() : "null handle"; }
+
+// ---- setters ---------------------------------------------------------------------------------------------
+int b200reg_set_transformation_epsilon(b200reg_t h, double eps) {
+  if (!h) return B200REG_ERR_ARG;
+  h->ndt.trans_eps = eps;
+  h->gicp.trans_eps = eps;
+  return B200REG_OK;
+}
+int b200reg_set_maximum_iterations(b200reg_t h, int n) {
+  if (!h) return B200REG_ERR_ARG;
+  h->ndt.max_iterations = n;
+  h->gicp.max_iterations = n;
+  return B200REG_OK;
+}
+int b200reg_set_max_correspondence_distance(b200reg_t h, double d) {
+  if (!h) return B200REG_ERR_ARG;
+  h->corr_dist = d;
+  return B200REG_OK;
+}
+int b200reg_set_euclidean_fitness_epsilon(b200reg_t h, double eps) {
+  if (!h) return B200REG_ERR_ARG;
+  h->euclid_eps = eps;
+  return B200REG_OK;
+}
+int b200reg_set_ransac_iterations(b200reg_t h, int n) {
+  if (!h) return B200REG_ERR_ARG;
+  h->ransac_iters = n;
+  return B200REG_OK;
+}
+
+int b200reg_ndt_set_resolution(b200reg_t h, float resolution) {
+  if (!h || h->kind != B200REG_NDT || !(resolution > 0)) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (h->ndt.resolution != resolution) {  // ndt_omp.h:127-137: re-voxelise only when it changes
+      h->ndt.resolution = resolution;
+      if (h->have_target && h->have_source) ensure_map(h);  // reference re-inits `if (input_)`
+    }
+    return (int)B200REG_OK;
+  });
+}
+int b200reg_ndt_set_step_size(b200reg_t h, double step) {
+  if (!h || h->kind != B200REG_NDT) return B200REG_ERR_ARG;
+  h->ndt.step_size = step;
+  return B200REG_OK;
+}
+int b200reg_ndt_set_outlier_ratio(b200reg_t h, double ratio) {
+  if (!h || h->kind != B200REG_NDT) return B200REG_ERR_ARG;
+  h->ndt.outlier_ratio = ratio;
+  return B200REG_OK;
+}
+int b200reg_ndt_set_neighborhood_search_method(b200reg_t h, int m) {
+  if (!h || h->kind != B200REG_NDT || m < 0 || m > 3) return B200REG_ERR_ARG;
+  h->ndt.search_method = m;
+  return B200REG_OK;
+}
+int b200reg_ndt_set_num_threads(b200reg_t h, int) { return h ? B200REG_OK : B200REG_ERR_ARG; }
+int b200reg_ndt_get_transformation_probability(b200reg_t h, double* out) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  *out = h->trans_probability;
+  return B200REG_OK;
+}
+int b200reg_ndt_get_final_num_iteration(b200reg_t h, int* out) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  *out = h->iterations;
+  return B200REG_OK;
+}
+
+int b200reg_gicp_set_rotation_epsilon(b200reg_t h, double eps) {
+  if (!h || h->kind != B200REG_GICP) return B200REG_ERR_ARG;
+  h->gicp.rotation_eps = eps;
+  return B200REG_OK;
+}
+int b200reg_gicp_set_correspondence_randomness(b200reg_t h, int k) {
+  if (!h || h->kind != B200REG_GICP || k < 3 || k > GICP_MAX_K) return B200REG_ERR_ARG;
+  h->gicp.k_correspondences = k;
+  h->gicp_solver.invalidate_target();
+  h->gicp_solver.invalidate_source();
+  return B200REG_OK;
+}
+int b200reg_gicp_set_maximum_optimizer_iterations(b200reg_t h, int n) {
+  if (!h || h->kind != B200REG_GICP) return B200REG_ERR_ARG;
+  h->gicp.max_inner_iterations = n;
+  return B200REG_OK;
+}
+int b200reg_gicp_set_epsilon(b200reg_t h, double e) {
+  if (!h || h->kind != B200REG_GICP) return B200REG_ERR_ARG;
+  h->gicp.gicp_epsilon = e;
+  h->gicp_solver.invalidate_target();
+  h->gicp_solver.invalidate_source();
+  return B200REG_OK;
+}
+
+// ---- clouds ----------------------------------------------------------------------------------------------
+int b200reg_set_input_target(b200reg_t h, const float* base, size_t n, size_t stride_bytes) {
+  return guarded(h, [&]() { return set_cloud(h, true, base, n, stride_bytes, nullptr); });
+}
+int b200reg_set_input_source(b200reg_t h, const float* base, size_t n, size_t stride_bytes) {
+  return guarded(h, [&]() { return set_cloud(h, false, base, n, stride_bytes, nullptr); });
+}
+int b200reg_set_input_target_device(b200reg_t h, const void* dev, size_t n) {
+  return guarded(h, [&]() { return set_cloud(h, true, nullptr, n, 16, dev); });
+}
+int b200reg_set_input_source_device(b200reg_t h, const void* dev, size_t n) {
+  return guarded(h, [&]() { return set_cloud(h, false, nullptr, n, 16, dev); });
+}
+
+// ---- align -----------------------------------------------------------------------------------------------
+int b200reg_align(b200reg_t h, const float* guess, float* final_out) {
+  return guarded(h, [&]() {
+    int rc;
+    if (h->kind == B200REG_NDT) {
+      rc = ndt_align_begin(h, guess);
+      if (rc == B200REG_OK) rc = ndt_align_end(h);
+    } else {
+      rc = gicp_align(h, guess);
+    }
+    if (final_out) row_to_col(h->final_T, final_out);
+    return rc;
+  });
+}
+
+int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, float* finals) {
+  if (!handles || count < 0) return B200REG_ERR_ARG;
+  int worst = B200REG_OK;
+  std::vector<int> rc(count, B200REG_OK);
+  for (int i = 0; i < count; i++) {  // enqueue every NDT solve on its own stream before waiting for any
+    b200reg_t h = handles[i];
+    if (!h) return B200REG_ERR_ARG;
+    if (h->kind != B200REG_NDT) continue;
+    rc[i] = guarded(h, [&]() { return ndt_align_begin(h, guesses ? guesses + 16 * i : nullptr); });
+  }
+  for (int i = 0; i < count; i++) {
+    b200reg_t h = handles[i];
+    if (h->kind == B200REG_NDT) {
+      if (rc[i] == B200REG_OK) rc[i] = guarded(h, [&]() { return ndt_align_end(h); });
+    } else {
+      rc[i] = guarded(h, [&]() { return gicp_align(h, guesses ? guesses + 16 * i : nullptr); });
+    }
+    if (finals) row_to_col(h->final_T, finals + 16 * i);
+    if (rc[i] != B200REG_OK) worst = rc[i];
+  }
+  return worst;
+}
+
+int b200reg_get_final_transformation(b200reg_t h, float* out16) {
+  if (!h || !out16) return B200REG_ERR_ARG;
+  row_to_col(h->final_T, out16);
+  return B200REG_OK;
+}
+int b200reg_has_converged(b200reg_t h, int* out) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  *out = h->converged;
+  return B200REG_OK;
+}
+
+int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "getFitnessScore: no input target");
+    if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "getFitnessScore: no input source");
+    ensure_nn(h);
+    h->nn_idx.ensure(h->n_source);
+    h->nn_d2.ensure(h->n_source);
+    nn1_query(h->nn, h->d_source.ptr, h->n_source, h->final_T, h->nn_idx.ptr, h->nn_d2.ptr, h->stream);
+    double sum = 0;
+    long long cnt = 0;
+    fitness_reduce(h->nn_d2.ptr, h->nn_idx.ptr, h->n_source, max_range, h->scratch_d.ptr, &sum, &cnt, h->stream);
+    h->other_launches += 2;
+    *out = cnt > 0 ? sum / (double)cnt : DBL_MAX;
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes) {
+  if (!h || !out || stride_bytes < 12) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "no input source");
+    h->d_aligned.ensure(h->n_source);
+    B200_CUDA(cudaMemcpyAsync(h->scratch_f.ptr, h->final_T, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    transform_cloud_device(h->d_source.ptr, h->n_source, h->d_aligned.ptr, h->scratch_f.ptr, h->stream);
+    h->other_launches += 1;
+    h->staging.ensure(h->n_source);
+    B200_CUDA(cudaMemcpyAsync(h->staging.ptr, h->d_aligned.ptr, h->n_source * sizeof(float4), cudaMemcpyDeviceToHost,
+                              h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    char* b = reinterpret_cast<char*>(out);
+    for (size_t i = 0; i < h->n_source; i++) {
+      float* f = reinterpret_cast<float*>(b + i * stride_bytes);
+      f[0] = h->staging.ptr[i].x;
+      f[1] = h->staging.ptr[i].y;
+      f[2] = h->staging.ptr[i].z;
+      if (stride_bytes >= 16) f[3] = 1.0f;
+    }
+    return (int)B200REG_OK;
+  });
+}
+
+// ---- VoxelGrid ---------------------------------------------------------------------------------------------
+int b200reg_voxelgrid(int device, const float* in, size_t n, size_t stride_bytes, long intensity_offset_bytes, float leaf,
+                      float* out, size_t out_capacity, size_t* m) {
+  if (!in || !out || !m || stride_bytes < 12 || !(leaf > 0)) return B200REG_ERR_ARG;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lock(mu);
+  try {
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || device < 0 || device >= count) {
+      cudaGetLastError();
+      return B200REG_ERR_CUDA;
+    }
+    B200_CUDA(cudaSetDevice(device));
+    static VoxelGridFilter* filters[64] = {nullptr};
+    static cudaStream_t streams[64] = {nullptr};
+    if (device >= 64) return B200REG_ERR_ARG;
+    if (!filters[device]) {
+      filters[device] = new VoxelGridFilter();
+      B200_CUDA(cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking));
+    }
+    VoxelGridFilter& F = *filters[device];
+    cudaStream_t s = streams[device];
+    *m = 0;
+    if (n == 0) return B200REG_OK;
+    F.in.ensure(n);
+    F.staging.ensure(n);
+    const char* b = reinterpret_cast<const char*>(in);
+    for (size_t i = 0; i < n; i++) {
+      const float* f = reinterpret_cast<const float*>(b + i * stride_bytes);
+      float inten = intensity_offset_bytes >= 0 ? *reinterpret_cast<const float*>(b + i * stride_bytes + intensity_offset_bytes)
+                                                : 0.0f;
+      F.staging.ptr[i] = make_float4(f[0], f[1], f[2], inten);
+    }
+    B200_CUDA(cudaMemcpyAsync(F.in.ptr, F.staging.ptr, n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    long long cnt = F.filter_device(F.in.ptr, n, leaf, s);
+    char* ob = reinterpret_cast<char*>(out);
+    if (cnt < 0) {  // overflow guard: PCL returns the input cloud unchanged
+      size_t k = std::min(n, out_capacity);
+      for (size_t i = 0; i < k; i++) std::memcpy(ob + i * stride_bytes, b + i * stride_bytes, stride_bytes);
+      *m = n;
+      return B200REG_OK;
+    }
+    size_t mm = (size_t)cnt;
+    F.staging.ensure(std::max(mm, n));
+    B200_CUDA(cudaMemcpyAsync(F.staging.ptr, F.out.ptr, mm * sizeof(float4), cudaMemcpyDeviceToHost, s));
+    B200_CUDA(cudaStreamSynchronize(s));
+    size_t k = std::min(mm, out_capacity);
+    for (size_t i = 0; i < k; i++) {
+      float* f = reinterpret_cast<float*>(ob + i * stride_bytes);
+      const float4 v = F.staging.ptr[i];
+      f[0] = v.x;
+      f[1] = v.y;
+      f[2] = v.z;
+      if (intensity_offset_bytes >= 0) *reinterpret_cast<float*>(ob + i * stride_bytes + intensity_offset_bytes) = v.w;
+      if (stride_bytes >= 32 || (stride_bytes >= 16 && intensity_offset_bytes != 12)) f[3] = 1.0f;
+    }
+    *m = mm;
+    return B200REG_OK;
+  } catch (const std::exception&) {
+    cudaGetLastError();
+    return B200REG_ERR_CUDA;
+  }
+}
+
+// ---- introspection -----------------------------------------------------------------------------------------
+int b200reg_get_stats(b200reg_t h, b200reg_stats* out) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  std::memset(out, 0, sizeof(*out));
+  out->evaluations = h->evaluations;
+  out->iterations = h->iterations;
+  out->hits = h->hits_last;
+  out->hits_total = h->hits_total;
+  out->solve_ms = h->solve_ms;
+  out->target_build_ms = h->target_build_ms;
+  out->kernel_launches = h->solver.launches + h->map.launches + h->nn.launches + h->gicp_solver.launches + h->other_launches;
+  out->grid_ctas = h->solver.grid_ctas();
+  out->block_threads = h->solver.block_threads();
+  out->index_in_smem = h->solver.index_in_smem();
+  out->n_voxels = (long long)h->map.n_voxels;
+  out->n_cells = h->map.geom.n_cells;
+  out->n_source = (long long)h->n_source;
+  out->n_target = (long long)h->n_target;
+  return B200REG_OK;
+}
+
+int b200reg_ndt_derivatives(b200reg_t h, const float* T, const double* p6, int compute_hessian, double* score, double* g6,
+                            double* H36) {
+  if (!h || h->kind != B200REG_NDT || !T || !p6) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
+    if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "no input source");
+    ensure_map(h);
+    if (h->map.n_voxels == 0) {
+      if (score) *score = 0;
+      if (g6) std::memset(g6, 0, 6 * sizeof(double));
+      if (H36) std::memset(H36, 0, 36 * sizeof(double));
+      h->hits_last = 0;
+      return (int)B200REG_OK;
+    }
+    float Tr[16];
+    col_to_row(T, Tr);
+    B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+    h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_DERIVATIVES, Tr, p6, compute_hessian, 0);
+    B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
+    const NdtResult& r = h->solver.result();
+    if (r.error != 0) {
+      h->solver.reset_barrier();
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      return fail(h, B200REG_ERR_TIMEOUT, "NDT derivative kernel watchdog fired");
+    }
+    if (score) *score = r.score;
+    if (g6) std::memcpy(g6, r.g, sizeof(r.g));
+    if (H36) std::memcpy(H36, r.H, sizeof(r.H));
+    h->hits_last = r.hits_last;
+    h->hits_total = r.hits_total;
+    h->evaluations = r.evaluations;
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_ndt_hessian_radius(b200reg_t h, const float* T, const double* p6, double* H36) {
+  if (!h || h->kind != B200REG_NDT || !T || !p6 || !H36) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
+    if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "no input source");
+    ensure_map(h);
+    std::memset(H36, 0, 36 * sizeof(double));
+    if (h->map.n_voxels == 0) return (int)B200REG_OK;
+    float Tr[16], ja[24], ha[45];
+    double tabs[69];
+    col_to_row(T, Tr);
+    angle_tables(p6, ja, ha, tabs, tabs + 24);
+    h->scratch_d.ensure(128);
+    B200_CUDA(cudaMemcpyAsync(h->scratch_d.ptr + 32, tabs, sizeof(tabs), cudaMemcpyHostToDevice, h->stream));
+    B200_CUDA(cudaMemcpyAsync(h->scratch_f.ptr, Tr, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    ndt_hessian_radius(h->map, h->d_source.ptr, h->n_source, h->ndt, h->scratch_f.ptr, h->scratch_d.ptr + 32,
+                       h->scratch_d.ptr + 56, h->scratch_d.ptr, h->stream);
+    h->other_launches += 1;
+    double up[21];
+    B200_CUDA(cudaMemcpyAsync(up, h->scratch_d.ptr, sizeof(up), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < 6; i++)
+      for (int j = i; j < 6; j++) H36[i * 6 + j] = H36[j * 6 + i] = up[tri_index(i, j)];
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_ndt_calculate_score(b200reg_t h, const float* base, size_t n, size_t stride_bytes, double* out) {
+  if (!h || h->kind != B200REG_NDT || !base || !out || stride_bytes < 12) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
+    ensure_map(h);
+    *out = 0;
+    if (n == 0 || h->map.n_voxels == 0) return (int)B200REG_OK;
+    upload_cloud(base, n, stride_bytes, h->query_buf, h->staging, h->stream);
+    ndt_score(h->map, h->query_buf.ptr, n, h->ndt, h->scratch_d.ptr, h->stream);
+    h->other_launches += 1;
+    double s = 0;
+    B200_CUDA(cudaMemcpyAsync(&s, h->scratch_d.ptr, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    *out = s / (double)n;
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_ndt_num_voxels(b200reg_t h, size_t* out) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
+    ensure_map(h);
+    *out = h->map.n_voxels;
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_ndt_get_voxels(b200reg_t h, int* leaf_idx, int* npts, double* mean3, double* icov9, float* centroid3) {
+  if (!h) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
+    ensure_map(h);
+    const size_t V = h->map.n_voxels;
+    if (V == 0) return (int)B200REG_OK;
+    std::vector<VoxelRecord> rec(V);
+    std::vector<float4> cen(V);
+    B200_CUDA(cudaMemcpyAsync(rec.data(), h->map.records.ptr, V * sizeof(VoxelRecord), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaMemcpyAsync(cen.data(), h->map.centroids.ptr, V * sizeof(float4), cudaMemcpyDeviceToHost, h->stream));
+    if (npts) B200_CUDA(cudaMemcpyAsync(npts, h->map.npts.ptr, V * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (icov9)
+      B200_CUDA(cudaMemcpyAsync(icov9, h->map.icov_d.ptr, V * 9 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t v = 0; v < V; v++) {
+      if (mean3) {
+        mean3[3 * v + 0] = rec[v].mx;
+        mean3[3 * v + 1] = rec[v].my;
+        mean3[3 * v + 2] = rec[v].mz;
+      }
+      if (centroid3) {
+        centroid3[3 * v + 0] = cen[v].x;
+        centroid3[3 * v + 1] = cen[v].y;
+        centroid3[3 * v + 2] = cen[v].z;
+      }
+      if (leaf_idx) std::memcpy(&leaf_idx[v], &cen[v].w, sizeof(int));
+    }
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, int* idx, float* d2) {
+  if (!h || !base || !idx || !d2 || stride_bytes < 12) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
+    if (n == 0) return (int)B200REG_OK;
+    ensure_nn(h);
+    upload_cloud(base, n, stride_bytes, h->query_buf, h->staging, h->stream);
+    h->nn_idx.ensure(n);
+    h->nn_d2.ensure(n);
+    nn1_query(h->nn, h->query_buf.ptr, n, nullptr, h->nn_idx.ptr, h->nn_d2.ptr, h->stream);
+    h->other_launches += 1;
+    B200_CUDA(cudaMemcpyAsync(idx, h->nn_idx.ptr, n * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaMemcpyAsync(d2, h->nn_d2.ptr, n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    return (int)B200REG_OK;
+  });
+}
+
+}  // extern "C"

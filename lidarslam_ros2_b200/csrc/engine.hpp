@@ -1,0 +1,214 @@
+// Host-side engine classes behind the C-ABI (include/b200reg.h). C++17, CUDA runtime only — no torch types.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "ndt_math.cuh"
+
+namespace b200 {
+
+// ---- RAII device / pinned buffers -------------------------------------------------------------------
+template <typename T>
+struct DeviceBuffer {
+  T* ptr = nullptr;
+  size_t cap = 0;
+  DeviceBuffer() = default;
+  DeviceBuffer(const DeviceBuffer&) = delete;
+  DeviceBuffer& operator=(const DeviceBuffer&) = delete;
+  ~DeviceBuffer() { release(); }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+  // grow-only; contents are NOT preserved
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    release();
+    size_t want = n + n / 8 + 64;
+    B200_CUDA(cudaMalloc(&ptr, want * sizeof(T)));
+    cap = want;
+  }
+};
+
+template <typename T>
+struct PinnedBuffer {
+  T* ptr = nullptr;
+  size_t cap = 0;
+  PinnedBuffer() = default;
+  PinnedBuffer(const PinnedBuffer&) = delete;
+  PinnedBuffer& operator=(const PinnedBuffer&) = delete;
+  ~PinnedBuffer() {
+    if (ptr) cudaFreeHost(ptr);
+  }
+  void ensure(size_t n) {
+    if (n <= cap) return;
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    size_t want = n + n / 8 + 64;
+    B200_CUDA(cudaMallocHost(&ptr, want * sizeof(T)));
+    cap = want;
+  }
+};
+
+// ---- rank index (occupancy bitmap + popcount prefix), see common.cuh -----------------------------------
+struct RankIndexScratch {
+  DeviceBuffer<unsigned> block_sums;
+  DeviceBuffer<unsigned> total;  // 1 element
+};
+// zero-fills table[0..n_words)
+void rank_index_clear(RankWord* table, int n_words, cudaStream_t s);
+// fills .prefix from .bits; returns (synchronously) the number of set bits
+unsigned rank_index_scan(RankWord* table, int n_words, RankIndexScratch& scratch, cudaStream_t s);
+
+// min/max of the finite points of a float4 cloud → host (synchronises the stream). Returns #finite points.
+struct Bounds {
+  float mn[3], mx[3];
+  bool any;
+};
+Bounds cloud_bounds(const float4* pts, size_t n, unsigned* d_scratch8, cudaStream_t s);
+// PCL grid geometry from bounds (voxel_grid_covariance_omp_impl.hpp:67-103); returns false on int32 overflow
+bool make_grid_geom(const Bounds& b, float leaf, GridGeom& g);
+
+// upload an arbitrary-stride host cloud into a float4 device buffer (w = 1)
+void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst,
+                  PinnedBuffer<float4>& staging, cudaStream_t s);
+
+// ---- NDT voxel map (K3) -------------------------------------------------------------------------------
+struct VoxelMap {
+  GridGeom geom{};
+  size_t n_voxels = 0;    // voxels with >= min_points (valid), ascending leaf index
+  size_t n_occupied = 0;  // all occupied leaves
+  DeviceBuffer<RankWord> index;      // rank index over VALID voxels (what the solver probes)
+  DeviceBuffer<VoxelRecord> records; // n_voxels
+  DeviceBuffer<double> icov_d;       // n_voxels x 9 (f64 inverse covariance, for the f64 paths)
+  DeviceBuffer<float4> centroids;    // n_voxels: f32 centroid xyz, w = leaf index (int bits)
+  DeviceBuffer<int> npts;            // n_voxels
+  // build scratch
+  DeviceBuffer<RankWord> index_all;
+  DeviceBuffer<int> cell_of_point;
+  DeviceBuffer<double> acc;          // n_occupied x 10
+  DeviceBuffer<int> leaf_of_rank;
+  DeviceBuffer<VoxelRecord> tmp_records;
+  DeviceBuffer<double> tmp_icov;
+  DeviceBuffer<float4> tmp_centroids;
+  DeviceBuffer<int> tmp_npts;
+  DeviceBuffer<unsigned char> tmp_valid;
+  DeviceBuffer<unsigned> bounds_scratch;
+  RankIndexScratch scan_scratch;
+  int launches = 0;
+
+  // returns false if the grid overflows int32 (map left empty, like voxel_grid_covariance_omp_impl.hpp:79-84)
+  bool build(const float4* pts, size_t n, float leaf, int min_points_per_voxel, double min_covar_eigvalue_mult,
+             cudaStream_t s);
+};
+
+// ---- exact nearest-neighbour grid over a cloud (K8 fitness, GICP) ---------------------------------------
+struct NnGrid {
+  float h = 0, inv_h = 0;
+  float origin[3] = {0, 0, 0};
+  int dims[3] = {0, 0, 0};
+  long long n_cells = 0;
+  int n_words = 0;
+  size_t n_points = 0, n_cells_occupied = 0;
+  DeviceBuffer<RankWord> index;
+  DeviceBuffer<unsigned> cell_start;  // n_cells_occupied + 1
+  DeviceBuffer<float4> sorted;        // xyz + original index (int bits) in w
+  DeviceBuffer<int> cell_of_point;
+  DeviceBuffer<unsigned> cursor;
+  DeviceBuffer<unsigned> bounds_scratch;
+  RankIndexScratch scan_scratch;
+  DeviceBuffer<unsigned> scan_tmp;
+  int launches = 0;
+  bool valid = false;
+  void build(const float4* pts, size_t n, cudaStream_t s);
+};
+// 1-NN of n queries (optionally transformed by T, 3x4 row-major; nullptr = none). d2 accumulated in f32 as
+// ((dx*dx + dy*dy) + dz*dz); ties → lower index. idx = -1 when the target is empty.
+void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float* T12_host, int* d_idx, float* d_d2,
+               cudaStream_t s);
+// mean of d2 over queries with d2 <= max_range → (sum, count) on device, returned to host (synchronises)
+void fitness_reduce(const float* d_d2, const int* d_idx, size_t n, double max_range, double* d_scratch2, double* sum,
+                    long long* count, cudaStream_t s);
+
+// ---- NDT solver (K1 fused derivative kernel inside a persistent cooperative Newton loop) ----------------
+struct NdtSolverWork;  // device-side work area, defined in ndt_solver.cu
+
+struct NdtResult {
+  float final_T[16];  // row-major 4x4
+  double score;
+  double trans_probability;
+  double g[6];
+  double H[36];
+  long long hits_last, hits_total;
+  int converged, iterations, evaluations, error;
+};
+
+struct NdtConfig {
+  float resolution = 1.0f;
+  double step_size = 0.1, outlier_ratio = 0.55, trans_eps = 0.1;
+  int max_iterations = 35;
+  int search_method = 2;  // DIRECT7
+};
+
+enum NdtMode : int { NDT_MODE_ALIGN = 0, NDT_MODE_DERIVATIVES = 1, NDT_MODE_HESSIAN_RADIUS = 2, NDT_MODE_SCORE = 3 };
+
+class NdtSolver {
+ public:
+  NdtSolver() = default;
+  ~NdtSolver();
+  void init(int device, cudaStream_t s);
+  // enqueue one solver launch on the stream; result lands in pinned host memory after the stream syncs
+  // resume = 1 continues a solve that left the kernel for a K2 (radius Hessian) pass
+  void launch(const VoxelMap& map, const float4* src, size_t n_src, const NdtConfig& cfg, int mode,
+              const float* T_rowmajor16, const double* p6, int compute_hessian, int resume = 0);
+  NdtSolverWork* work() const { return d_work_; }
+  // device addresses of the controller's f64 angle tables / current transform (inputs of the K2 pass)
+  const double* state_jd() const;
+  const double* state_hd() const;
+  const float* control_T() const;
+  const NdtResult& result() const { return *h_result_; }
+  int grid_ctas() const { return grid_; }
+  int block_threads() const { return block_; }
+  int index_in_smem() const { return index_in_smem_; }
+  int launches = 0;
+  void reset_barrier();
+
+ private:
+  int device_ = 0;
+  cudaStream_t stream_ = nullptr;
+  int sm_count_ = 0;
+  int grid_ = 0, block_ = 0, index_in_smem_ = 0;
+  int max_smem_optin_ = 0;
+  NdtSolverWork* d_work_ = nullptr;
+  NdtResult* h_result_ = nullptr;  // pinned
+};
+
+// off-hot-path f64 kernels (ndt_aux.cu)
+// d_T12: DEVICE pointer to the 3x4 row-major transform applied to src
+void ndt_hessian_radius(const VoxelMap& map, const float4* src, size_t n, const NdtConfig& cfg, const float* d_T12,
+                        const double* d_jd, const double* d_hd, double* d_out21, cudaStream_t s);
+void ndt_hessian_into_state(const double* d_upper21, NdtSolverWork* work, cudaStream_t s);
+void ndt_score(const VoxelMap& map, const float4* cloud, size_t n, const NdtConfig& cfg, double* d_out1, cudaStream_t s);
+void transform_cloud_device(const float4* in, size_t n, float4* out, const float* d_T12, cudaStream_t s);
+
+// ---- VoxelGrid downsample (K4) --------------------------------------------------------------------------
+struct VoxelGridFilter {
+  DeviceBuffer<float4> in;   // xyz + intensity
+  DeviceBuffer<float4> out;
+  DeviceBuffer<RankWord> index;
+  DeviceBuffer<int> cell_of_point;
+  DeviceBuffer<double> acc;  // n_vox x 5
+  DeviceBuffer<unsigned> bounds_scratch;
+  RankIndexScratch scan_scratch;
+  PinnedBuffer<float4> staging;
+  int launches = 0;
+  // device-resident core: returns number of output points, or -1 on grid overflow (output = input)
+  long long filter_device(const float4* d_in, size_t n, float leaf, cudaStream_t s);
+};
+
+}  // namespace b200

@@ -1,0 +1,105 @@
+// Device-side structures shared by the NDT solver kernels (ndt_solver.cu, ndt_aux.cu).
+#pragma once
+#include "common.cuh"
+#include "engine.hpp"
+
+namespace b200 {
+
+constexpr int NDT_MAX_CTAS = 148 * 8;
+
+enum EvalMode : int {
+  EVAL_DERIV = 0,        // fused derivative pass (K1)
+  EVAL_DONE = 1,         // solver finished, result written
+  EVAL_NEED_HESSIAN = 2  // leave the persistent kernel: host runs the f64 radius-Hessian pass (K2) and resumes
+};
+
+enum SolverPhase : int { PH_INITIAL = 0, PH_LS_FIRST = 1, PH_LS_ITER = 2, PH_LS_HESSIAN = 3 };
+
+// what every CTA needs for one evaluation round; written by the controller (or by the host for round 0)
+struct NdtControl {
+  float T[12];     // 3x4 row-major transform applied to the source points
+  float jang[24];  // 8 x 3 f32 angle-Jacobian table   (ndt_omp_impl.hpp:337-345)
+  float hang[45];  // 15 x 3 f32 angle-Hessian table    (ndt_omp_impl.hpp:371-391)
+  int mode;        // EvalMode
+  int compute_hessian;
+  int pad[2];
+};
+constexpr int NDT_CONTROL_WORDS = sizeof(NdtControl) / 4;
+
+// controller state (lives in global memory: a different CTA may run the controller every round)
+struct NdtState {
+  double p[6], score, g[6], H[36];
+  double dir[6], x_t[6];
+  double jd[24], hd[45];  // f64 angle tables at x_t, consumed by the K2 pass
+  double phi_0, d_phi_0, a_l, f_l, g_l, a_u, f_u, g_u, a_t;
+  float final_T[16];
+  long long hits_last, hits_total;
+  int interval_converged, open_interval, step_iterations;
+  int phase, nr_iterations, evaluations, converged;
+};
+
+struct NdtSolverWork {
+  unsigned arrive;
+  unsigned gen;
+  unsigned error;
+  unsigned pad;
+  NdtControl control;
+  NdtState state;
+  NdtResult result;
+  double partials[NDT_MAX_CTAS][SLOT_COUNT];
+};
+
+struct NdtLaunch {
+  const float4* src;
+  const RankWord* index;
+  const VoxelRecord* records;
+  const double* icov_d;
+  const float4* centroids;
+  NdtSolverWork* work;
+  GridGeom geom;
+  int n_src;
+  int n_voxels;
+  int search_method;
+  int mode;    // NdtMode
+  int resume;  // 1: state/control already in work (after a K2 pass); first round skips the evaluation
+  int index_in_smem;
+  int max_iterations;
+  float resolution;
+  float radius2;  // (float)(resolution * resolution) in double, the FLANN radius of KDTREE mode
+  double d1, d2, d3;
+  double step_size, trans_eps;
+  double p0[6];
+  float init_final[16];
+  NdtControl init;
+};
+
+// ---- rank-index probe ----------------------------------------------------------------------------------
+// returns the record index of the voxel at absolute cell coordinates (ci, cj, ck), or -1
+// (VoxelGridCovariance::getNeighborhoodAtPoint, voxel_grid_covariance_omp_impl.hpp:382-399)
+template <bool STAGED>
+__device__ __forceinline__ int probe_cell(const GridGeom& g, const RankWord* __restrict__ gidx,
+                                          const RankWord* __restrict__ sidx, int ci, int cj, int ck) {
+  if (ci < g.min_b[0] || ci > g.max_b[0] || cj < g.min_b[1] || cj > g.max_b[1] || ck < g.min_b[2] || ck > g.max_b[2])
+    return -1;
+  const int lin = (ci - g.min_b[0]) + (cj - g.min_b[1]) * g.mul[1] + (ck - g.min_b[2]) * g.mul[2];
+  uint2 w;
+  if (STAGED) w = *reinterpret_cast<const uint2*>(sidx + (lin >> 5));
+  else w = __ldg(reinterpret_cast<const uint2*>(gidx + (lin >> 5)));
+  const unsigned bit = lin & 31;
+  if (!((w.x >> bit) & 1u)) return -1;
+  return (int)(w.y + __popc(w.x & ((1u << bit) - 1u)));
+}
+
+__device__ __forceinline__ float3 transform_point(const float* T, float4 p) {
+  // ((T0*x + T1*y) + T2*z) + T3, un-fused like pcl::transformPointCloud's float arithmetic
+  float3 r;
+  r.x = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], p.x), __fmul_rn(T[1], p.y)), __fmul_rn(T[2], p.z)), T[3]);
+  r.y = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], p.x), __fmul_rn(T[5], p.y)), __fmul_rn(T[6], p.z)), T[7]);
+  r.z = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], p.x), __fmul_rn(T[9], p.y)), __fmul_rn(T[10], p.z)), T[11]);
+  return r;
+}
+
+// lookup cell of a transformed point: floor(x / leaf) with an IEEE division (impl.hpp:379-381)
+__device__ __forceinline__ int lookup_cell(float x, float leaf) { return (int)floorf(__fdiv_rn(x, leaf)); }
+
+}  // namespace b200

@@ -1,0 +1,286 @@
+// K8 — exact nearest neighbour over the target cloud on a uniform cell grid (rank index + cell lists), and the
+// fitness reduction. Replaces pcl::KdTreeFLANN::nearestKSearch(k=1) as used by
+// pcl::Registration::getFitnessScore (called at graph_based_slam_component.cpp:231, scanmatcher_component.cpp:376,
+// apps/align.cpp:37) and by GICP's searchForNeighbors (gicp_omp.h:340-347).
+//
+// Exactness: cells are visited in Chebyshev rings around the query's cell; after ring r every unvisited point is at
+// least r*h away, so the search stops as soon as best_d2 <= (r*h)^2 (with a conservative float margin). Squared
+// distances are accumulated in f32 exactly like FLANN's L2_Simple, ((dx*dx + dy*dy) + dz*dz), un-fused; ties go to
+// the lower point index.
+#include <cfloat>
+#include <cmath>
+
+#include "engine.hpp"
+
+namespace b200 {
+
+namespace {
+
+__device__ __forceinline__ unsigned rank_of(const RankWord* __restrict__ table, int cell) {
+  RankWord w = table[cell >> 5];
+  return w.prefix + __popc(w.bits & ((1u << (cell & 31)) - 1u));
+}
+
+struct NnGeom {
+  float origin[3];
+  float h, inv_h;
+  int dims[3];
+};
+
+__device__ __forceinline__ int nn_cell_coord(float v, float o, float inv_h, int dim) {
+  int c = (int)floorf((v - o) * inv_h);
+  return max(0, min(dim - 1, c));
+}
+
+__global__ void __launch_bounds__(256) nn_mark_kernel(const float4* __restrict__ pts, size_t n, NnGeom g, RankWord* table,
+                                                      int* cell_of_point) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pts[i];
+  int cell = -1;
+  if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+    int ix = nn_cell_coord(p.x, g.origin[0], g.inv_h, g.dims[0]);
+    int iy = nn_cell_coord(p.y, g.origin[1], g.inv_h, g.dims[1]);
+    int iz = nn_cell_coord(p.z, g.origin[2], g.inv_h, g.dims[2]);
+    cell = ix + g.dims[0] * (iy + g.dims[1] * iz);
+    atomicOr(&table[cell >> 5].bits, 1u << (cell & 31));
+  }
+  cell_of_point[i] = cell;
+}
+
+__global__ void __launch_bounds__(256) nn_count_kernel(size_t n, const int* __restrict__ cell_of_point,
+                                                       const RankWord* __restrict__ table, unsigned* counts) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cell = cell_of_point[i];
+  if (cell < 0) return;
+  atomicAdd(&counts[rank_of(table, cell)], 1u);
+}
+
+__global__ void __launch_bounds__(256) nn_scatter_kernel(const float4* __restrict__ pts, size_t n,
+                                                         const int* __restrict__ cell_of_point,
+                                                         const RankWord* __restrict__ table,
+                                                         const unsigned* __restrict__ cell_start, unsigned* cursor,
+                                                         float4* sorted) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int cell = cell_of_point[i];
+  if (cell < 0) return;
+  unsigned r = rank_of(table, cell);
+  unsigned pos = cell_start[r] + atomicAdd(&cursor[r], 1u);
+  float4 p = pts[i];
+  sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
+}
+
+// exclusive scan of a u32 array (in place), n + 1 outputs (last = total). Single block; n is "occupied cells".
+__global__ void __launch_bounds__(1024) scan_u32_kernel(unsigned* data, size_t n) {
+  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned carry_s;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (size_t base = 0; base < n; base += 1024) {
+    size_t i = base + threadIdx.x;
+    unsigned v = (i < n) ? data[i] : 0u;
+    unsigned incl = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+      if (lane >= d) incl += t;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    unsigned off = 0;
+    for (int w = 0; w < warp; w++) off += warp_tot[w];
+    unsigned carry = carry_s;
+    if (i < n) data[i] = carry + off + incl - v;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + off + incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) data[n] = carry_s;
+}
+
+struct NnQueryParams {
+  const RankWord* index;
+  const unsigned* cell_start;
+  const float4* sorted;
+  NnGeom g;
+  float T[12];
+  int has_T;
+};
+
+__global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4* __restrict__ queries, size_t n, int* out_idx,
+                                                  float* out_d2) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 q4 = queries[i];
+  float qx = q4.x, qy = q4.y, qz = q4.z;
+  if (P.has_T) {  // same un-fused float transform as the solver / pcl::transformPointCloud
+    const float* T = P.T;
+    float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], qx), __fmul_rn(T[1], qy)), __fmul_rn(T[2], qz)), T[3]);
+    float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], qx), __fmul_rn(T[5], qy)), __fmul_rn(T[6], qz)), T[7]);
+    float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], qx), __fmul_rn(T[9], qy)), __fmul_rn(T[10], qz)), T[11]);
+    qx = tx; qy = ty; qz = tz;
+  }
+  const NnGeom& g = P.g;
+  const int cx = nn_cell_coord(qx, g.origin[0], g.inv_h, g.dims[0]);
+  const int cy = nn_cell_coord(qy, g.origin[1], g.inv_h, g.dims[1]);
+  const int cz = nn_cell_coord(qz, g.origin[2], g.inv_h, g.dims[2]);
+  float best = FLT_MAX;
+  int best_i = -1;
+  const int max_r = max(g.dims[0], max(g.dims[1], g.dims[2]));
+  for (int r = 0; r <= max_r; r++) {
+    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dims[2] - 1);
+    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dims[1] - 1);
+    for (int z = z0; z <= z1; z++) {
+      const bool zface = (z == cz - r) || (z == cz + r);
+      for (int y = y0; y <= y1; y++) {
+        const bool yface = (y == cy - r) || (y == cy + r);
+        const int step = (zface || yface || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
+        for (int x = cx - r; x <= cx + r; x += step) {
+          if (x < 0 || x >= g.dims[0]) continue;
+          const int cell = x + g.dims[0] * (y + g.dims[1] * z);
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(P.index + (cell >> 5)));
+          const unsigned bit = cell & 31;
+          if (!((w.x >> bit) & 1u)) continue;
+          const unsigned rk = w.y + __popc(w.x & ((1u << bit) - 1u));
+          const unsigned s = __ldg(P.cell_start + rk), e = __ldg(P.cell_start + rk + 1);
+          for (unsigned k = s; k < e; k++) {
+            const float4 t = __ldg(P.sorted + k);
+            const float dx = __fsub_rn(qx, t.x), dy = __fsub_rn(qy, t.y), dz = __fsub_rn(qz, t.z);
+            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+            const int ti = __float_as_int(t.w);
+            if (d2 < best || (d2 == best && ti < best_i)) {
+              best = d2;
+              best_i = ti;
+            }
+          }
+        }
+      }
+    }
+    // after ring r every unvisited point is >= r*h away
+    const float bound = (float)r * g.h;
+    if (best_i >= 0 && best <= bound * bound * 0.99999f) break;
+  }
+  out_idx[i] = best_i;
+  out_d2[i] = best;
+}
+
+__global__ void __launch_bounds__(256) fitness_kernel(const float* __restrict__ d2, const int* __restrict__ idx, size_t n,
+                                                      double max_range, double* out2) {
+  double s = 0, c = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    if (idx[i] < 0) continue;
+    double d = (double)d2[i];
+    if (d <= max_range) {
+      s += d;
+      c += 1.0;
+    }
+  }
+#pragma unroll
+  for (int k = 16; k > 0; k >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, k);
+    c += __shfl_xor_sync(0xffffffffu, c, k);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicAdd(out2, s);
+    atomicAdd(out2 + 1, c);
+  }
+}
+
+}  // namespace
+
+void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
+  valid = false;
+  n_points = n;
+  n_cells_occupied = 0;
+  if (n == 0) return;
+  bounds_scratch.ensure(8);
+  Bounds b = cloud_bounds(pts, n, bounds_scratch.ptr, s);
+  launches += 1;
+  if (!b.any) return;
+  double ext[3];
+  for (int a = 0; a < 3; a++) {
+    origin[a] = b.mn[a];
+    ext[a] = std::max(1e-3, (double)b.mx[a] - (double)b.mn[a]);
+  }
+  double vol = ext[0] * ext[1] * ext[2];
+  double hh = std::cbrt(vol / (4.0 * (double)n));
+  hh = std::max(hh, 1e-3);
+  for (;;) {  // keep the cell count below 2^28
+    double cells = 1;
+    for (int a = 0; a < 3; a++) cells *= std::floor(ext[a] / hh) + 1;
+    if (cells <= 268435456.0) break;
+    hh *= 1.26;
+  }
+  h = (float)hh;
+  inv_h = 1.0f / h;
+  n_cells = 1;
+  for (int a = 0; a < 3; a++) {
+    dims[a] = (int)std::floor(ext[a] / hh) + 1;
+    n_cells *= dims[a];
+  }
+  n_words = (int)((n_cells + 31) / 32);
+  index.ensure((size_t)n_words);
+  cell_of_point.ensure(n);
+  rank_index_clear(index.ptr, n_words, s);
+  NnGeom g;
+  for (int a = 0; a < 3; a++) {
+    g.origin[a] = origin[a];
+    g.dims[a] = dims[a];
+  }
+  g.h = h;
+  g.inv_h = inv_h;
+  const int blocks = (int)((n + 255) / 256);
+  nn_mark_kernel<<<blocks, 256, 0, s>>>(pts, n, g, index.ptr, cell_of_point.ptr);
+  n_cells_occupied = rank_index_scan(index.ptr, n_words, scan_scratch, s);
+  launches += 4;
+  if (n_cells_occupied == 0) return;
+  cell_start.ensure(n_cells_occupied + 1);
+  cursor.ensure(n_cells_occupied);
+  sorted.ensure(n);
+  B200_CUDA(cudaMemsetAsync(cell_start.ptr, 0, sizeof(unsigned) * (n_cells_occupied + 1), s));
+  B200_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned) * n_cells_occupied, s));
+  nn_count_kernel<<<blocks, 256, 0, s>>>(n, cell_of_point.ptr, index.ptr, cell_start.ptr);
+  scan_u32_kernel<<<1, 1024, 0, s>>>(cell_start.ptr, n_cells_occupied);
+  nn_scatter_kernel<<<blocks, 256, 0, s>>>(pts, n, cell_of_point.ptr, index.ptr, cell_start.ptr, cursor.ptr, sorted.ptr);
+  launches += 3;
+  B200_CUDA(cudaGetLastError());
+  valid = true;
+}
+
+void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float* T12_host, int* d_idx, float* d_d2,
+               cudaStream_t s) {
+  if (n == 0) return;
+  NnQueryParams P;
+  P.index = grid.index.ptr;
+  P.cell_start = grid.cell_start.ptr;
+  P.sorted = grid.sorted.ptr;
+  for (int a = 0; a < 3; a++) {
+    P.g.origin[a] = grid.origin[a];
+    P.g.dims[a] = grid.dims[a];
+  }
+  P.g.h = grid.h;
+  P.g.inv_h = grid.inv_h;
+  P.has_T = T12_host ? 1 : 0;
+  for (int k = 0; k < 12; k++) P.T[k] = T12_host ? T12_host[k] : 0.f;
+  const int blocks = (int)((n + 127) / 128);
+  nn1_kernel<<<blocks, 128, 0, s>>>(P, queries, n, d_idx, d_d2);
+  B200_CUDA(cudaGetLastError());
+}
+
+void fitness_reduce(const float* d_d2, const int* d_idx, size_t n, double max_range, double* d_scratch2, double* sum,
+                    long long* count, cudaStream_t s) {
+  B200_CUDA(cudaMemsetAsync(d_scratch2, 0, 2 * sizeof(double), s));
+  int blocks = (int)std::min<size_t>((n + 255) / 256, 148 * 4);
+  if (blocks < 1) blocks = 1;
+  fitness_kernel<<<blocks, 256, 0, s>>>(d_d2, d_idx, n, max_range, d_scratch2);
+  double res[2];
+  B200_CUDA(cudaMemcpyAsync(res, d_scratch2, sizeof(res), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  *sum = res[0];
+  *count = (long long)(res[1] + 0.5);
+}
+
+}  // namespace b200
