@@ -2,6 +2,7 @@
 // kernels; if no device is present b200reg_create fails.
 #include <cfloat>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -252,6 +253,8 @@ int b200reg_create(int kind, int device, b200reg_t* out) {
     B200_CUDA(cudaEventCreate(&h->ev0));
     B200_CUDA(cudaEventCreate(&h->ev1));
     h->solver.init(device, h->stream);
+    h->solver.timing_enabled = getenv("B200REG_TIMING") != nullptr;
+    h->solver.scalar_controller = getenv("B200REG_SCALAR_CTL") != nullptr;
     h->gicp_solver.init(device, h->stream);
     if (kind == B200REG_GICP) {
       h->corr_dist = 5.0;  // gicp_omp.h:119
@@ -671,9 +674,9 @@ int b200reg_ndt_get_voxels(b200reg_t h, int* leaf_idx, int* npts, double* mean3,
     B200_CUDA(cudaStreamSynchronize(h->stream));
     for (size_t v = 0; v < V; v++) {
       if (mean3) {
-        mean3[3 * v + 0] = rec[v].mx;
-        mean3[3 * v + 1] = rec[v].my;
-        mean3[3 * v + 2] = rec[v].mz;
+        mean3[3 * v + 0] = record_mean(rec[v], 0);
+        mean3[3 * v + 1] = record_mean(rec[v], 1);
+        mean3[3 * v + 2] = record_mean(rec[v], 2);
       }
       if (centroid3) {
         centroid3[3 * v + 0] = cen[v].x;
@@ -682,6 +685,23 @@ int b200reg_ndt_get_voxels(b200reg_t h, int* leaf_idx, int* npts, double* mean3,
       }
       if (leaf_idx) std::memcpy(&leaf_idx[v], &cen[v].w, sizeof(int));
     }
+    return (int)B200REG_OK;
+  });
+}
+
+// developer instrumentation, not part of include/b200reg.h: per-round phase stamps of the last solver launch
+int b200reg_debug_timing(b200reg_t h, unsigned long long* out48x8) {
+  if (!h || !out48x8) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    h->solver.read_timing(out48x8);
+    return (int)B200REG_OK;
+  });
+}
+
+int b200reg_debug_cta_eval_ns(b200reg_t h, unsigned* out, int n) {
+  if (!h || !out) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    h->solver.read_cta_eval_ns(out, n);
     return (int)B200REG_OK;
   });
 }

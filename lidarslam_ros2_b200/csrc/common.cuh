@@ -46,13 +46,19 @@ struct RankWord {
 };
 
 // One NDT voxel as the fused kernel reads it (48 B, three 16-byte loads):
-//   mean in f64 so that x' = (double)x_trans - mean is formed exactly like ndt_omp_impl.hpp:259-262,
+//   mean as a float-float pair (hi + lo carries the f64 mean to ~2^-48 relative) so that
+//   x' = (x_trans - mean_hi) - mean_lo reproduces the reference's f64 subtraction followed by the cast to float
+//   (ndt_omp_impl.hpp:259-262, 490) without FP64 instructions on the hot path;
 //   inverse covariance as the f32 cast the reference applies at ndt_omp_impl.hpp:490-492 (symmetric 6).
 struct __align__(16) VoxelRecord {
-  double mx, my, mz;
-  float c00, c01, c02, c11, c12, c22;
+  float mhx, mhy, mhz, mlx;
+  float mly, mlz, c00, c01;
+  float c02, c11, c12, c22;
 };
 static_assert(sizeof(VoxelRecord) == 48, "VoxelRecord must be 48 bytes");
+__host__ __device__ inline double record_mean(const VoxelRecord& r, int axis) {
+  return axis == 0 ? (double)r.mhx + (double)r.mlx : (axis == 1 ? (double)r.mhy + (double)r.mly : (double)r.mhz + (double)r.mlz);
+}
 
 // slots of the 32-wide reduction vector produced by one derivative pass
 enum : int { SLOT_SCORE = 0, SLOT_G = 1, SLOT_H = 7, SLOT_HITS = 28, SLOT_COUNT = 32 };

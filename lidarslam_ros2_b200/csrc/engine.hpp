@@ -176,6 +176,10 @@ class NdtSolver {
   int block_threads() const { return block_; }
   int index_in_smem() const { return index_in_smem_; }
   int launches = 0;
+  bool scalar_controller = false;  // developer switch (env B200REG_SCALAR_CTL=1)
+  bool timing_enabled = false;  // developer instrumentation (env B200REG_TIMING=1)
+  void read_timing(unsigned long long* out48x8) const;
+  void read_cta_eval_ns(unsigned* out, int n) const;
   void reset_barrier();
 
  private:

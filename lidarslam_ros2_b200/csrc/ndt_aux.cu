@@ -79,7 +79,8 @@ __global__ void __launch_bounds__(128) hessian_radius_kernel(AuxParams P) {
     const double vf[3] = {dot3(x, P.hd + 36), dot3(x, P.hd + 39), dot3(x, P.hd + 42)};
     for_radius_neighbours(P, xt, [&](int r) {
       const VoxelRecord* rec = P.records + r;
-      const double xd[3] = {(double)xt.x - rec->mx, (double)xt.y - rec->my, (double)xt.z - rec->mz};
+      const double xd[3] = {(double)xt.x - record_mean(*rec, 0), (double)xt.y - record_mean(*rec, 1),
+                            (double)xt.z - record_mean(*rec, 2)};
       const double* C = P.icov_d + (size_t)r * 9;
       double Cx[3];
       matvec3(C, xd, Cx);
@@ -123,7 +124,8 @@ __global__ void __launch_bounds__(128) score_kernel(AuxParams P) {
     double s = 0.0;
     for_radius_neighbours(P, xt, [&](int r) {
       const VoxelRecord* rec = P.records + r;
-      const double xd[3] = {(double)xt.x - rec->mx, (double)xt.y - rec->my, (double)xt.z - rec->mz};
+      const double xd[3] = {(double)xt.x - record_mean(*rec, 0), (double)xt.y - record_mean(*rec, 1),
+                            (double)xt.z - record_mean(*rec, 2)};
       double Cx[3];
       matvec3(P.icov_d + (size_t)r * 9, xd, Cx);
       const double e = exp(-P.d2 * dot3(xd, Cx) / 2);

@@ -89,6 +89,55 @@ B200_HD void angle_tables(const double* p, float* jang, float* hang, double* jd,
   hang[20] = (float)sy;  // the live f32 table has +sy (ndt_omp_impl.hpp:381)
 }
 
+// The same 69 table entries (24 of J then 45 of H, f64 values) in coded form, so that independent lanes can evaluate
+// them: each entry is sign0 * f[a0]*f[a1]*f[a2] + sign1 * f[b0]*f[b1]*f[b2] with f = {sx,cx,sy,cy,sz,cz,1}
+// (angle_table_code.inc, generated by tools/gen_angle_table_code.py from the formulas above).
+#if defined(__CUDACC__)
+__device__ __constant__
+#endif
+    static const unsigned kAngleTableCode[69] = {
+#include "angle_table_code.inc"
+};
+
+B200_HD double angle_table_term(unsigned code, const double* f) {
+  const unsigned sign = code & 3u;
+  if (sign == 0u) return 0.0;
+  const double v = f[(code >> 2) & 7u] * f[(code >> 5) & 7u] * f[(code >> 8) & 7u];
+  return sign == 2u ? -v : v;
+}
+// f64 value of entry e (0..23: J, 24..68: H with the f64 sign convention, i.e. d1.z = -sy)
+B200_HD double angle_table_entry(unsigned word, const double* f) {
+  return angle_table_term(word & 0x7ffu, f) + angle_table_term((word >> 11) & 0x7ffu, f);
+}
+
+// sin/cos of a moderate angle (|x| << 1e5; Euler angles live in [-pi, pi]) to < 1 ulp: Cody-Waite reduction by pi/2
+// and the fdlibm kernel polynomials. Compact on purpose: the device-side controller is instruction-fetch bound (ndt_solver.cu).
+B200_HD void sincos_compact(double x, double* s_out, double* c_out) {
+  const double n = rint(x * 6.36619772367581382433e-01);
+  double r = fma(-n, 1.57079632673412561417e+00, x);
+  r = fma(-n, 6.07710050650619224932e-11, r);
+  r = fma(-n, 2.02226624879595063154e-21, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  const double sn = fma(r * z, ps, r);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double cs = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int q = ((int)n) & 3;
+  const double s0 = (q & 1) ? cs : sn, c0 = (q & 1) ? sn : cs;
+  *s_out = (q == 2 || q == 3) ? -s0 : s0;
+  *c_out = (q == 1 || q == 2) ? -c0 : c0;
+}
+
 // T: 3x4 row-major float
 B200_HD void pose_to_matrix(const double* p, float* T) {
   float a = (float)p[3], b = (float)p[4], c = (float)p[5];

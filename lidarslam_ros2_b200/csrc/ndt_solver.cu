@@ -4,25 +4,25 @@
 //   computeTransformation :80-171, computeDerivatives :179-284, computePointDerivatives :396-438,
 //   updateDerivatives :482-535, computeStepLengthMT :756-916 (+ :632-753), and the neighbourhood lookups
 //   voxel_grid_covariance_omp_impl.hpp:373-442; pcl::transformPointCloud (ndt_omp_impl.hpp:100,817,862) is fused
-//   into the point load.
+//   into the evaluation.
 //
 // B200 design (not a translation of the OpenMP loop):
-//   * ONE kernel launch per align(): a cooperative grid of persistent CTAs iterates
-//       evaluate (all CTAs) -> grid barrier -> controller (last-arriving CTA: 6x6 solve, line-search state
-//       machine, next pose + angle tables) -> release -> evaluate ...
-//     so the ~5-40 sequential evaluations of one registration cost no launches and no host round trips.
-//   * per (point, voxel) pair only the exponential weight e, s = C x' and the 15 sums S += e s, M += e C,
-//     Q += e s s^T are formed; the 6-vector gradient and 6x6 Hessian contribution J^T(.)J is applied once per
-//     POINT (J, H_E depend on the point only). ~35 FMA per pair + ~140 per point instead of ~600 MAC per pair.
-//   * voxel lookup = occupancy-bitmap rank index (common.cuh), staged into shared memory by a TMA bulk copy
-//     (cp.async.bulk + mbarrier) once per launch and reused by every evaluation; 48-byte voxel records are read
-//     with three 16-byte read-only loads.
-//   * reductions: per-thread f32 sums of <= a few points -> f64 halving-butterfly across the warp (31 shuffled
-//     doubles instead of 32*5) -> per-CTA partial -> fixed-order f64 sum over CTAs: bitwise deterministic.
+//   * ONE cooperative kernel launch per align(). Evaluator CTAs keep their source points in REGISTERS for the
+//     whole solve and loop   evaluate -> CTA partial -> arrive -> wait for the next pose;   one dedicated
+//     CONTROLLER CTA keeps the Newton / More-Thuente state in shared memory and loops
+//     wait for all arrivals -> fixed-order f64 reduction of the partials -> 6x6 solve -> next pose + angle
+//     tables -> release.  The ~5-40 sequential evaluations of a registration cost no launches, no host round
+//     trips and no global-memory state traffic.
+//   * per (point, voxel) pair only e, s = C x' and the sums S += e s, M += e C, Q += e s s^T are formed; the
+//     gradient / Hessian contribution J^T(.)J is applied once per POINT (J, H_E depend on the point only):
+//     ~35 FMA per pair + ~140 per point instead of ~600 MAC per pair in the reference.
+//   * voxel lookup = occupancy-bitmap rank index (common.cuh) staged into shared memory by TMA bulk copies
+//     (cp.async.bulk + mbarrier) once per launch; 48-byte voxel records are fetched with batched 16-byte
+//     read-only loads (several records of a point are in flight before the first one is consumed).
+//   * reductions: per-thread f32 sums of <= a few points in shared memory -> lane L of each warp sums slot L over the
+//     warp's 32 columns in f64 (fixed order) -> per-CTA partial -> fixed-order f64 sum over CTAs: bitwise deterministic.
 //
 // Algorithmic HBM bytes per evaluation: N_src*16 + N_src*probes*8 + N_hit*48 + 28*8.
-#include <cooperative_groups.h>
-
 #include "ndt_solver.cuh"
 
 namespace b200 {
@@ -31,13 +31,24 @@ namespace {
 
 constexpr int SOLVER_THREADS = 256;
 constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
-constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s: device-side watchdog, never reached in normal runs
+#ifndef B200_SOLVER_MIN_CTAS
+#define B200_SOLVER_MIN_CTAS 3
+#endif
+constexpr int SOLVER_MIN_CTAS = B200_SOLVER_MIN_CTAS;  // resident CTAs per SM the register budget is sized for
+constexpr int SMEM_POINTS = 1024;  // source points of a CTA's chunk staged in shared memory for the whole solve
+constexpr int ACC_SLOTS = 27;      // 6 gradient + 21 upper-triangular Hessian sums per thread (f32, in shared memory)
+constexpr int ACC_STRIDE = SOLVER_THREADS + 1;  // padded row: slot-major reads by 32 lanes hit 32 different banks
+constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s device-side watchdog, never reached in normal runs
 
-struct SharedCtl {
-  NdtControl c;
-  int is_last;
-  int abort;
-};
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define B200_STAMP(cond, round, slot)                                                                  \
+  do {                                                                                                 \
+    if (L.timing && (cond) && (round) < NDT_TIMING_ROUNDS) W->timing[round][slot] = globaltimer_ns(); \
+  } while (0)
 
 // ---- TMA bulk copy helpers (cp.async.bulk → UBLKCP) -----------------------------------------------------
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -66,65 +77,65 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-
-// ---- warp reduction of 32 doubles per lane: after the call lane L holds the warp total of slot L ----------
-template <int N, int S>
-struct Butterfly {
-  static __device__ __forceinline__ void run(double* v, int lane) {
-    const bool upper = (lane & S) != 0;
-#pragma unroll
-    for (int k = 0; k < N / 2; k++) {
-      double send = upper ? v[k] : v[k + N / 2];
-      double keep = upper ? v[k + N / 2] : v[k];
-      double recv = __shfl_xor_sync(0xffffffffu, send, S);
-      v[k] = keep + recv;
-    }
-    Butterfly<N / 2, S / 2>::run(v, lane);
-  }
-};
-template <>
-struct Butterfly<1, 0> {
-  static __device__ __forceinline__ void run(double*, int) {}
-};
+__device__ __forceinline__ void red_add_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 
 // ---- per-thread accumulators of one evaluation --------------------------------------------------------------
+// The 27 f32 sums of a thread live in SHARED memory (column tid of acc[slot][tid], conflict-free; the warp-level
+// reduction then reads them slot-major, see the kernel) so that the
+// registers stay available for the batched voxel-record loads; score (f64) and the hit count stay in registers.
 struct Accum {
-  float g[6];
-  float h[21];
+  float (*s)[ACC_STRIDE];  // [ACC_SLOTS][ACC_STRIDE]
+  int tid;
+  bool first;  // no point applied yet this evaluation: store instead of read-modify-write
   double score;
   int hits;
+  __device__ __forceinline__ void add(int slot, float v) { s[slot][tid] = first ? v : s[slot][tid] + v; }
 };
 
 struct PairSums {  // sums over the voxels hit by one point
-  float S0, S1, S2;                      // sum e * s,           s = C x'
-  float M00, M01, M02, M11, M12, M22;    // sum e * C
-  float Q00, Q01, Q02, Q11, Q12, Q22;    // sum e * s s^T
+  float S0, S1, S2;                    // sum e * s,           s = C x'
+  float M00, M01, M02, M11, M12, M22;  // sum e * C
+  float Q00, Q01, Q02, Q11, Q12, Q22;  // sum e * s s^T
+  float score;                         // sum of the f32 score increments of this point
+  int hits;
 };
 
-// one (point, voxel) pair — updateDerivatives (ndt_omp_impl.hpp:482-535) reduced to its per-pair core
+struct Rec {
+  float4 a, b, c;
+};
+__device__ __forceinline__ Rec load_record(const VoxelRecord* __restrict__ rec) {
+  Rec r;
+  const float4* p = reinterpret_cast<const float4*>(rec);
+  r.a = __ldg(p);
+  r.b = __ldg(p + 1);
+  r.c = __ldg(p + 2);
+  return r;
+}
+
+// one (point, voxel) pair — updateDerivatives (ndt_omp_impl.hpp:482-535) reduced to its per-pair core.
+// Branch-free: a probe that missed reads record 0 and is masked out, so that the compiler may keep the loads and
+// the arithmetic of several pairs in flight. All f32: the reference forms score_inc = float(-d1 * e) and
+// e' = float(e * d1) through a double product (:499, :508); multiplying by float(d1) instead differs by at most one
+// f32 ulp (6e-8 relative), far below the f32 noise of the per-pair products themselves.
 template <bool HESS>
-__device__ __forceinline__ void accumulate_pair(const VoxelRecord* __restrict__ rec, float3 xt, const NdtLaunch& L,
-                                                float gd2, PairSums& ps, double& score, int& hits) {
-  const double2 m01 = __ldg(reinterpret_cast<const double2*>(rec));
-  const double2 m2c = __ldg(reinterpret_cast<const double2*>(rec) + 1);
-  const float4 cc = __ldg(reinterpret_cast<const float4*>(rec) + 2);
-  const float c00 = __int_as_float(__double2loint(m2c.y)), c01 = __int_as_float(__double2hiint(m2c.y));
-  const float c02 = cc.x, c11 = cc.y, c12 = cc.z, c22 = cc.w;
-  // x' = x_trans - mean in f64, then to f32 (ndt_omp_impl.hpp:259-262, 490)
-  const float x0 = (float)((double)xt.x - m01.x);
-  const float x1 = (float)((double)xt.y - m01.y);
-  const float x2 = (float)((double)xt.z - m2c.x);
+__device__ __forceinline__ void accumulate_pair(const Rec& R, bool valid, float3 xt, float d1f, float gd2, PairSums& ps) {
+  const float c00 = R.b.z, c01 = R.b.w, c02 = R.c.x, c11 = R.c.y, c12 = R.c.z, c22 = R.c.w;
+  // x' = x_trans - mean (float-float mean: equals the reference's f64 subtraction + cast, :259-262, :490)
+  const float x0 = __fsub_rn(__fsub_rn(xt.x, R.a.x), R.a.w);
+  const float x1 = __fsub_rn(__fsub_rn(xt.y, R.a.y), R.b.x);
+  const float x2 = __fsub_rn(__fsub_rn(xt.z, R.a.z), R.b.y);
   const float s0 = c00 * x0 + c01 * x1 + c02 * x2;
   const float s1 = c01 * x0 + c11 * x1 + c12 * x2;
   const float s2 = c02 * x0 + c12 * x1 + c22 * x2;
   const float q = x0 * s0 + x1 * s1 + x2 * s2;
-  float e = expf(-gd2 * q * 0.5f);                 // :497
-  const float score_inc = (float)(-L.d1 * (double)e);  // :499
-  e = gd2 * e;                                     // :501
-  if (e > 1.0f || e < 0.0f || e != e) return;      // :504-505 (the score increment is dropped too)
-  e = (float)((double)e * L.d1);                   // :508
-  score += (double)score_inc;
-  hits += 1;
+  const float ex = expf(-gd2 * q * 0.5f);  // :497
+  const float e2 = gd2 * ex;               // :501
+  const bool ok = valid && !(e2 > 1.0f || e2 < 0.0f || e2 != e2);  // :504-505 (the score increment is dropped too)
+  const float e = ok ? e2 * d1f : 0.0f;    // :508
+  ps.score += ok ? -d1f * ex : 0.0f;       // :499
+  ps.hits += ok ? 1 : 0;
   ps.S0 += e * s0;
   ps.S1 += e * s1;
   ps.S2 += e * s2;
@@ -139,26 +150,29 @@ __device__ __forceinline__ void accumulate_pair(const VoxelRecord* __restrict__ 
 
 // per-POINT application of J (point gradient, :396-412) and H_E (:414-436) to the pair sums
 template <bool HESS>
-__device__ __forceinline__ void apply_point(const float4 p, const PairSums& ps, const SharedCtl& sc, float gd2, Accum& a) {
-  const float* ja = sc.c.jang;
+__device__ __forceinline__ void apply_point(const float4 p, const PairSums& ps, const NdtControl& c, float gd2, Accum& a) {
   const float x = p.x, y = p.y, z = p.z;
+  // the 24 + 45 table floats are read as 16-byte shared-memory vectors (NdtControl: jang at byte 48, hang at 144)
+  const float4* jv = reinterpret_cast<const float4*>(c.jang);
+  const float4 ja0 = jv[0], ja1 = jv[1], ja2 = jv[2], ja3 = jv[3], ja4 = jv[4], ja5 = jv[5];
   // J columns 3..5: J3 = (0, j0, j1), J4 = (j2, j3, j4), J5 = (j5, j6, j7)
-  const float j0 = ja[0] * x + ja[1] * y + ja[2] * z;
-  const float j1 = ja[3] * x + ja[4] * y + ja[5] * z;
-  const float j2 = ja[6] * x + ja[7] * y + ja[8] * z;
-  const float j3 = ja[9] * x + ja[10] * y + ja[11] * z;
-  const float j4 = ja[12] * x + ja[13] * y + ja[14] * z;
-  const float j5 = ja[15] * x + ja[16] * y + ja[17] * z;
-  const float j6 = ja[18] * x + ja[19] * y + ja[20] * z;
-  const float j7 = ja[21] * x + ja[22] * y + ja[23] * z;
-  a.g[0] += ps.S0;
-  a.g[1] += ps.S1;
-  a.g[2] += ps.S2;
-  a.g[3] += j0 * ps.S1 + j1 * ps.S2;
-  a.g[4] += j2 * ps.S0 + j3 * ps.S1 + j4 * ps.S2;
-  a.g[5] += j5 * ps.S0 + j6 * ps.S1 + j7 * ps.S2;
+  const float j0 = ja0.x * x + ja0.y * y + ja0.z * z;
+  const float j1 = ja0.w * x + ja1.x * y + ja1.y * z;
+  const float j2 = ja1.z * x + ja1.w * y + ja2.x * z;
+  const float j3 = ja2.y * x + ja2.z * y + ja2.w * z;
+  const float j4 = ja3.x * x + ja3.y * y + ja3.z * z;
+  const float j5 = ja3.w * x + ja4.x * y + ja4.y * z;
+  const float j6 = ja4.z * x + ja4.w * y + ja5.x * z;
+  const float j7 = ja5.y * x + ja5.z * y + ja5.w * z;
+  a.score += (double)ps.score;
+  a.hits += ps.hits;
+  a.add(0, ps.S0);
+  a.add(1, ps.S1);
+  a.add(2, ps.S2);
+  a.add(3, j0 * ps.S1 + j1 * ps.S2);
+  a.add(4, j2 * ps.S0 + j3 * ps.S1 + j4 * ps.S2);
+  a.add(5, j5 * ps.S0 + j6 * ps.S1 + j7 * ps.S2);
   if (HESS) {
-    const float* ha = sc.c.hang;
     // W = sum e (C - d2 s s^T)
     const float W00 = ps.M00 - gd2 * ps.Q00, W01 = ps.M01 - gd2 * ps.Q01, W02 = ps.M02 - gd2 * ps.Q02;
     const float W11 = ps.M11 - gd2 * ps.Q11, W12 = ps.M12 - gd2 * ps.Q12, W22 = ps.M22 - gd2 * ps.Q22;
@@ -167,104 +181,427 @@ __device__ __forceinline__ void apply_point(const float4 p, const PairSums& ps, 
     const float b0 = W00 * j2 + W01 * j3 + W02 * j4, b1 = W01 * j2 + W11 * j3 + W12 * j4, b2 = W02 * j2 + W12 * j3 + W22 * j4;
     const float c0 = W00 * j5 + W01 * j6 + W02 * j7, c1 = W01 * j5 + W11 * j6 + W12 * j7, c2 = W02 * j5 + W12 * j6 + W22 * j7;
     // second-derivative vectors a..f dotted with S (rows of hang: a2 a3 b2 b3 c2 c3 d1 d2 d3 e1 e2 e3 f1 f2 f3)
-    const float hA2 = ha[0] * x + ha[1] * y + ha[2] * z, hA3 = ha[3] * x + ha[4] * y + ha[5] * z;
-    const float hB2 = ha[6] * x + ha[7] * y + ha[8] * z, hB3 = ha[9] * x + ha[10] * y + ha[11] * z;
-    const float hC2 = ha[12] * x + ha[13] * y + ha[14] * z, hC3 = ha[15] * x + ha[16] * y + ha[17] * z;
-    const float hD1 = ha[18] * x + ha[19] * y + ha[20] * z, hD2 = ha[21] * x + ha[22] * y + ha[23] * z,
-                hD3 = ha[24] * x + ha[25] * y + ha[26] * z;
-    const float hE1 = ha[27] * x + ha[28] * y + ha[29] * z, hE2 = ha[30] * x + ha[31] * y + ha[32] * z,
-                hE3 = ha[33] * x + ha[34] * y + ha[35] * z;
-    const float hF1 = ha[36] * x + ha[37] * y + ha[38] * z, hF2 = ha[39] * x + ha[40] * y + ha[41] * z,
-                hF3 = ha[42] * x + ha[43] * y + ha[44] * z;
+    const float4* hv = reinterpret_cast<const float4*>(c.hang);
+    const float4 h0 = hv[0], h1 = hv[1], h2 = hv[2], h3 = hv[3], h4 = hv[4], h5 = hv[5], h6 = hv[6], h7 = hv[7], h8 = hv[8],
+                 h9 = hv[9], h10 = hv[10];
+    const float h44 = c.hang[44];
+    const float hA2 = h0.x * x + h0.y * y + h0.z * z, hA3 = h0.w * x + h1.x * y + h1.y * z;
+    const float hB2 = h1.z * x + h1.w * y + h2.x * z, hB3 = h2.y * x + h2.z * y + h2.w * z;
+    const float hC2 = h3.x * x + h3.y * y + h3.z * z, hC3 = h3.w * x + h4.x * y + h4.y * z;
+    const float hD1 = h4.z * x + h4.w * y + h5.x * z, hD2 = h5.y * x + h5.z * y + h5.w * z, hD3 = h6.x * x + h6.y * y + h6.z * z;
+    const float hE1 = h6.w * x + h7.x * y + h7.y * z, hE2 = h7.z * x + h7.w * y + h8.x * z, hE3 = h8.y * x + h8.z * y + h8.w * z;
+    const float hF1 = h9.x * x + h9.y * y + h9.z * z, hF2 = h9.w * x + h10.x * y + h10.y * z,
+                hF3 = h10.z * x + h10.w * y + h44 * z;
     // upper triangle, row-major: (0,0..5) (1,1..5) (2,2..5) (3,3..5) (4,4..5) (5,5)
-    a.h[0] += W00; a.h[1] += W01; a.h[2] += W02; a.h[3] += a0; a.h[4] += b0; a.h[5] += c0;
-    a.h[6] += W11; a.h[7] += W12; a.h[8] += a1; a.h[9] += b1; a.h[10] += c1;
-    a.h[11] += W22; a.h[12] += a2; a.h[13] += b2; a.h[14] += c2;
-    a.h[15] += (j0 * a1 + j1 * a2) + (hA2 * ps.S1 + hA3 * ps.S2);
-    a.h[16] += (j0 * b1 + j1 * b2) + (hB2 * ps.S1 + hB3 * ps.S2);
-    a.h[17] += (j0 * c1 + j1 * c2) + (hC2 * ps.S1 + hC3 * ps.S2);
-    a.h[18] += (j2 * b0 + j3 * b1 + j4 * b2) + (hD1 * ps.S0 + hD2 * ps.S1 + hD3 * ps.S2);
-    a.h[19] += (j2 * c0 + j3 * c1 + j4 * c2) + (hE1 * ps.S0 + hE2 * ps.S1 + hE3 * ps.S2);
-    a.h[20] += (j5 * c0 + j6 * c1 + j7 * c2) + (hF1 * ps.S0 + hF2 * ps.S1 + hF3 * ps.S2);
+    a.add(6 + 0, W00); a.add(6 + 1, W01); a.add(6 + 2, W02); a.add(6 + 3, a0); a.add(6 + 4, b0); a.add(6 + 5, c0);
+    a.add(6 + 6, W11); a.add(6 + 7, W12); a.add(6 + 8, a1); a.add(6 + 9, b1); a.add(6 + 10, c1);
+    a.add(6 + 11, W22); a.add(6 + 12, a2); a.add(6 + 13, b2); a.add(6 + 14, c2);
+    a.add(6 + 15, (j0 * a1 + j1 * a2) + (hA2 * ps.S1 + hA3 * ps.S2));
+    a.add(6 + 16, (j0 * b1 + j1 * b2) + (hB2 * ps.S1 + hB3 * ps.S2));
+    a.add(6 + 17, (j0 * c1 + j1 * c2) + (hC2 * ps.S1 + hC3 * ps.S2));
+    a.add(6 + 18, (j2 * b0 + j3 * b1 + j4 * b2) + (hD1 * ps.S0 + hD2 * ps.S1 + hD3 * ps.S2));
+    a.add(6 + 19, (j2 * c0 + j3 * c1 + j4 * c2) + (hE1 * ps.S0 + hE2 * ps.S1 + hE3 * ps.S2));
+    a.add(6 + 20, (j5 * c0 + j6 * c1 + j7 * c2) + (hF1 * ps.S0 + hF2 * ps.S1 + hF3 * ps.S2));
   }
 }
 
+// rank-index probe of a leaf index known to be inside the grid
+// (idx points either at the shared-memory copy staged by TMA or at the global table)
+__device__ __forceinline__ int probe_lin(const RankWord* __restrict__ idx, int lin) {
+  const uint2 w = *reinterpret_cast<const uint2*>(idx + (lin >> 5));
+  const unsigned bit = lin & 31;
+  if (!((w.x >> bit) & 1u)) return -1;
+  return (int)(w.y + __popc(w.x & ((1u << bit) - 1u)));
+}
+
 // neighbourhood of one transformed point for the four pclomp::NeighborSearchMethod values
-template <int METHOD, bool HESS, bool STAGED>
-__device__ __forceinline__ void process_point(const NdtLaunch& L, const SharedCtl& sc, const RankWord* sidx, int i,
+template <int METHOD, bool HESS>
+__device__ __forceinline__ void process_point(const NdtLaunch& L, const NdtControl& c, const RankWord* idx, const float4 p,
                                               float gd2, Accum& acc) {
-  const float4 p = L.src[i];
-  const float3 xt = transform_point(sc.c.T, p);
-  const int ci = lookup_cell(xt.x, L.geom.leaf), cj = lookup_cell(xt.y, L.geom.leaf), ck = lookup_cell(xt.z, L.geom.leaf);
+  const float3 xt = transform_point(c.T, p);
+  const GridGeom& g = L.geom;
+  const int ri = lookup_cell_fast(xt.x, g.leaf, g.inv_leaf) - g.min_b[0],
+            rj = lookup_cell_fast(xt.y, g.leaf, g.inv_leaf) - g.min_b[1],
+            rk = lookup_cell_fast(xt.z, g.leaf, g.inv_leaf) - g.min_b[2];
   PairSums ps = {};
-  const int hits_before = acc.hits;
-  if (METHOD == 2) {  // DIRECT7 (voxel_grid_covariance_omp_impl.hpp:418-433)
+  const float d1f = (float)L.d1;
+  if (METHOD == 2 || METHOD == 3) {  // DIRECT7 (voxel_grid_covariance_omp_impl.hpp:418-433) / DIRECT1
+    // in-grid tests per axis (impl.hpp:382-392), shared by the probes
+    const bool ix = (unsigned)ri < (unsigned)g.div_b[0], iy = (unsigned)rj < (unsigned)g.div_b[1],
+               iz = (unsigned)rk < (unsigned)g.div_b[2];
+    const int lin = ri + rj * g.mul[1] + rk * g.mul[2];
     int r[7];
-    r[0] = probe_cell<STAGED>(L.geom, L.index, sidx, ci, cj, ck);
-    r[1] = probe_cell<STAGED>(L.geom, L.index, sidx, ci + 1, cj, ck);
-    r[2] = probe_cell<STAGED>(L.geom, L.index, sidx, ci - 1, cj, ck);
-    r[3] = probe_cell<STAGED>(L.geom, L.index, sidx, ci, cj + 1, ck);
-    r[4] = probe_cell<STAGED>(L.geom, L.index, sidx, ci, cj - 1, ck);
-    r[5] = probe_cell<STAGED>(L.geom, L.index, sidx, ci, cj, ck + 1);
-    r[6] = probe_cell<STAGED>(L.geom, L.index, sidx, ci, cj, ck - 1);
+    r[0] = (ix && iy && iz) ? probe_lin(idx, lin) : -1;
+    if (METHOD == 2) {
+      const bool yz = iy && iz, xz = ix && iz, xy = ix && iy;
+      r[1] = (yz && (unsigned)(ri + 1) < (unsigned)g.div_b[0]) ? probe_lin(idx, lin + 1) : -1;
+      r[2] = (yz && (unsigned)(ri - 1) < (unsigned)g.div_b[0]) ? probe_lin(idx, lin - 1) : -1;
+      r[3] = (xz && (unsigned)(rj + 1) < (unsigned)g.div_b[1]) ? probe_lin(idx, lin + g.mul[1]) : -1;
+      r[4] = (xz && (unsigned)(rj - 1) < (unsigned)g.div_b[1]) ? probe_lin(idx, lin - g.mul[1]) : -1;
+      r[5] = (xy && (unsigned)(rk + 1) < (unsigned)g.div_b[2]) ? probe_lin(idx, lin + g.mul[2]) : -1;
+      r[6] = (xy && (unsigned)(rk - 1) < (unsigned)g.div_b[2]) ? probe_lin(idx, lin - g.mul[2]) : -1;
 #pragma unroll
-    for (int k = 0; k < 7; k++)
-      if (r[k] >= 0) accumulate_pair<HESS>(L.records + r[k], xt, L, gd2, ps, acc.score, acc.hits);
-  } else if (METHOD == 3) {  // DIRECT1
-    int r0 = probe_cell<STAGED>(L.geom, L.index, sidx, ci, cj, ck);
-    if (r0 >= 0) accumulate_pair<HESS>(L.records + r0, xt, L, gd2, ps, acc.score, acc.hits);
+      for (int k = 0; k < 7; k++)
+        accumulate_pair<HESS>(load_record(L.records + max(r[k], 0)), r[k] >= 0, xt, d1f, gd2, ps);
+    } else {
+      accumulate_pair<HESS>(load_record(L.records + max(r[0], 0)), r[0] >= 0, xt, d1f, gd2, ps);
+    }
   } else {  // DIRECT26 (26 cells, centre excluded) / KDTREE (27 cells + centroid radius test)
     for (int dz = -1; dz <= 1; dz++)
       for (int dy = -1; dy <= 1; dy++)
         for (int dx = -1; dx <= 1; dx++) {
           if (METHOD == 1 && dx == 0 && dy == 0 && dz == 0) continue;
-          int r = probe_cell<STAGED>(L.geom, L.index, sidx, ci + dx, cj + dy, ck + dz);
+          const int ni = ri + dx, nj = rj + dy, nk = rk + dz;
+          if ((unsigned)ni >= (unsigned)g.div_b[0] || (unsigned)nj >= (unsigned)g.div_b[1] || (unsigned)nk >= (unsigned)g.div_b[2])
+            continue;
+          const int r = probe_lin(idx, ni + nj * g.mul[1] + nk * g.mul[2]);
           if (r < 0) continue;
           if (METHOD == 0) {  // radiusSearch over voxel centroids (voxel_grid_covariance_omp.h:470-499)
-            const float4 c = __ldg(L.centroids + r);
-            const float ex = __fsub_rn(xt.x, c.x), ey = __fsub_rn(xt.y, c.y), ez = __fsub_rn(xt.z, c.z);
+            const float4 cc = __ldg(L.centroids + r);
+            const float ex = __fsub_rn(xt.x, cc.x), ey = __fsub_rn(xt.y, cc.y), ez = __fsub_rn(xt.z, cc.z);
             const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey)), __fmul_rn(ez, ez));
             if (!(d2 < L.radius2)) continue;
           }
-          accumulate_pair<HESS>(L.records + r, xt, L, gd2, ps, acc.score, acc.hits);
+          accumulate_pair<HESS>(load_record(L.records + r), true, xt, d1f, gd2, ps);
         }
   }
-  if (acc.hits != hits_before) apply_point<HESS>(p, ps, sc, gd2, acc);
-}
-
-template <int METHOD, bool STAGED>
-__device__ __forceinline__ void evaluate(const NdtLaunch& L, const SharedCtl& sc, const RankWord* sidx, Accum& acc) {
-  const float gd2 = (float)L.d2;
-  const int stride = gridDim.x * SOLVER_THREADS;
-  if (sc.c.compute_hessian) {
-    for (int i = blockIdx.x * SOLVER_THREADS + threadIdx.x; i < L.n_src; i += stride)
-      process_point<METHOD, true, STAGED>(L, sc, sidx, i, gd2, acc);
-  } else {
-    for (int i = blockIdx.x * SOLVER_THREADS + threadIdx.x; i < L.n_src; i += stride)
-      process_point<METHOD, false, STAGED>(L, sc, sidx, i, gd2, acc);
+  if (ps.hits) {
+    apply_point<HESS>(p, ps, c, gd2, acc);
+    acc.first = false;
   }
 }
 
 // =====================================================================================================
-// controller: runs in ONE thread of the last-arriving CTA after every evaluation
+// controller (runs warp-uniformly in warp 0 of the controller CTA; state in shared memory)
 // =====================================================================================================
-__device__ void write_control(NdtSolverWork* W, const double* x_t, int compute_hessian, bool want_f64_tables) {
-  NdtControl& c = W->control;
-  pose_to_matrix(x_t, c.T);
-  angle_tables(x_t, c.jang, c.hang, want_f64_tables ? W->state.jd : nullptr, want_f64_tables ? W->state.hd : nullptr);
-  c.mode = EVAL_DERIV;
-  c.compute_hessian = compute_hessian;
-  float* F = W->state.final_T;  // final_transformation_ (ndt_omp_impl.hpp:811-814)
-  for (int r = 0; r < 3; r++)
-    for (int k = 0; k < 4; k++) F[r * 4 + k] = c.T[r * 4 + k];
-  F[12] = F[13] = F[14] = 0.0f;
-  F[15] = 1.0f;
+// LU with partial pivoting entirely in registers (all indices static after unrolling). Returns false when a pivot
+// collapses (rank deficiency) — the caller then uses the SVD path that reproduces JacobiSVD's truncation.
+__device__ __forceinline__ bool lu_solve6(const double* H, const double* b, double* x) {
+  double A[6][7];
+  double amax = 0;
+  bool finite = true;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) {
+      A[r][c] = H[r * 6 + c];
+      double a = fabs(A[r][c]);
+      finite = finite && (a <= 1.7e308);
+      amax = fmax(amax, a);
+    }
+    A[r][6] = b[r];
+  }
+  if (!finite) {
+#pragma unroll
+    for (int i = 0; i < 6; i++) x[i] = NAN;
+    return true;  // NaN/inf propagate like the SVD would (delta_p_norm != delta_p_norm branch, :134-139)
+  }
+  if (!(amax > 0)) return false;
+  bool ok = true;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    int piv = k;
+    double pm = fabs(A[k][k]);
+#pragma unroll
+    for (int r = k + 1; r < 6; r++) {
+      double v = fabs(A[r][k]);
+      if (v > pm) {
+        pm = v;
+        piv = r;
+      }
+    }
+    if (pm <= 1e-13 * amax) ok = false;
+#pragma unroll
+    for (int r = k + 1; r < 6; r++) {
+      const bool sw = (r == piv);
+#pragma unroll
+      for (int c = k; c < 7; c++) {
+        double t0 = A[k][c], t1 = A[r][c];
+        A[k][c] = sw ? t1 : t0;
+        A[r][c] = sw ? t0 : t1;
+      }
+    }
+    const double inv = 1.0 / A[k][k];
+#pragma unroll
+    for (int r = k + 1; r < 6; r++) {
+      const double f = A[r][k] * inv;
+#pragma unroll
+      for (int c = k + 1; c < 7; c++) A[r][c] -= f * A[k][c];
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int k = 5; k >= 0; k--) {
+    double s = A[k][6];
+#pragma unroll
+    for (int c = k + 1; c < 6; c++) s -= A[k][c] * x[c];
+    x[k] = s / A[k][k];
+  }
+  return true;
 }
 
-__device__ void load_totals(NdtState& st, const double* tot, bool with_hessian) {
+struct CtlShared {
+  NdtState st;
+  NdtControl next;  // control block under construction (then copied to global by the whole warp)
+  double tot[SLOT_COUNT];
+  int done;
+  int build;          // 1: the controller asks the warp to build the control block for st.x_t
+  int build_hessian;  // compute_hessian flag of that evaluation
+  int build_f64;      // also keep the f64 angle tables (needed by a later K2 pass)
+  double fac[8];      // sx, cx, sy, cy, sz, cz, 1, 0 of the pose being built (f64, with the 1e-4 snap)
+  float facf[8];      // f32 sin/cos of the same angles (for the transform)
+  unsigned code[72];  // shared-memory copy of kAngleTableCode
+  double M[6][8];     // fast-path scratch: H (36 doubles) followed by A^-1 (9)
+  double blk[3][12];  // fast-path scratch: Y | v1, S | w, S^-1
+  NdtControl scratch; // target of warm-up passes
+  float scratch_T[16];
+  double vec[4][8];   // fast-path scratch: p, g, dp, dir
+};
+
+// ---- compact f64 helpers ------------------------------------------------------------------------------------
+// The controller runs ONCE per evaluation in ONE warp: its cost is the length of its dependent instruction chain
+// (measured ~10 cycles per instruction; neither instruction-cache warming nor rolled-vs-unrolled code changed it).
+// The per-evaluation path is therefore organised to minimise the number of sequential steps: data-parallel across
+// the lanes wherever the mathematics allows it.
+__device__ __noinline__ double ddiv(double a, double b) { return a / b; }
+__device__ __noinline__ double dsqrt(double a) { return sqrt(a); }
+
+__device__ __noinline__ void dsincos(double x, double* s_out, double* c_out) { sincos_compact(x, s_out, c_out); }
+
+// next pose -> transform + angle tables, by the whole warp: lanes 0..2 evaluate sin/cos of the three angles, then
+// every lane evaluates up to three of the 69 table entries from their coded form (ndt_math.cuh) and stores them; lane 0
+// forms the 3x4 transform. Nothing here read-modify-writes shared state, so lanes need not run in lockstep.
+__device__ __noinline__ void build_control(CtlShared& cs, int lane, const unsigned* warm_arrive, unsigned warm_target) {
+  const bool dry = warm_arrive != nullptr;
+  const double* x_t = cs.st.x_t;
+  const bool want_f64 = !dry && cs.build_f64 != 0;
+  if (lane < 3) {
+    const double ang = x_t[3 + lane];
+    double sd, cd, sfd, cfd;
+    dsincos(ang, &sd, &cd);
+    if (fabs(ang) < 10e-5) {  // ndt_omp_impl.hpp:292-325
+      sd = 0.0;
+      cd = 1.0;
+    }
+    // the transform uses cos/sin of the angle cast to float, in float (Eigen::AngleAxis<float>, :811-814):
+    // correctly rounded from the f64 value at the float argument
+    dsincos((double)(float)ang, &sfd, &cfd);
+    cs.fac[2 * lane] = sd;
+    cs.fac[2 * lane + 1] = cd;
+    cs.facf[2 * lane] = (float)sfd;
+    cs.facf[2 * lane + 1] = (float)cfd;
+  } else if (lane == 3) {
+    cs.fac[6] = 1.0;
+    cs.fac[7] = 0.0;
+  }
+  __syncwarp();
+  if (dry) {
+    unsigned seen = 0;
+    if (lane == 0) seen = ld_relaxed_gpu(warm_arrive);
+    if (__shfl_sync(0xffffffffu, seen, 0) == warm_target) return;
+  }
+  NdtControl& c = dry ? cs.scratch : cs.next;
+#pragma unroll 1
+  for (int e = lane; e < 69; e += 32) {
+    const double v = angle_table_entry(cs.code[e], cs.fac);  // f64 value (H row d1 carries -sy, :359)
+    float fv = (float)v;
+    if (e == 24 + 20) fv = -fv;  // the live f32 table keeps +sy (:381)
+    if (e < 24) c.jang[e] = fv;
+    else c.hang[e - 24] = fv;
+    if (want_f64) {
+      if (e < 24) cs.st.jd[e] = v;
+      else cs.st.hd[e - 24] = v;
+    }
+  }
+  if (lane < 3) {
+    // T = Translation * Rx * Ry * Rz in float (ndt_omp_impl.hpp:811-814), same product order as pose_to_matrix();
+    // lane r forms row r
+    const float fsx = cs.facf[0], fcx = cs.facf[1], fsy = cs.facf[2], fcy = cs.facf[3], fsz = cs.facf[4], fcz = cs.facf[5];
+    const float a0 = lane == 0 ? fcy : (lane == 1 ? fsx * fsy : -fcx * fsy);
+    const float a1 = lane == 0 ? 0.0f : (lane == 1 ? fcx : fsx);
+    const float a2 = lane == 0 ? fsy : (lane == 1 ? -fsx * fcy : fcx * fcy);
+    const float t0 = __fadd_rn(__fmul_rn(a0, fcz), __fmul_rn(a1, fsz));
+    const float t1 = __fadd_rn(__fmul_rn(a0, -fsz), __fmul_rn(a1, fcz));
+    const float t3 = (float)x_t[lane];
+    float* F = dry ? cs.scratch_T : cs.st.final_T;  // final_transformation_
+    c.T[lane * 4 + 0] = t0; c.T[lane * 4 + 1] = t1; c.T[lane * 4 + 2] = a2; c.T[lane * 4 + 3] = t3;
+    F[lane * 4 + 0] = t0; F[lane * 4 + 1] = t1; F[lane * 4 + 2] = a2; F[lane * 4 + 3] = t3;
+    F[12 + lane] = 0.0f;
+    if (lane == 0) {
+      F[15] = 1.0f;
+      c.mode = EVAL_DERIV;
+      c.compute_hessian = cs.build_hessian;
+    }
+  }
+}
+
+// Warp-parallel fast path of the controller for the case every shipped configuration takes: step_max > step_min
+// (so computeStepLengthMT performs exactly one evaluation, ndt_omp_impl.hpp:803) and the state is PH_INITIAL or
+// PH_LS_FIRST. It performs  [p += dir * a_t; convergence test; ++nr_iterations]  (:143-164), the Newton solve
+// (:127-129) by 3x3 block elimination with one matrix element per lane, and the prologue of computeStepLengthMT
+// (:761-809). Anything unusual (convergence, ill-conditioned or non-finite Hessian, zero step) returns false BEFORE any
+// solver state is written, and the scalar controller() redoes the round from scratch. Scalars are computed redundantly by every lane; lane 0 alone writes the state.
+// `warm_arrive` != nullptr selects the WARM-UP mode used while the controller warp waits for the evaluators: the same
+// instructions run on whatever the shared state currently holds, nothing of the solver state is written, and the
+// arrival counter is polled at a few checkpoints so that the pass is abandoned as soon as every evaluator has
+// arrived. Measured on B200: a cold pass costs 4.6 us (instruction fetch from L2 — the evaluator CTAs sharing the SM
+// stream their code through its instruction caches), the same pass re-executed immediately costs 2.05 us.
+#define B200_WARM_CHECKPOINT()                                                                           \
+  do {                                                                                                   \
+    if (warm_arrive) {                                                                                   \
+      unsigned seen = 0;                                                                                 \
+      if (lane == 0) seen = ld_relaxed_gpu(warm_arrive);                                                 \
+      if (__shfl_sync(0xffffffffu, seen, 0) == warm_target) return true;                                 \
+    }                                                                                                    \
+  } while (0)
+__device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, int lane, const unsigned* warm_arrive,
+                                             unsigned warm_target) {
+  const bool dry = warm_arrive != nullptr;
+  NdtState& st = cs.st;
+  const double step_max = L.step_size, step_min = L.trans_eps / 2;
+  if (L.mode != NDT_MODE_ALIGN || L.scalar_controller || !((step_max - step_min) > 0)) return false;
+  const int phase = st.phase;
+  if (phase != PH_INITIAL && phase != PH_LS_FIRST) return false;
+  const double* tot = cs.tot;
+  double* pv = cs.vec[0];   // updated pose
+  double* gv = cs.vec[1];   // gradient
+  double* dpv = cs.vec[2];  // Newton step
+  double* dirv = cs.vec[3]; // unit direction
+  int nr_it = st.nr_iterations;
+  const double a_prev = st.a_t;
+  if (!dry && phase == PH_LS_FIRST && (nr_it > L.max_iterations || (nr_it && (fabs(a_prev) < L.trans_eps)))) return false;
+  if (phase == PH_LS_FIRST) nr_it += 1;
+  // scratch fill: the full symmetric H (two elements per lane), pose and gradient (lanes 0..5)
+  double* Hs = &cs.M[0][0];  // 36 doubles: H row-major
+  double* Ai = Hs + 36;      // 9: inverse of the translation block A = H[0:3, 0:3]
+  double* Yv = cs.blk[0];    // 9: Y = A^-1 B, then [9..11]: v1 = A^-1 b1
+  double* Sv = cs.blk[1];    // 9: Schur complement S = D - B^T Y, then [9..11]: w = b2 - B^T v1
+  double* Si = cs.blk[2];    // 9: S^-1
+#pragma unroll 1
+  for (int e = lane; e < 36; e += 32) {
+    const int rr = e / 6, cc = e - rr * 6;
+    Hs[e] = tot[SLOT_H + tri_index(min(rr, cc), max(rr, cc))];
+  }
+  if (lane < 6) {
+    pv[lane] = (phase == PH_LS_FIRST) ? st.p[lane] + st.dir[lane] * a_prev : st.p[lane];
+    gv[lane] = tot[SLOT_G + lane];
+  }
+  __syncwarp();
+  double amax = 0.0;
+  bool finite = true;
+#pragma unroll 1
+  for (int e = lane; e < 36; e += 32) {
+    const double v = fabs(Hs[e]);
+    finite = finite && (v <= 1.7e308);  // false for NaN / inf
+    amax = fmax(amax, v);
+  }
+#pragma unroll 1
+  for (int d = 16; d > 0; d >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, d));
+  if (!__all_sync(0xffffffffu, finite) || !(amax > 0.0)) return false;
+  B200_WARM_CHECKPOINT();
+  // Newton system H x = -g solved by block elimination on the 3x3 blocks  H = [A B; B^T D]  with closed-form 3x3
+  // inverses, one matrix element per lane (the same x as JacobiSVD::solve whenever both A and the Schur complement are
+  // well conditioned; otherwise → scalar path: pivoted LU, then SVD).
+  const int i3 = lane / 3 % 3, j3 = lane % 3;                      // element (i3, j3) of a 3x3 for lanes 0..8
+  const int ja = (j3 + 1) % 3, jb = (j3 + 2) % 3, ia = (i3 + 1) % 3, ib = (i3 + 2) % 3;
+  {
+    // adj(A)(i,j) = A(j+1,i+1) A(j+2,i+2) - A(j+1,i+2) A(j+2,i+1)   (indices mod 3)
+    const double adj = Hs[ja * 6 + ia] * Hs[jb * 6 + ib] - Hs[ja * 6 + ib] * Hs[jb * 6 + ia];
+    const double det = Hs[0] * (Hs[7] * Hs[14] - Hs[8] * Hs[13]) - Hs[1] * (Hs[6] * Hs[14] - Hs[8] * Hs[12]) +
+                       Hs[2] * (Hs[6] * Hs[13] - Hs[7] * Hs[12]);
+    const double sc = fmax(fmax(fabs(Hs[0]), fabs(Hs[7])), fabs(Hs[14]));
+    if (!(fabs(det) > 1e-9 * sc * sc * sc)) return false;
+    if (lane < 9) Ai[lane] = adj * ddiv(1.0, det);
+  }
+  __syncwarp();
+  if (lane < 9) {  // Y = A^-1 B
+    Yv[lane] = Ai[i3 * 3 + 0] * Hs[0 * 6 + 3 + j3] + Ai[i3 * 3 + 1] * Hs[1 * 6 + 3 + j3] + Ai[i3 * 3 + 2] * Hs[2 * 6 + 3 + j3];
+  } else if (lane < 12) {  // v1 = A^-1 b1,  b1 = -g[0:3]
+    const int i = lane - 9;
+    Yv[lane] = -(Ai[i * 3 + 0] * gv[0] + Ai[i * 3 + 1] * gv[1] + Ai[i * 3 + 2] * gv[2]);
+  }
+  __syncwarp();
+  B200_WARM_CHECKPOINT();
+  if (lane < 9) {  // S = D - B^T Y
+    Sv[lane] = Hs[(3 + i3) * 6 + 3 + j3] - (Hs[0 * 6 + 3 + i3] * Yv[0 * 3 + j3] + Hs[1 * 6 + 3 + i3] * Yv[1 * 3 + j3] + Hs[2 * 6 + 3 + i3] * Yv[2 * 3 + j3]);
+  } else if (lane < 12) {  // w = b2 - B^T v1,  b2 = -g[3:6]
+    const int i = lane - 9;
+    Sv[lane] = -gv[3 + i] - (Hs[0 * 6 + 3 + i] * Yv[9] + Hs[1 * 6 + 3 + i] * Yv[10] + Hs[2 * 6 + 3 + i] * Yv[11]);
+  }
+  __syncwarp();
+  B200_WARM_CHECKPOINT();
+  {
+    const double adj = Sv[ja * 3 + ia] * Sv[jb * 3 + ib] - Sv[ja * 3 + ib] * Sv[jb * 3 + ia];
+    const double det = Sv[0] * (Sv[4] * Sv[8] - Sv[5] * Sv[7]) - Sv[1] * (Sv[3] * Sv[8] - Sv[5] * Sv[6]) +
+                       Sv[2] * (Sv[3] * Sv[7] - Sv[4] * Sv[6]);
+    const double sc = fmax(fmax(fabs(Sv[0]), fabs(Sv[4])), fabs(Sv[8]));
+    if (!(fabs(det) > 1e-9 * sc * sc * sc)) return false;
+    if (lane < 9) Si[lane] = adj * ddiv(1.0, det);
+  }
+  __syncwarp();
+  if (lane < 3) dpv[3 + lane] = Si[lane * 3 + 0] * Sv[9] + Si[lane * 3 + 1] * Sv[10] + Si[lane * 3 + 2] * Sv[11];  // x2 = S^-1 w
+  __syncwarp();
+  if (lane < 3) dpv[lane] = Yv[9 + lane] - (Yv[lane * 3 + 0] * dpv[3] + Yv[lane * 3 + 1] * dpv[4] + Yv[lane * 3 + 2] * dpv[5]);  // x1
+  __syncwarp();
+  B200_WARM_CHECKPOINT();
+  double n2 = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; i++) n2 += dpv[i] * dpv[i];
+  const double norm = dsqrt(n2);
+  if (norm == 0 || norm != norm) return false;
+  if (lane < 6) dirv[lane] = ddiv(dpv[lane], norm);
+  __syncwarp();
+  double dd = 0.0;
+#pragma unroll 1
+  for (int k = 0; k < 6; k++) dd += gv[k] * dirv[k];
+  double d_phi_0 = -dd;
+  double sgn = 1.0;
+  if (d_phi_0 >= 0) {
+    if (d_phi_0 == 0) return false;
+    d_phi_0 *= -1;
+    sgn = -1.0;
+  }
+  double a_t = norm;
+  a_t = fmin(a_t, step_max);
+  a_t = fmax(a_t, step_min);
+  // ---- write phase ----
+  if (dry) return true;
+  const double score = tot[SLOT_SCORE];
+  if (lane < 6) {
+    const double d = dirv[lane] * sgn;
+    st.p[lane] = pv[lane];
+    st.g[lane] = gv[lane];
+    st.dir[lane] = d;
+    st.x_t[lane] = pv[lane] + d * a_t;
+  }
+  if (lane == 0) {
+    const long long hits = (long long)(tot[SLOT_HITS] + 0.5);
+    st.score = score;
+    st.hits_last = hits;
+    st.hits_total += hits;
+    st.evaluations += 1;
+    st.nr_iterations = nr_it;
+    st.phi_0 = -score;
+    st.d_phi_0 = d_phi_0;
+    st.a_t = a_t;
+    st.step_iterations = 0;
+    st.interval_converged = 1;
+    st.open_interval = 1;
+    st.phase = PH_LS_FIRST;
+    cs.build = 1;
+    cs.build_hessian = 1;
+    cs.build_f64 = 0;
+  }
+  return true;
+}
+
+__device__ __forceinline__ void load_totals(NdtState& st, const double* tot, bool with_hessian) {
   st.score = tot[SLOT_SCORE];
+#pragma unroll
   for (int k = 0; k < 6; k++) st.g[k] = tot[SLOT_G + k];
+#pragma unroll
   for (int i = 0; i < 6; i++)
+#pragma unroll
     for (int j = i; j < 6; j++) {
       double v = with_hessian ? tot[SLOT_H + tri_index(i, j)] : 0.0;
       st.H[i * 6 + j] = v;
@@ -275,41 +612,50 @@ __device__ void load_totals(NdtState& st, const double* tot, bool with_hessian) 
   st.evaluations += 1;
 }
 
-__device__ void finish(const NdtLaunch& L, NdtSolverWork* W) {
-  NdtState& st = W->state;
-  NdtResult& r = W->result;
-  for (int k = 0; k < 16; k++) r.final_T[k] = st.final_T[k];
-  r.score = st.score;
-  r.trans_probability = st.score / (double)L.n_src;  // ndt_omp_impl.hpp:136,170
-  for (int k = 0; k < 6; k++) r.g[k] = st.g[k];
-  for (int k = 0; k < 36; k++) r.H[k] = st.H[k];
-  r.hits_last = st.hits_last;
-  r.hits_total = st.hits_total;
-  r.converged = st.converged;
-  r.iterations = st.nr_iterations;
-  r.evaluations = st.evaluations;
-  r.error = 0;
-  W->control.mode = EVAL_DONE;
+__device__ void finish(const NdtLaunch& L, CtlShared& cs, NdtSolverWork* W, int lane) {
+  NdtState& st = cs.st;
+  if (lane == 0) {
+    NdtResult& r = W->result;
+    for (int k = 0; k < 16; k++) r.final_T[k] = st.final_T[k];
+    r.score = st.score;
+    r.trans_probability = st.score / (double)L.n_src;  // ndt_omp_impl.hpp:136,170
+    for (int k = 0; k < 6; k++) r.g[k] = st.g[k];
+    for (int k = 0; k < 36; k++) r.H[k] = st.H[k];
+    r.hits_last = st.hits_last;
+    r.hits_total = st.hits_total;
+    r.converged = st.converged;
+    r.iterations = st.nr_iterations;
+    r.evaluations = st.evaluations;
+    r.error = 0;
+  }
+  cs.next.mode = EVAL_DONE;
+  cs.done = 1;
 }
 
-__device__ __noinline__ void controller(const NdtLaunch& L, NdtSolverWork* W, const double* tot) {
-  NdtState& st = W->state;
+// One controller step, executed by ONE thread (lane 0 of warp 0 of the controller CTA): consumes the totals of the
+// evaluation that just finished and either requests the control block of the next pose (cs.build) or finishes.
+__device__ __noinline__ void controller(const NdtLaunch& L, CtlShared& cs, NdtSolverWork* W) {
+  const int lane = 0;
+  cs.build = 0;
+  NdtState& st = cs.st;
+  const double* tot = cs.tot;
   const double mu = 1.e-4, nu = 0.9;  // ndt_omp_impl.hpp:788-790
   const double step_max = L.step_size, step_min = L.trans_eps / 2;
-  enum { ACT_NEWTON_BEGIN, ACT_NEWTON_END, ACT_LS_CHECK, ACT_RETURN };
+  enum { ACT_NEWTON_BEGIN, ACT_NEWTON_END, ACT_LS_CHECK };
   int act;
   double phi_t = 0, d_phi_t = 0, psi_t = 0, d_psi_t = 0;
 
   if (L.mode != NDT_MODE_ALIGN) {  // single derivative pass requested through the C-ABI
     load_totals(st, tot, L.init.compute_hessian != 0);
     st.converged = 0;
-    finish(L, W);
+    finish(L, cs, W, lane);
     return;
   }
 
   auto eval_point_values = [&]() {
     phi_t = -st.score;
     double dd = 0;
+#pragma unroll
     for (int k = 0; k < 6; k++) dd += st.g[k] * st.dir[k];
     d_phi_t = -dd;
     psi_t = mt_psi(st.a_t, phi_t, st.phi_0, st.d_phi_0, mu);
@@ -336,10 +682,12 @@ __device__ __noinline__ void controller(const NdtLaunch& L, NdtSolverWork* W, co
         st.f_u = st.f_u + st.phi_0 - mu * st.d_phi_0 * st.a_u;
         st.g_u = st.g_u + mu * st.d_phi_0;
       }
-      if (st.open_interval)
-        st.interval_converged = mt_update_interval(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, psi_t, d_psi_t);
-      else
-        st.interval_converged = mt_update_interval(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, phi_t, d_phi_t);
+      {
+        double a_l = st.a_l, f_l = st.f_l, g_l = st.g_l, a_u = st.a_u, f_u = st.f_u, g_u = st.g_u;
+        if (st.open_interval) st.interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, st.a_t, psi_t, d_psi_t);
+        else st.interval_converged = mt_update_interval(a_l, f_l, g_l, a_u, f_u, g_u, st.a_t, phi_t, d_phi_t);
+        st.a_l = a_l; st.f_l = f_l; st.g_l = g_l; st.a_u = a_u; st.f_u = f_u; st.g_u = g_u;
+      }
       st.step_iterations++;
       act = ACT_LS_CHECK;
       break;
@@ -352,32 +700,36 @@ __device__ __noinline__ void controller(const NdtLaunch& L, NdtSolverWork* W, co
     if (act == ACT_LS_CHECK) {
       // :834
       if (!st.interval_converged && st.step_iterations < 10 && !(psi_t <= 0 && d_phi_t <= -nu * st.d_phi_0)) {
-        if (st.open_interval)
-          st.a_t = mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, psi_t, d_psi_t);
-        else
-          st.a_t = mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, phi_t, d_phi_t);
-        st.a_t = fmin(st.a_t, step_max);
-        st.a_t = fmax(st.a_t, step_min);
-        for (int k = 0; k < 6; k++) st.x_t[k] = st.p[k] + st.dir[k] * st.a_t;
-        write_control(W, st.x_t, 0, true);
+        double a_t;
+        if (st.open_interval) a_t = mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, psi_t, d_psi_t);
+        else a_t = mt_trial_value(st.a_l, st.f_l, st.g_l, st.a_u, st.f_u, st.g_u, st.a_t, phi_t, d_phi_t);
+        a_t = fmin(a_t, step_max);
+        a_t = fmax(a_t, step_min);
+        st.a_t = a_t;
+#pragma unroll
+        for (int k = 0; k < 6; k++) st.x_t[k] = st.p[k] + st.dir[k] * a_t;
+        cs.build = 1;
+        cs.build_hessian = 0;
+        cs.build_f64 = 1;
         st.phase = PH_LS_ITER;
         return;
       }
       if (st.step_iterations) {  // :912-913 — needs the f64 radius-neighbourhood Hessian (K2): leave the kernel
         st.phase = PH_LS_HESSIAN;
-        W->control.mode = EVAL_NEED_HESSIAN;
-        W->result.error = 100;  // host: run the K2 pass, then resume
+        cs.next.mode = EVAL_NEED_HESSIAN;
+        cs.done = 2;
         return;
       }
       act = ACT_NEWTON_END;
     }
     if (act == ACT_NEWTON_END) {
       // :143-164
+#pragma unroll
       for (int k = 0; k < 6; k++) st.p[k] = st.p[k] + st.dir[k] * st.a_t;
       if (st.nr_iterations > L.max_iterations || (st.nr_iterations && (fabs(st.a_t) < L.trans_eps))) st.converged = 1;
       st.nr_iterations++;
       if (st.converged) {
-        finish(L, W);
+        finish(L, cs, W, lane);
         return;
       }
       act = ACT_NEWTON_BEGIN;
@@ -385,69 +737,218 @@ __device__ __noinline__ void controller(const NdtLaunch& L, NdtSolverWork* W, co
     if (act == ACT_NEWTON_BEGIN) {
       // :127-142 and the prologue of computeStepLengthMT :761-821
       double neg_g[6], dp[6];
+#pragma unroll
       for (int k = 0; k < 6; k++) neg_g[k] = -st.g[k];
-      solve6(st.H, neg_g, dp);
+      if (!lu_solve6(st.H, neg_g, dp)) solve6_svd(st.H, neg_g, dp);
       double n2 = 0;
+#pragma unroll
       for (int k = 0; k < 6; k++) n2 += dp[k] * dp[k];
       const double norm = sqrt(n2);
       if (norm == 0 || norm != norm) {
         st.converged = (norm == norm) ? 1 : 0;
-        finish(L, W);
+        finish(L, cs, W, lane);
         return;
       }
-      for (int k = 0; k < 6; k++) st.dir[k] = dp[k] / norm;
+      double dir[6];
+#pragma unroll
+      for (int k = 0; k < 6; k++) dir[k] = dp[k] / norm;
       st.phi_0 = -st.score;
       double dd = 0;
-      for (int k = 0; k < 6; k++) dd += st.g[k] * st.dir[k];
-      st.d_phi_0 = -dd;
-      if (st.d_phi_0 >= 0) {
-        if (st.d_phi_0 == 0) {  // :771-772: zero step, no evaluation
-          st.a_t = 0;
-          act = ACT_NEWTON_END;
-          continue;
+#pragma unroll
+      for (int k = 0; k < 6; k++) dd += st.g[k] * dir[k];
+      double d_phi_0 = -dd;
+      bool zero_step = false;
+      if (d_phi_0 >= 0) {
+        if (d_phi_0 == 0) {
+          zero_step = true;  // :771-772: zero step, no evaluation
+        } else {
+          d_phi_0 *= -1;
+#pragma unroll
+          for (int k = 0; k < 6; k++) dir[k] *= -1;
         }
-        st.d_phi_0 *= -1;
-        for (int k = 0; k < 6; k++) st.dir[k] *= -1;
+      }
+#pragma unroll
+      for (int k = 0; k < 6; k++) st.dir[k] = dir[k];
+      st.d_phi_0 = d_phi_0;
+      if (zero_step) {
+        st.a_t = 0;
+        act = ACT_NEWTON_END;
+        continue;
       }
       st.step_iterations = 0;
       st.a_l = 0;
       st.a_u = 0;
-      st.f_l = mt_psi(st.a_l, st.phi_0, st.phi_0, st.d_phi_0, mu);
-      st.g_l = mt_dpsi(st.d_phi_0, st.d_phi_0, mu);
-      st.f_u = mt_psi(st.a_u, st.phi_0, st.phi_0, st.d_phi_0, mu);
-      st.g_u = mt_dpsi(st.d_phi_0, st.d_phi_0, mu);
+      st.f_l = mt_psi(0.0, st.phi_0, st.phi_0, d_phi_0, mu);
+      st.g_l = mt_dpsi(d_phi_0, d_phi_0, mu);
+      st.f_u = st.f_l;
+      st.g_u = st.g_l;
       st.interval_converged = (step_max - step_min) > 0 ? 1 : 0;  // :803 (sic)
       st.open_interval = 1;
-      st.a_t = norm;
-      st.a_t = fmin(st.a_t, step_max);
-      st.a_t = fmax(st.a_t, step_min);
-      for (int k = 0; k < 6; k++) st.x_t[k] = st.p[k] + st.dir[k] * st.a_t;
-      write_control(W, st.x_t, 1, !st.interval_converged);
+      double a_t = norm;
+      a_t = fmin(a_t, step_max);
+      a_t = fmax(a_t, step_min);
+      st.a_t = a_t;
+#pragma unroll
+      for (int k = 0; k < 6; k++) st.x_t[k] = st.p[k] + dir[k] * a_t;
+      cs.build = 1;
+      cs.build_hessian = 1;
+      cs.build_f64 = st.interval_converged ? 0 : 1;
       st.phase = PH_LS_FIRST;
       return;
     }
   }
-  // unreachable in practice (two consecutive zero-step iterations terminate); fail safe
-  st.converged = 0;
-  finish(L, W);
+  st.converged = 0;  // unreachable in practice (two consecutive zero-step iterations terminate); fail safe
+  finish(L, cs, W, lane);
+}
+
+// =====================================================================================================
+// controller CTA
+// =====================================================================================================
+__device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, double (*warp_part)[SLOT_COUNT]) {
+  NdtSolverWork* W = L.work;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned n_eval = gridDim.x - 1;
+  unsigned my_gen = 0;
+  if (tid == 0) my_gen = ld_relaxed_gpu(&W->gen);
+
+  // state: fresh, or restored from global after a K2 pass
+  if (L.resume) {
+    const int* src = reinterpret_cast<const int*>(&W->state);
+    int* dst = reinterpret_cast<int*>(&cs.st);
+    for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += SOLVER_THREADS) dst[k] = __ldcg(src + k);
+  } else if (tid == 0) {
+    NdtState& st = cs.st;
+    for (int k = 0; k < 6; k++) st.p[k] = L.p0[k];
+    for (int k = 0; k < 16; k++) st.final_T[k] = L.init_final[k];
+    st.phase = PH_INITIAL;
+    st.nr_iterations = 0;
+    st.evaluations = 0;
+    st.converged = 0;
+    st.hits_total = 0;
+    st.hits_last = 0;
+    st.step_iterations = 0;
+    st.a_t = 0;
+    W->result.error = 2;  // "not finished"; finish() sets 0, the watchdog 1, a K2 request 100
+  }
+  if (tid == 0) cs.done = 0;
+  if (tid < 69) cs.code[tid] = kAngleTableCode[tid];
+  __syncthreads();
+
+  for (int round = 0;; round++) {
+    // ---- wait until every evaluator CTA has published its partial ------------------------------------------
+    if (warp == 0) {
+      // Wait for the evaluators. While waiting, keep THIS warp's instruction path warm by executing the controller
+      // step and the control-block build in warm-up mode (see controller_fast): the real pass then runs from the
+      // instruction caches instead of fetching ~14 KB of code from L2.
+      const long long t0 = clock64();
+      for (;;) {
+        unsigned seen = 0;
+        if (lane == 0) seen = ld_relaxed_gpu(&W->arrive);
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        if (seen == n_eval) break;
+        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+          if (lane == 0) {
+            W->result.error = 1;
+            cs.done = 3;
+          }
+          break;
+        }
+        if (!L.scalar_controller && L.mode == NDT_MODE_ALIGN) {
+          (void)controller_fast(L, cs, lane, &W->arrive, n_eval);
+          __syncwarp();
+          build_control(cs, lane, &W->arrive, n_eval);
+          __syncwarp();
+        }
+      }
+      if (lane == 0) {
+        fence_acq_rel_gpu();
+        B200_STAMP(true, round, 4);
+      }
+    }
+    __syncthreads();
+    if (cs.done == 3) break;
+    // ---- fixed-order f64 reduction of the partials (8 row groups x 32 columns, 4 loads in flight) -----------
+    {
+      double s = 0;
+      int r = warp;
+      for (; r < (int)n_eval; r += 16 * SOLVER_WARPS) {  // 16 independent L2 loads in flight, fixed summation order
+        double v[16];
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+          const int row = r + u * SOLVER_WARPS;
+          v[u] = row < (int)n_eval ? __ldcg(&W->partials[row][lane]) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) s += v[u];
+      }
+      warp_part[warp][lane] = s;
+    }
+    __syncthreads();
+    if (tid < SLOT_COUNT) {
+      double t = 0;
+#pragma unroll
+      for (int w = 0; w < SOLVER_WARPS; w++) t += warp_part[w][tid];
+      cs.tot[tid] = t;
+    }
+    __syncthreads();
+    B200_STAMP(tid == 0, round, 5);
+    // ---- controller step (warp 0, uniform) + publication of the next control block -----------------------------
+    if (warp == 0) {
+      if (lane == 0) cs.build = 0;
+      __syncwarp();
+      const bool handled = controller_fast(L, cs, lane, nullptr, 0u);  // warp-uniform result
+      if (!handled && lane == 0) controller(L, cs, W);
+      __syncwarp();
+      if (cs.build) build_control(cs, lane, nullptr, 0u);
+      __syncwarp();
+      const int* src = reinterpret_cast<const int*>(&cs.next);
+      int* dst = reinterpret_cast<int*>(&W->control);
+      for (int k = lane; k < NDT_CONTROL_WORDS; k += 32) dst[k] = src[k];
+      B200_STAMP(lane == 0, round, 6);
+      __syncwarp();
+      if (lane == 0) {
+        W->arrive = 0;
+        st_release_gpu(&W->gen, my_gen + 1);  // release: orders the control block and the counter reset
+        my_gen += 1;
+      }
+    }
+    __syncthreads();
+    if (cs.done) break;
+  }
+  if (cs.done == 2) {  // leaving for a K2 pass: park the state in global memory
+    const int* src = reinterpret_cast<const int*>(&cs.st);
+    int* dst = reinterpret_cast<int*>(&W->state);
+    for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += SOLVER_THREADS) dst[k] = src[k];
+    if (tid == 0) W->result.error = 100;
+  }
 }
 
 // =====================================================================================================
 // the persistent kernel
 // =====================================================================================================
 template <int METHOD>
-__global__ void __launch_bounds__(SOLVER_THREADS, 2) ndt_solver_kernel(const __grid_constant__ NdtLaunch L) {
+__global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_kernel(const __grid_constant__ NdtLaunch L) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
-  __shared__ SharedCtl sc;
   __shared__ double warp_part[SOLVER_WARPS][SLOT_COUNT];
-  __shared__ double tot[SLOT_COUNT];
-  __shared__ __align__(8) unsigned long long tma_bar;
 
   NdtSolverWork* W = L.work;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const RankWord* sidx = reinterpret_cast<const RankWord*>(dyn_smem);
 
-  // ---- stage the voxel rank index into shared memory with TMA bulk copies (once per launch) -------------
+  if (blockIdx.x == gridDim.x - 1) {  // ---- the controller CTA ----
+    CtlShared& cs = *reinterpret_cast<CtlShared*>(dyn_smem);
+    controller_cta(L, cs, warp_part);
+    return;
+  }
+
+  // ---- evaluator CTAs --------------------------------------------------------------------------------------
+  __shared__ __align__(16) NdtControl ctl;
+  __shared__ int abort_flag;
+  __shared__ __align__(8) unsigned long long tma_bar;
+  __shared__ float acc_s[ACC_SLOTS][ACC_STRIDE];
+  __shared__ float4 pts_s[SMEM_POINTS];
+  const RankWord* idx = L.index_in_smem ? reinterpret_cast<const RankWord*>(dyn_smem) : L.index;
+
+  // stage the voxel rank index into shared memory with TMA bulk copies (once per launch)
   if (L.index_in_smem) {
     const unsigned bytes = ((unsigned)L.geom.n_words * 8u + 15u) & ~15u;
     if (tid == 0) {
@@ -462,73 +963,88 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) ndt_solver_kernel(const __g
         tma_bulk_g2s(dyn_smem + off, reinterpret_cast<const unsigned char*>(L.index) + off, chunk, &tma_bar);
       }
     }
+  }
+
+  // this CTA's contiguous chunk of source points, staged once into shared memory for the whole solve
+  const int n_eval = gridDim.x - 1;
+  const int chunk = (L.n_src + n_eval - 1) / n_eval;
+  const int begin = blockIdx.x * chunk;
+  const int end = min(L.n_src, begin + chunk);
+  const int n_staged = max(0, min(end - begin, SMEM_POINTS));
+  for (int i = tid; i < n_staged; i += SOLVER_THREADS) pts_s[i] = L.src[begin + i];
+
+  unsigned my_gen = 0;
+  if (tid == 0) {
+    my_gen = ld_relaxed_gpu(&W->gen);
+    abort_flag = 0;
+  }
+  {  // round-0 control: from the launch parameters (fresh solve) or from the work area (resume after K2)
+    const int* src = L.resume ? reinterpret_cast<const int*>(&W->control) : reinterpret_cast<const int*>(&L.init);
+    int* dst = reinterpret_cast<int*>(&ctl);
+    for (int k = tid; k < NDT_CONTROL_WORDS; k += SOLVER_THREADS) dst[k] = L.resume ? __ldcg(src + k) : src[k];
+  }
+  if (L.index_in_smem) {
     long long t0 = clock64();
     while (!mbar_try_wait(&tma_bar, 0)) {
       if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) break;
     }
   }
-
-  unsigned my_gen = 0;
-  if (tid == 0) {
-    my_gen = ld_relaxed_gpu(&W->gen);
-    sc.abort = 0;
-    sc.is_last = 0;
-  }
-  // round-0 control: from the launch parameters (fresh solve) or from the work area (resume after K2)
-  {
-    const int* src = L.resume ? reinterpret_cast<const int*>(&W->control) : reinterpret_cast<const int*>(&L.init);
-    int* dst = reinterpret_cast<int*>(&sc.c);
-    for (int k = tid; k < NDT_CONTROL_WORDS; k += SOLVER_THREADS) dst[k] = L.resume ? __ldcg(src + k) : src[k];
-  }
-  if (!L.resume && blockIdx.x == 0 && tid == 0) {
-    // fresh controller state; only the CTA that later runs the controller reads it, after a grid barrier
-    NdtState& st = W->state;
-    for (int k = 0; k < 6; k++) st.p[k] = L.p0[k];
-    for (int k = 0; k < 16; k++) st.final_T[k] = L.init_final[k];
-    st.phase = PH_INITIAL;
-    st.nr_iterations = 0;
-    st.evaluations = 0;
-    st.converged = 0;
-    st.hits_total = 0;
-    st.hits_last = 0;
-    st.step_iterations = 0;
-    st.a_t = 0;
-    W->result.error = 2;  // "not finished"; finish() sets 0, the watchdog 1, a K2 request 100
-  }
   bool skip_eval = L.resume != 0;
+  const bool stamp0 = (blockIdx.x == 0 && tid == 0);
+  const float gd2 = (float)L.d2;
 
-  for (;;) {
+  for (int round = 0;; round++) {
     __syncthreads();
-    if (sc.c.mode != EVAL_DERIV || sc.abort) break;
+    if (ctl.mode != EVAL_DERIV || abort_flag) break;
+    B200_STAMP(stamp0, round, 0);
+    const unsigned long long t_round = (L.timing && tid == 0) ? globaltimer_ns() : 0ull;
 
     // ---- (1) evaluate this CTA's points ---------------------------------------------------------------
     Accum acc;
-#pragma unroll
-    for (int k = 0; k < 6; k++) acc.g[k] = 0.f;
-#pragma unroll
-    for (int k = 0; k < 21; k++) acc.h[k] = 0.f;
+    acc.s = acc_s;
+    acc.tid = tid;
+    acc.first = true;
     acc.score = 0.0;
     acc.hits = 0;
     if (!skip_eval) {
-      if (L.index_in_smem) evaluate<METHOD, true>(L, sc, sidx, acc);
-      else evaluate<METHOD, false>(L, sc, sidx, acc);
+      if (ctl.compute_hessian) {
+        for (int i = tid; i < n_staged; i += SOLVER_THREADS) process_point<METHOD, true>(L, ctl, idx, pts_s[i], gd2, acc);
+        for (int i = begin + SMEM_POINTS + tid; i < end; i += SOLVER_THREADS)
+          process_point<METHOD, true>(L, ctl, idx, L.src[i], gd2, acc);
+      } else {
+        for (int i = tid; i < n_staged; i += SOLVER_THREADS) process_point<METHOD, false>(L, ctl, idx, pts_s[i], gd2, acc);
+        for (int i = begin + SMEM_POINTS + tid; i < end; i += SOLVER_THREADS)
+          process_point<METHOD, false>(L, ctl, idx, L.src[i], gd2, acc);
+      }
     }
     skip_eval = false;
+    B200_STAMP(stamp0, round, 1);
+    if (L.timing && tid == 0 && round == 2) W->cta_eval_ns[blockIdx.x] = (unsigned)(globaltimer_ns() - t_round);
 
-    // ---- (2) warp butterfly in f64, CTA partial --------------------------------------------------------
+    // ---- (2) per-warp reduction: lane L sums slot L over the warp's 32 columns in fixed order (f64), CTA partial --
+    if (acc.first) {
+#pragma unroll
+      for (int k = 0; k < ACC_SLOTS; k++) acc_s[k][tid] = 0.f;
+    }
+    double sc = acc.score, hc = (double)acc.hits;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      sc += __shfl_xor_sync(0xffffffffu, sc, d);
+      hc += __shfl_xor_sync(0xffffffffu, hc, d);
+    }
+    __syncwarp();
     {
-      double v[SLOT_COUNT];
-      v[SLOT_SCORE] = acc.score;
-#pragma unroll
-      for (int k = 0; k < 6; k++) v[SLOT_G + k] = (double)acc.g[k];
-#pragma unroll
-      for (int k = 0; k < 21; k++) v[SLOT_H + k] = (double)acc.h[k];
-      v[SLOT_HITS] = (double)acc.hits;
-      v[29] = 0.0;
-      v[30] = 0.0;
-      v[31] = 0.0;
-      Butterfly<32, 16>::run(v, lane);
-      warp_part[warp][lane] = v[0];
+      double v = 0.0;
+      if (lane >= SLOT_G && lane < SLOT_G + ACC_SLOTS) {
+        const float* row = &acc_s[lane - SLOT_G][warp * 32];
+#pragma unroll 8
+        for (int t = 0; t < 32; t++) v += (double)row[t];
+      } else if (lane == SLOT_SCORE) {
+        v = sc;
+      } else if (lane == SLOT_HITS) {
+        v = hc;
+      }
+      warp_part[warp][lane] = v;
     }
     __syncthreads();
     if (tid < SLOT_COUNT) {
@@ -538,51 +1054,28 @@ __global__ void __launch_bounds__(SOLVER_THREADS, 2) ndt_solver_kernel(const __g
       W->partials[blockIdx.x][tid] = s;
     }
     __syncthreads();
+    B200_STAMP(stamp0, round, 2);
 
-    // ---- (3) grid barrier; the last CTA to arrive reduces and runs the controller -----------------------
+    // ---- (3) arrive (release) and wait for the controller CTA to publish the next control block ------------
     if (tid == 0) {
-      __threadfence();
-      unsigned prev = atom_add_acq_rel_gpu(&W->arrive, 1u);
-      sc.is_last = (prev == gridDim.x - 1) ? 1 : 0;
-    }
-    __syncthreads();
-    if (sc.is_last) {
-      __threadfence();
-      double s = 0;
-      for (int r = warp; r < (int)gridDim.x; r += SOLVER_WARPS) s += __ldcg(&W->partials[r][lane]);
-      warp_part[warp][lane] = s;
-      __syncthreads();
-      if (tid < SLOT_COUNT) {
-        double t = 0;
-#pragma unroll
-        for (int w = 0; w < SOLVER_WARPS; w++) t += warp_part[w][tid];
-        tot[tid] = t;
-      }
-      __syncthreads();
-      if (tid == 0) {
-        controller(L, W, tot);
-        W->arrive = 0;
-        __threadfence();
-        st_release_gpu(&W->gen, my_gen + 1);
-      }
-    } else if (tid == 0) {
+      red_add_release_gpu(&W->arrive, 1u);
+      B200_STAMP(stamp0, round, 3);
       long long t0 = clock64();
       while (ld_relaxed_gpu(&W->gen) == my_gen) {
         if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
-          atomicExch(&W->error, 1u);
           W->result.error = 1;
-          sc.abort = 1;
+          abort_flag = 1;
           break;
         }
       }
       fence_acq_rel_gpu();
+      my_gen += 1;
+      B200_STAMP(stamp0, round, 7);
     }
-    if (tid == 0) my_gen += 1;
     __syncthreads();
-    // ---- (4) next round's control block (written by the controller; read through L2) --------------------
-    {
+    {  // next round's control block (written by the controller CTA; read through L2)
       const int* src = reinterpret_cast<const int*>(&W->control);
-      int* dst = reinterpret_cast<int*>(&sc.c);
+      int* dst = reinterpret_cast<int*>(&ctl);
       for (int k = tid; k < NDT_CONTROL_WORDS; k += SOLVER_THREADS) dst[k] = __ldcg(src + k);
     }
   }
@@ -623,6 +1116,13 @@ void NdtSolver::init(int device, cudaStream_t s) {
     B200_CUDA(cudaFuncSetAttribute(kernel_for(m), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
 }
 
+void NdtSolver::read_cta_eval_ns(unsigned* out, int n) const {
+  B200_CUDA(cudaMemcpy(out, d_work_->cta_eval_ns, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+}
+void NdtSolver::read_timing(unsigned long long* out) const {
+  B200_CUDA(cudaMemcpy(out, d_work_->timing, sizeof(unsigned long long) * NDT_TIMING_ROUNDS * NDT_TIMING_SLOTS,
+                       cudaMemcpyDeviceToHost));
+}
 const double* NdtSolver::state_jd() const { return d_work_->state.jd; }
 const double* NdtSolver::state_hd() const { return d_work_->state.hd; }
 const float* NdtSolver::control_T() const { return d_work_->control.T; }
@@ -646,6 +1146,8 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   L.search_method = cfg.search_method;
   L.mode = mode;
   L.resume = resume;
+  L.timing = timing_enabled ? 1 : 0;
+  L.scalar_controller = scalar_controller ? 1 : 0;
   L.max_iterations = cfg.max_iterations;
   L.resolution = cfg.resolution;
   L.radius2 = static_cast<float>((double)cfg.resolution * (double)cfg.resolution);
@@ -684,15 +1186,19 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   // shared-memory staging of the rank index when it fits
   const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 15) & ~(size_t)15;
   L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= 64 * 1024) ? 1 : 0;
-  const size_t dyn_smem = L.index_in_smem ? index_bytes : 0;
+  size_t dyn_smem = std::max(L.index_in_smem ? index_bytes : (size_t)0, sizeof(CtlShared));
+  dyn_smem = (dyn_smem + 15) & ~(size_t)15;
 
   KernelFn fn = kernel_for(cfg.search_method);
   int per_sm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SOLVER_THREADS, dyn_smem));
   if (per_sm < 1) throw CudaError("ndt_solver_kernel does not fit on an SM");
-  int max_ctas = std::min(per_sm * sm_count_, NDT_MAX_CTAS);
-  int want = (int)((n_src + SOLVER_THREADS - 1) / SOLVER_THREADS);
-  grid_ = std::max(1, std::min(max_ctas, want));
+  const int max_ctas = std::min(per_sm * sm_count_, NDT_MAX_CTAS);
+  // evaluator CTAs: one point per thread when the scan is small; otherwise every resident slot, so that each SM gets
+  // the same number of points (the evaluation is issue-bound per SM)
+  const int want = (int)((n_src + SOLVER_THREADS - 1) / SOLVER_THREADS);
+  const int n_eval = (want + 1 > sm_count_) ? (max_ctas - 1) : std::max(1, want);
+  grid_ = n_eval + 1;  // + the controller CTA
   block_ = SOLVER_THREADS;
   index_in_smem_ = L.index_in_smem;
 

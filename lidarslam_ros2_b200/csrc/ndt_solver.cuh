@@ -38,6 +38,10 @@ struct NdtState {
   int phase, nr_iterations, evaluations, converged;
 };
 
+constexpr int NDT_TIMING_ROUNDS = 48;
+constexpr int NDT_TIMING_SLOTS = 10;
+// slots (globaltimer ns): 0 CTA0 round start, 1 CTA0 after evaluate, 2 CTA0 partial written, 3 CTA0 arrived,
+//                         4 last CTA detected, 5 partials reduced, 6 controller done, 7 CTA0 released
 struct NdtSolverWork {
   unsigned arrive;
   unsigned gen;
@@ -47,6 +51,8 @@ struct NdtSolverWork {
   NdtState state;
   NdtResult result;
   double partials[NDT_MAX_CTAS][SLOT_COUNT];
+  unsigned long long timing[NDT_TIMING_ROUNDS][NDT_TIMING_SLOTS];
+  unsigned cta_eval_ns[NDT_MAX_CTAS];  // timing mode: evaluate duration of every CTA in round 2
 };
 
 struct NdtLaunch {
@@ -61,6 +67,8 @@ struct NdtLaunch {
   int n_voxels;
   int search_method;
   int mode;    // NdtMode
+  int scalar_controller;  // 1: disable the warp-parallel controller fast path (developer switch)
+  int timing;  // 1: record per-phase globaltimer stamps into work->timing (developer instrumentation)
   int resume;  // 1: state/control already in work (after a K2 pass); first round skips the evaluation
   int index_in_smem;
   int max_iterations;
@@ -101,5 +109,13 @@ __device__ __forceinline__ float3 transform_point(const float* T, float4 p) {
 
 // lookup cell of a transformed point: floor(x / leaf) with an IEEE division (impl.hpp:379-381)
 __device__ __forceinline__ int lookup_cell(float x, float leaf) { return (int)floorf(__fdiv_rn(x, leaf)); }
+// Same result without the division on the common path: q = x * (1/leaf) is within 2 ulp of the IEEE quotient, so
+// floor(q) can only differ from floor(x / leaf) when q lies within a few ulp of an integer — only then is the exact
+// division evaluated.
+__device__ __forceinline__ int lookup_cell_fast(float x, float leaf, float inv_leaf) {
+  const float q = __fmul_rn(x, inv_leaf);
+  if (fabsf(q - rintf(q)) <= 1e-6f * fabsf(q) + 1e-30f) return (int)floorf(__fdiv_rn(x, leaf));
+  return (int)floorf(q);
+}
 
 }  // namespace b200

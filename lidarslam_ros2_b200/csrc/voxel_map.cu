@@ -345,7 +345,9 @@ __global__ void __launch_bounds__(128) vm_finalize_kernel(const double* __restri
   }
   if (isinf(mxv) || isinf(mnv) || isnan(mxv) || isnan(mnv)) return;
   VoxelRecord o;
-  o.mx = mean[0]; o.my = mean[1]; o.mz = mean[2];
+  o.mhx = (float)mean[0]; o.mlx = (float)(mean[0] - (double)o.mhx);
+  o.mhy = (float)mean[1]; o.mly = (float)(mean[1] - (double)o.mhy);
+  o.mhz = (float)mean[2]; o.mlz = (float)(mean[2] - (double)o.mhz);
   o.c00 = (float)ic[0]; o.c01 = (float)ic[1]; o.c02 = (float)ic[2];
   o.c11 = (float)ic[4]; o.c12 = (float)ic[5]; o.c22 = (float)ic[8];
   rec[r] = o;

@@ -149,21 +149,20 @@ class VoxelGridCovariance {
   }
   // pcl::getAllNeighborCellIndices(): the 26 non-centre cells.
   int neighborhood26(const P3& pt, std::vector<const Leaf*>& out) const {
-    static int rel[78];
-    static bool init = false;
-    if (!init) {
-      int k = 0;
+    // C++11 guarantees this initialisation is thread-safe (the search runs inside an OpenMP parallel region)
+    static const std::vector<int> rel = [] {
+      std::vector<int> v;
       for (int dz = -1; dz <= 1; dz++)
         for (int dy = -1; dy <= 1; dy++)
           for (int dx = -1; dx <= 1; dx++) {
             if (dx == 0 && dy == 0 && dz == 0) continue;
-            rel[k++] = dx;
-            rel[k++] = dy;
-            rel[k++] = dz;
+            v.push_back(dx);
+            v.push_back(dy);
+            v.push_back(dz);
           }
-      init = true;
-    }
-    return neighborhood(rel, 26, pt, out);
+      return v;
+    }();
+    return neighborhood(rel.data(), 26, pt, out);
   }
   // voxel_grid_covariance_omp.h:470-499 (FLANN radius result set keeps dist < r^2)
   int radius_search(const P3& pt, double radius, std::vector<const Leaf*>& out) const {
