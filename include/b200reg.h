@@ -137,6 +137,10 @@ int b200reg_ndt_hessian_radius(b200reg_t h, const float* T, const double* p6, do
  * 282-367). Any pointer may be NULL. mean3/icov9 doubles, centroid3 floats. */
 int b200reg_ndt_num_voxels(b200reg_t h, size_t* out);
 int b200reg_ndt_get_voxels(b200reg_t h, int* leaf_idx, int* npts, double* mean3, double* icov9, float* centroid3);
+/* GICP read-back for parity tests: per-point 3x3 covariances (row-major doubles, gicp_omp_impl.hpp:48-122) of the
+ * source (which = 0) or target (which = 1) cloud after an align(); *n = number of points (out9 may be NULL). */
+int b200reg_gicp_get_covariances(b200reg_t h, int which, double* out9, size_t* n);
+int b200reg_gicp_num_correspondences(b200reg_t h, int* out);
 /* exact 1-NN of n query points against the target cloud (building block of getFitnessScore / GICP) */
 int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, int* idx, float* d2);
 

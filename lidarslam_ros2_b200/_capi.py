@@ -32,6 +32,7 @@ SYMBOLS = [
     "b200reg_get_fitness_score", "b200reg_get_aligned", "b200reg_align_batch",
     "b200reg_voxelgrid", "b200reg_get_stats", "b200reg_ndt_derivatives", "b200reg_ndt_hessian_radius",
     "b200reg_ndt_num_voxels", "b200reg_ndt_get_voxels", "b200reg_nn1",
+    "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences",
 ]
 
 
@@ -103,6 +104,8 @@ def lib() -> C.CDLL:
     L.b200reg_ndt_num_voxels.argtypes = [vp, C.POINTER(sz)]
     L.b200reg_ndt_get_voxels.argtypes = [vp, vp, vp, vp, vp, vp]
     L.b200reg_nn1.argtypes = [vp, vp, sz, sz, vp, vp]
+    L.b200reg_gicp_get_covariances.argtypes = [vp, i, vp, C.POINTER(sz)]
+    L.b200reg_gicp_num_correspondences.argtypes = [vp, C.POINTER(i)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name != "b200reg_last_error":

@@ -706,6 +706,21 @@ int b200reg_debug_cta_eval_ns(b200reg_t h, unsigned* out, int n) {
   });
 }
 
+int b200reg_gicp_get_covariances(b200reg_t h, int which, double* out9, size_t* n) {
+  if (!h || h->kind != B200REG_GICP || !n) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    std::vector<double> tmp;
+    *n = h->gicp_solver.covariances(which, tmp, h->stream);
+    if (out9 && !tmp.empty()) std::memcpy(out9, tmp.data(), tmp.size() * sizeof(double));
+    return (int)B200REG_OK;
+  });
+}
+int b200reg_gicp_num_correspondences(b200reg_t h, int* out) {
+  if (!h || h->kind != B200REG_GICP || !out) return B200REG_ERR_ARG;
+  *out = h->gicp_solver.last_correspondences();
+  return B200REG_OK;
+}
+
 int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, int* idx, float* d2) {
   if (!h || !base || !idx || !d2 || stride_bytes < 12) return B200REG_ERR_ARG;
   return guarded(h, [&]() {

@@ -11,6 +11,7 @@
 #include <cmath>
 
 #include "engine.hpp"
+#include "nn_search.cuh"
 
 namespace b200 {
 
@@ -19,17 +20,6 @@ namespace {
 __device__ __forceinline__ unsigned rank_of(const RankWord* __restrict__ table, int cell) {
   RankWord w = table[cell >> 5];
   return w.prefix + __popc(w.bits & ((1u << (cell & 31)) - 1u));
-}
-
-struct NnGeom {
-  float origin[3];
-  float h, inv_h;
-  int dims[3];
-};
-
-__device__ __forceinline__ int nn_cell_coord(float v, float o, float inv_h, int dim) {
-  int c = (int)floorf((v - o) * inv_h);
-  return max(0, min(dim - 1, c));
 }
 
 __global__ void __launch_bounds__(256) nn_mark_kernel(const float4* __restrict__ pts, size_t n, NnGeom g, RankWord* table,
@@ -102,10 +92,7 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(unsigned* data, size_t n
 }
 
 struct NnQueryParams {
-  const RankWord* index;
-  const unsigned* cell_start;
-  const float4* sorted;
-  NnGeom g;
+  NnView V;
   float T[12];
   int has_T;
 };
@@ -123,46 +110,9 @@ __global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4*
     float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], qx), __fmul_rn(T[9], qy)), __fmul_rn(T[10], qz)), T[11]);
     qx = tx; qy = ty; qz = tz;
   }
-  const NnGeom& g = P.g;
-  const int cx = nn_cell_coord(qx, g.origin[0], g.inv_h, g.dims[0]);
-  const int cy = nn_cell_coord(qy, g.origin[1], g.inv_h, g.dims[1]);
-  const int cz = nn_cell_coord(qz, g.origin[2], g.inv_h, g.dims[2]);
-  float best = FLT_MAX;
-  int best_i = -1;
-  const int max_r = max(g.dims[0], max(g.dims[1], g.dims[2]));
-  for (int r = 0; r <= max_r; r++) {
-    const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dims[2] - 1);
-    const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dims[1] - 1);
-    for (int z = z0; z <= z1; z++) {
-      const bool zface = (z == cz - r) || (z == cz + r);
-      for (int y = y0; y <= y1; y++) {
-        const bool yface = (y == cy - r) || (y == cy + r);
-        const int step = (zface || yface || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
-        for (int x = cx - r; x <= cx + r; x += step) {
-          if (x < 0 || x >= g.dims[0]) continue;
-          const int cell = x + g.dims[0] * (y + g.dims[1] * z);
-          const uint2 w = __ldg(reinterpret_cast<const uint2*>(P.index + (cell >> 5)));
-          const unsigned bit = cell & 31;
-          if (!((w.x >> bit) & 1u)) continue;
-          const unsigned rk = w.y + __popc(w.x & ((1u << bit) - 1u));
-          const unsigned s = __ldg(P.cell_start + rk), e = __ldg(P.cell_start + rk + 1);
-          for (unsigned k = s; k < e; k++) {
-            const float4 t = __ldg(P.sorted + k);
-            const float dx = __fsub_rn(qx, t.x), dy = __fsub_rn(qy, t.y), dz = __fsub_rn(qz, t.z);
-            const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            const int ti = __float_as_int(t.w);
-            if (d2 < best || (d2 == best && ti < best_i)) {
-              best = d2;
-              best_i = ti;
-            }
-          }
-        }
-      }
-    }
-    // after ring r every unvisited point is >= r*h away
-    const float bound = (float)r * g.h;
-    if (best_i >= 0 && best <= bound * bound * 0.99999f) break;
-  }
+  float best;
+  int best_i;
+  nn1_search(P.V, qx, qy, qz, FLT_MAX, best, best_i);
   out_idx[i] = best_i;
   out_d2[i] = best;
 }
@@ -190,6 +140,20 @@ __global__ void __launch_bounds__(256) fitness_kernel(const float* __restrict__ 
 }
 
 }  // namespace
+
+NnView nn_view(const NnGrid& grid) {
+  NnView V;
+  V.index = grid.index.ptr;
+  V.cell_start = grid.cell_start.ptr;
+  V.sorted = grid.sorted.ptr;
+  for (int a = 0; a < 3; a++) {
+    V.g.origin[a] = grid.origin[a];
+    V.g.dims[a] = grid.dims[a];
+  }
+  V.g.h = grid.h;
+  V.g.inv_h = grid.inv_h;
+  return V;
+}
 
 void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
   valid = false;
@@ -254,15 +218,7 @@ void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float*
                cudaStream_t s) {
   if (n == 0) return;
   NnQueryParams P;
-  P.index = grid.index.ptr;
-  P.cell_start = grid.cell_start.ptr;
-  P.sorted = grid.sorted.ptr;
-  for (int a = 0; a < 3; a++) {
-    P.g.origin[a] = grid.origin[a];
-    P.g.dims[a] = grid.dims[a];
-  }
-  P.g.h = grid.h;
-  P.g.inv_h = grid.inv_h;
+  P.V = nn_view(grid);
   P.has_T = T12_host ? 1 : 0;
   for (int k = 0; k < 12; k++) P.T[k] = T12_host ? T12_host[k] : 0.f;
   const int blocks = (int)((n + 127) / 128);

@@ -239,6 +239,21 @@ class GeneralizedIterativeClosestPoint(_Registration):
     def setMaximumOptimizerIterations(self, n: int):
         self._check(self._lib.b200reg_gicp_set_maximum_optimizer_iterations(self._h, int(n)))
 
+    # ---- parity hooks ----
+    def covariances(self, which: str) -> np.ndarray:
+        w = 1 if which == "target" else 0
+        n = C.c_size_t(0)
+        self._check(self._lib.b200reg_gicp_get_covariances(self._h, w, None, C.byref(n)))
+        out = np.empty((n.value, 3, 3))
+        if n.value:
+            self._check(self._lib.b200reg_gicp_get_covariances(self._h, w, _ptr(out), C.byref(n)))
+        return out
+
+    def numCorrespondences(self) -> int:
+        v = C.c_int(0)
+        self._check(self._lib.b200reg_gicp_num_correspondences(self._h, C.byref(v)))
+        return v.value
+
 
 def align_batch(engines, guesses=None) -> np.ndarray:
     """Batched loop-closure sweep on one GPU: all solves are enqueued before any is awaited. Returns (K,4,4)."""
