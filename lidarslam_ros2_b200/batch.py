@@ -1,0 +1,74 @@
+"""Batched loop-closure sweep: independent (scan, submap) registrations sharded one pair per GPU at a time, with ONE
+all-gather of the resulting poses.
+
+The reference evaluates a single revisit candidate per timer tick (graph_based_slam_component.cpp:187-233: nearest
+submap that passes the travelled-distance / range gates → align → getFitnessScore → threshold). Registering ALL gated
+candidates is the same computation repeated on independent inputs, so it shards with no data-path collective: pair i
+goes to rank i mod world; every rank builds its own targets, runs its own solves, and the only exchange is the
+all-gather of the fixed-size result rows so that every rank (and the host feeding the pose graph) sees all poses.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+ROW = 20  # 16 pose floats (row-major 4x4) + fitness + converged + iterations + pair index
+
+
+def shard_pairs(n_pairs: int, rank: int, world: int) -> list[int]:
+    """Pair indices owned by `rank`: i mod world == rank (round-robin keeps per-rank work balanced)."""
+    return [i for i in range(n_pairs) if i % world == rank]
+
+
+def pack_row(index: int, T: np.ndarray, fitness: float, converged: bool, iterations: int) -> np.ndarray:
+    row = np.zeros(ROW, dtype=np.float32)
+    row[:16] = np.asarray(T, dtype=np.float32).reshape(16)
+    row[16] = fitness
+    row[17] = 1.0 if converged else 0.0
+    row[18] = iterations
+    row[19] = index
+    return row
+
+
+def unpack_rows(rows: np.ndarray):
+    rows = np.asarray(rows, dtype=np.float32).reshape(-1, ROW)
+    order = np.argsort(rows[:, 19], kind="stable")
+    rows = rows[order]
+    return {
+        "index": rows[:, 19].astype(np.int64),
+        "pose": rows[:, :16].reshape(-1, 4, 4).copy(),
+        "fitness": rows[:, 16].copy(),
+        "converged": rows[:, 17] > 0.5,
+        "iterations": rows[:, 18].astype(np.int64),
+    }
+
+
+def gather_rows(local_rows: np.ndarray, n_pairs: int, rank: int, world: int, device=None):
+    """All-gather the per-rank result rows (NCCL on GPUs, gloo on CPU). Ranks own ceil/floor(n_pairs/world) pairs;
+    rows are padded to the maximum count with index -1 and dropped after the gather."""
+    import torch
+    import torch.distributed as dist
+
+    per = (n_pairs + world - 1) // world
+    buf = torch.full((per, ROW), -1.0, dtype=torch.float32)
+    if len(local_rows):
+        buf[:len(local_rows)] = torch.from_numpy(np.asarray(local_rows, dtype=np.float32).reshape(-1, ROW))
+    if device is not None:
+        buf = buf.to(device)
+    if world == 1:
+        allr = buf.cpu().numpy()
+    else:
+        out = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(out, buf)
+        allr = torch.cat(out).cpu().numpy()
+    allr = allr[allr[:, 19] >= 0]
+    return unpack_rows(allr)
+
+
+def register_pair(engine, source, target, guess=None, fitness_max_range=None):
+    """One loop-closure candidate: setInputTarget → setInputSource → align → getFitnessScore
+    (graph_based_slam_component.cpp:181, 227-231)."""
+    engine.setInputTarget(target)
+    engine.setInputSource(source)
+    T = engine.align(guess)
+    fit = engine.getFitnessScore() if fitness_max_range is None else engine.getFitnessScore(fitness_max_range)
+    return T, fit, engine.hasConverged(), engine.getFinalNumIteration()

@@ -1,0 +1,134 @@
+"""CPU tests of the host-side logic: C-ABI surface, synthetic generator determinism, and the multi-GPU sharding /
+all-gather of the loop-closure sweep on a world_size-2 gloo group."""
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_library_exports_every_declared_symbol():
+    """include/b200reg.h is the drop-in boundary: every function it declares must be exported by the in-tree library
+    (no compute calls here — there is no GPU in this container)."""
+    import ctypes as C
+
+    from lidarslam_ros2_b200 import _capi
+
+    header = open(os.path.join(ROOT, "include", "b200reg.h")).read()
+    declared = set(re.findall(r"\b(b200reg_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(_capi.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
+    lib = C.CDLL(_capi.LIB_PATH)
+    missing = [s for s in sorted(declared) if not hasattr(lib, s)]
+    assert not missing, missing
+    assert declared == set(_capi.SYMBOLS), declared ^ set(_capi.SYMBOLS)
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    import lidarslam_ros2_b200 as m
+
+    with pytest.raises(m.B200RegError):
+        m.NormalDistributionsTransform()
+    with pytest.raises(m.B200RegError):
+        m.voxel_grid_filter(np.zeros((10, 3), dtype=np.float32), 0.5)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lidarslam_ros2_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(import oracle|from oracle)", text, re.M), f
+                assert not re.search(r"#\s*include\s*[\"<][^\n]*oracle", text), f
+                assert "liboracle" not in text, f
+
+
+def test_synth_is_deterministic():
+    from lidarslam_ros2_b200 import synth
+
+    a = synth.registration_pair("tiny", 2.0)
+    b = synth.registration_pair("tiny", 2.0)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+    # counter-based RNG: value k of a stream does not depend on how the stream is consumed
+    r1, r2 = synth.Rng(7), synth.Rng(7)
+    x = r1.uniform(100)
+    y = np.concatenate([r2.uniform(40), r2.uniform(60)])
+    assert np.array_equal(x, y)
+    # pairs of the loop-closure workload are reproducible one by one
+    p3 = next(iter(synth.loop_closure_pairs(8, n_tgt=2000, rings=4, azimuths=90, first=3, count=1)))
+    allp = list(synth.loop_closure_pairs(8, n_tgt=2000, rings=4, azimuths=90))
+    assert p3[0] == 3 and np.array_equal(p3[1], allp[3][1]) and np.array_equal(p3[2], allp[3][2])
+
+
+def test_pose_error_metric():
+    from lidarslam_ros2_b200 import synth
+
+    A = synth.pose_matrix((0.4, -0.2, 0.06), (0.007, -0.005, 0.026))
+    assert synth.pose_error(A.astype(np.float32), A) [1] < 1e-7  # float32 quantisation must not look like rotation
+    B = synth.pose_matrix((0.4, -0.2, 0.06), (0.007, -0.005, 0.0265))
+    assert abs(synth.pose_error(A, B)[1] - 5e-4) < 1e-6
+
+
+def test_shard_pairs_partition():
+    from lidarslam_ros2_b200 import batch
+
+    for n, w in ((64, 1), (64, 2), (64, 8), (10, 4), (3, 8)):
+        got = sorted(i for r in range(w) for i in batch.shard_pairs(n, r, w))
+        assert got == list(range(n))
+        sizes = [len(batch.shard_pairs(n, r, w)) for r in range(w)]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, n_pairs, q):
+    import torch.distributed as dist
+
+    from lidarslam_ros2_b200 import batch
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows = []
+    for i in batch.shard_pairs(n_pairs, rank, world):
+        T = np.eye(4, dtype=np.float32)
+        T[0, 3] = i  # recognisable per pair
+        rows.append(batch.pack_row(i, T, 0.1 * i, i % 2 == 0, 5 + i))
+    res = batch.gather_rows(np.array(rows), n_pairs, rank, world)
+    q.put((rank, res["index"].tolist(), res["pose"][:, 0, 3].tolist(), res["fitness"].tolist(), res["iterations"].tolist()))
+    dist.destroy_process_group()
+
+
+def test_gather_rows_world2_gloo():
+    import torch.multiprocessing as mp
+
+    n_pairs, world = 7, 2  # ragged: ranks own 4 and 3 pairs
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, n_pairs, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, idx, tx, fit, it in out:  # every rank sees every pair, ordered by pair index
+        assert idx == list(range(n_pairs))
+        assert tx == [float(i) for i in range(n_pairs)]
+        np.testing.assert_allclose(fit, [0.1 * i for i in range(n_pairs)], rtol=1e-6)
+        assert it == [5 + i for i in range(n_pairs)]
