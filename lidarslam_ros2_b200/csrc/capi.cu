@@ -446,7 +446,9 @@ int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out) {
     ensure_nn(h);
     h->nn_idx.ensure(h->n_source);
     h->nn_d2.ensure(h->n_source);
-    nn1_query(h->nn, h->d_source.ptr, h->n_source, h->final_T, h->nn_idx.ptr, h->nn_d2.ptr, h->stream);
+    // points farther than max_range do not contribute: let the search stop there
+    const float bound = (max_range < 3.0e38) ? (float)max_range * 1.0001f + 1e-30f : 3.402823466e+38f;
+    nn1_query(h->nn, h->d_source.ptr, h->n_source, h->final_T, h->nn_idx.ptr, h->nn_d2.ptr, h->stream, bound);
     double sum = 0;
     long long cnt = 0;
     fitness_reduce(h->nn_d2.ptr, h->nn_idx.ptr, h->n_source, max_range, h->scratch_d.ptr, &sum, &cnt, h->stream);

@@ -123,14 +123,18 @@ struct NnGrid {
   DeviceBuffer<unsigned> bounds_scratch;
   RankIndexScratch scan_scratch;
   DeviceBuffer<unsigned> scan_tmp;
+  DeviceBuffer<int> unresolved;             // query scratch: indices of queries left to the brute-force pass
+  DeviceBuffer<unsigned> unresolved_count;
   int launches = 0;
   bool valid = false;
   void build(const float4* pts, size_t n, cudaStream_t s);
 };
 // 1-NN of n queries (optionally transformed by T, 3x4 row-major; nullptr = none). d2 accumulated in f32 as
 // ((dx*dx + dy*dy) + dz*dz); ties → lower index. idx = -1 when the target is empty.
+// max_d2: only neighbours closer than this matter to the caller (FLT_MAX = unbounded). Queries whose neighbourhood is
+// not resolved within a few cell rings are finished by a brute-force pass (exact either way).
 void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float* T12_host, int* d_idx, float* d_d2,
-               cudaStream_t s);
+               cudaStream_t s, float max_d2 = 3.402823466e+38f);
 // mean of d2 over queries with d2 <= max_range → (sum, count) on device, returned to host (synchronises)
 void fitness_reduce(const float* d_d2, const int* d_idx, size_t n, double max_range, double* d_scratch2, double* sum,
                     long long* count, cudaStream_t s);

@@ -164,30 +164,24 @@ __global__ void __launch_bounds__(128) gicp_cov_kernel(NnView V, const float4* _
 
 // ---- K6: correspondences + Mahalanobis matrices (gicp_omp_impl.hpp:420-456) ----------------------------------
 struct CorrParams {
-  NnView V;
-  const float4* moved;     // source transformed by the guess ("output")
   const double* cov_src;   // 6 per point
   const double* cov_tgt;
-  float T[12];             // transformation_ of this outer iteration (f32)
   double R[9];             // (transformation_ * guess) rotation in f64
   float dist_threshold;    // corr_dist^2 as the f32 the comparison effectively sees
   double dist_threshold_d;
   int n;
 };
 
-__global__ void __launch_bounds__(128) gicp_corr_kernel(CorrParams P, int* __restrict__ corr, float* __restrict__ maha,
+// nearest neighbours come from nn1_query (ring search + brute-force pass for outliers); this kernel applies the
+// distance gate and forms M = (R C1 R^T + C2)^-1 in f64
+__global__ void __launch_bounds__(128) gicp_corr_kernel(CorrParams P, const int* __restrict__ nn_idx, const float* __restrict__ nn_d2,
+                                                        int* __restrict__ corr, float* __restrict__ maha,
                                                         unsigned* __restrict__ count) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int found = 0;
   if (i < P.n) {
-    const float4 o = P.moved[i];
-    const float* T = P.T;
-    const float qx = T[0] * o.x + T[1] * o.y + T[2] * o.z + T[3];
-    const float qy = T[4] * o.x + T[5] * o.y + T[6] * o.z + T[7];
-    const float qz = T[8] * o.x + T[9] * o.y + T[10] * o.z + T[11];
-    float best;
-    int bi;
-    nn1_search(P.V, qx, qy, qz, P.dist_threshold * 1.0001f, best, bi);
+    const int bi = nn_idx[i];
+    const float best = nn_d2[i];
     int c = -1;
     if (bi >= 0 && (double)best < P.dist_threshold_d) {
       c = bi;
@@ -479,18 +473,19 @@ GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, s
       for (int j = 0; j < 4; j++)
         for (int kk = 0; kk < 4; kk++) TR[i * 4 + j] += double(transformation[i * 4 + kk]) * double(guess16[kk * 4 + j]);
     CorrParams P;
-    P.V = nn_view(target_grid);
-    P.moved = moved_.ptr;
     P.cov_src = source_cov_.ptr;
     P.cov_tgt = target_cov_.ptr;
-    for (int q = 0; q < 12; q++) P.T[q] = transformation[q];
     for (int r = 0; r < 3; r++)
       for (int c = 0; c < 3; c++) P.R[r * 3 + c] = TR[r * 4 + c];
     P.dist_threshold_d = dist_threshold;
     P.dist_threshold = dist_threshold > 3.0e38 ? 3.0e38f : (float)dist_threshold;
     P.n = (int)n_source;
     B200_CUDA(cudaMemsetAsync(counter_.ptr, 0, sizeof(unsigned), s));
-    gicp_corr_kernel<<<(int)((n_source + 127) / 128), 128, 0, s>>>(P, corr_.ptr, maha_.ptr, counter_.ptr);
+    // query = transformation_ * output[i] (:426-427); nn1_query applies the 3x4 transform in f32
+    nn_idx_.ensure(n_source);
+    nn_d2_.ensure(n_source);
+    nn1_query(target_grid, moved_.ptr, n_source, transformation, nn_idx_.ptr, nn_d2_.ptr, s, P.dist_threshold * 1.0001f);
+    gicp_corr_kernel<<<(int)((n_source + 127) / 128), 128, 0, s>>>(P, nn_idx_.ptr, nn_d2_.ptr, corr_.ptr, maha_.ptr, counter_.ptr);
     unsigned m = 0;
     B200_CUDA(cudaMemcpyAsync(&m, counter_.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
     B200_CUDA(cudaStreamSynchronize(s));

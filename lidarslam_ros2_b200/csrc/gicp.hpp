@@ -49,6 +49,8 @@ class GicpSolver {
   DeviceBuffer<double> target_cov_, source_cov_;  // 6 doubles per point (xx xy xz yy yz zz)
   DeviceBuffer<float> maha_;                      // 9 floats per source point
   DeviceBuffer<int> corr_;                        // target index per source point, -1 = none
+  DeviceBuffer<int> nn_idx_;
+  DeviceBuffer<float> nn_d2_;
   DeviceBuffer<float4> moved_;                    // source transformed by the guess ("output" cloud)
   DeviceBuffer<double> partials_;                 // per-CTA partial sums (16 doubles each)
   DeviceBuffer<double> result_;                   // 16 doubles

@@ -91,30 +91,90 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(unsigned* data, size_t n
   if (threadIdx.x == 0) data[n] = carry_s;
 }
 
+constexpr int NN_MAX_RINGS = 3;  // 7^3 cells; beyond that a query is an outlier and goes to the brute-force pass
+
 struct NnQueryParams {
   NnView V;
   float T[12];
   int has_T;
+  float max_d2;
+  int n_points;
 };
 
-__global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4* __restrict__ queries, size_t n, int* out_idx,
-                                                  float* out_d2) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 q4 = queries[i];
-  float qx = q4.x, qy = q4.y, qz = q4.z;
+__device__ __forceinline__ void nn_query_point(const NnQueryParams& P, float4 q4, float& qx, float& qy, float& qz) {
+  qx = q4.x; qy = q4.y; qz = q4.z;
   if (P.has_T) {  // same un-fused float transform as the solver / pcl::transformPointCloud
     const float* T = P.T;
-    float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], qx), __fmul_rn(T[1], qy)), __fmul_rn(T[2], qz)), T[3]);
-    float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], qx), __fmul_rn(T[5], qy)), __fmul_rn(T[6], qz)), T[7]);
-    float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], qx), __fmul_rn(T[9], qy)), __fmul_rn(T[10], qz)), T[11]);
+    const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[0], qx), __fmul_rn(T[1], qy)), __fmul_rn(T[2], qz)), T[3]);
+    const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[4], qx), __fmul_rn(T[5], qy)), __fmul_rn(T[6], qz)), T[7]);
+    const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[8], qx), __fmul_rn(T[9], qy)), __fmul_rn(T[10], qz)), T[11]);
     qx = tx; qy = ty; qz = tz;
   }
+}
+
+__global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4* __restrict__ queries, size_t n, int* out_idx,
+                                                  float* out_d2, unsigned* unresolved_count, int* unresolved_list) {
+  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float qx, qy, qz;
+  nn_query_point(P, queries[i], qx, qy, qz);
   float best;
   int best_i;
-  nn1_search(P.V, qx, qy, qz, FLT_MAX, best, best_i);
+  const bool resolved = nn1_search(P.V, qx, qy, qz, P.max_d2, NN_MAX_RINGS, best, best_i);
   out_idx[i] = best_i;
   out_d2[i] = best;
+  if (!resolved) unresolved_list[atomicAdd(unresolved_count, 1u)] = (int)i;
+}
+
+// Phase 2: one CTA per unresolved query scans the whole (cell-sorted) cloud; lexicographic (d2, index) minimum, so the
+// result does not depend on the scan order.
+__global__ void __launch_bounds__(256) nn1_bruteforce_kernel(NnQueryParams P, const float4* __restrict__ queries,
+                                                             const unsigned* __restrict__ unresolved_count,
+                                                             const int* __restrict__ unresolved_list, int* out_idx,
+                                                             float* out_d2) {
+  __shared__ float sd[8];
+  __shared__ int si[8];
+  const unsigned total = *unresolved_count;
+  for (unsigned u = blockIdx.x; u < total; u += gridDim.x) {
+    const int qi = unresolved_list[u];
+    float qx, qy, qz;
+    nn_query_point(P, queries[qi], qx, qy, qz);
+    float best = FLT_MAX;
+    int best_i = -1;
+    for (int k = threadIdx.x; k < P.n_points; k += blockDim.x) {
+      const float4 t = __ldg(P.V.sorted + k);
+      const float d2 = nn_dist2(qx, qy, qz, t);
+      const int ti = __float_as_int(t.w);
+      if (d2 < best || (d2 == best && ti < best_i)) {
+        best = d2;
+        best_i = ti;
+      }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      const float od = __shfl_xor_sync(0xffffffffu, best, d);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, d);
+      if (oi >= 0 && (od < best || (od == best && (best_i < 0 || oi < best_i)))) {
+        best = od;
+        best_i = oi;
+      }
+    }
+    if ((threadIdx.x & 31) == 0) {
+      sd[threadIdx.x >> 5] = best;
+      si[threadIdx.x >> 5] = best_i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int w = 1; w < 8; w++)
+        if (si[w] >= 0 && (sd[w] < best || (sd[w] == best && (best_i < 0 || si[w] < best_i)))) {
+          best = sd[w];
+          best_i = si[w];
+        }
+      out_idx[qi] = best_i;
+      out_d2[qi] = best;
+    }
+    __syncthreads();
+  }
 }
 
 __global__ void __launch_bounds__(256) fitness_kernel(const float* __restrict__ d2, const int* __restrict__ idx, size_t n,
@@ -215,14 +275,21 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
 }
 
 void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float* T12_host, int* d_idx, float* d_d2,
-               cudaStream_t s) {
+               cudaStream_t s, float max_d2) {
   if (n == 0) return;
   NnQueryParams P;
   P.V = nn_view(grid);
   P.has_T = T12_host ? 1 : 0;
   for (int k = 0; k < 12; k++) P.T[k] = T12_host ? T12_host[k] : 0.f;
+  P.max_d2 = max_d2;
+  P.n_points = (int)grid.n_points;
+  NnGrid& gm = const_cast<NnGrid&>(grid);  // per-grid query scratch
+  gm.unresolved.ensure(n + 1);
+  gm.unresolved_count.ensure(1);
+  B200_CUDA(cudaMemsetAsync(gm.unresolved_count.ptr, 0, sizeof(unsigned), s));
   const int blocks = (int)((n + 127) / 128);
-  nn1_kernel<<<blocks, 128, 0, s>>>(P, queries, n, d_idx, d_d2);
+  nn1_kernel<<<blocks, 128, 0, s>>>(P, queries, n, d_idx, d_d2, gm.unresolved_count.ptr, gm.unresolved.ptr);
+  nn1_bruteforce_kernel<<<148 * 4, 256, 0, s>>>(P, queries, gm.unresolved_count.ptr, gm.unresolved.ptr, d_idx, d_d2);
   B200_CUDA(cudaGetLastError());
 }
 

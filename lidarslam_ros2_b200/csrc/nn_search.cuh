@@ -60,15 +60,18 @@ __device__ __forceinline__ void nn_visit_ring(const NnView& V, int cx, int cy, i
 }
 
 // exact 1-NN; ties → lower index. If max_d2 < FLT_MAX the search also stops once no closer point than max_d2 can exist
-// (the caller then tests best < max_d2 itself).
-__device__ __forceinline__ void nn1_search(const NnView& V, float qx, float qy, float qz, float max_d2, float& best, int& best_i) {
+// (the caller then tests best < max_d2 itself). The ring expansion is capped at `max_rings`: a query whose
+// neighbourhood is still unresolved then (an outlier far from every target point) returns false and is finished by
+// the brute-force pass of nn_grid.cu — ring volumes grow with r^3, a linear scan of the cloud does not.
+__device__ __forceinline__ bool nn1_search(const NnView& V, float qx, float qy, float qz, float max_d2, int max_rings,
+                                           float& best, int& best_i) {
   const NnGeom& g = V.g;
   const int cx = nn_cell_coord(qx, g.origin[0], g.inv_h, g.dims[0]);
   const int cy = nn_cell_coord(qy, g.origin[1], g.inv_h, g.dims[1]);
   const int cz = nn_cell_coord(qz, g.origin[2], g.inv_h, g.dims[2]);
   best = FLT_MAX;
   best_i = -1;
-  const int max_r = max(g.dims[0], max(g.dims[1], g.dims[2]));
+  const int max_r = min(max_rings, max(g.dims[0], max(g.dims[1], g.dims[2])));
   for (int r = 0; r <= max_r; r++) {
     nn_visit_ring(V, cx, cy, cz, r, [&](float4 t) {
       const float d2 = nn_dist2(qx, qy, qz, t);
@@ -81,9 +84,10 @@ __device__ __forceinline__ void nn1_search(const NnView& V, float qx, float qy, 
     // after ring r every unvisited point is >= r*h away from the query
     const float bound = (float)r * g.h;
     const float b2 = bound * bound * 0.99999f;
-    if (best_i >= 0 && best <= b2) break;
-    if (b2 > max_d2) break;  // nothing within the caller's radius remains unvisited
+    if (best_i >= 0 && best <= b2) return true;
+    if (b2 > max_d2) return true;  // nothing within the caller's radius remains unvisited
   }
+  return max_r >= max(g.dims[0], max(g.dims[1], g.dims[2]));  // whole grid visited → resolved
 }
 
 }  // namespace b200
