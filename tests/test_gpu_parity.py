@@ -215,3 +215,18 @@ def test_edge_cases(b200, oracle_mod, pair_tiny):
     wide[:, 4] = 7.0
     g2, o2 = _mk(b200, oracle_mod, wide, tgt, 2.0)
     _check_pose(g2.align(), o2.align())
+
+
+def test_cpp_adapter_end_to_end(b200):
+    """The C++ adapter (include/b200reg_pcl.hpp) driven like apps/align.cpp: recovers a known shift on the GPU."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "adapter_smoke")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "adapter_smoke.cpp"), "-o", exe,
+                           "-L" + os.path.join(root, "lidarslam_ros2_b200", "csrc"), "-lb200reg",
+                           "-Wl,-rpath," + os.path.join(root, "lidarslam_ros2_b200", "csrc")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr

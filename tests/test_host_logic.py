@@ -132,3 +132,29 @@ def test_gather_rows_world2_gloo():
         assert tx == [float(i) for i in range(n_pairs)]
         np.testing.assert_allclose(fit, [0.1 * i for i in range(n_pairs)], rtol=1e-6)
         assert it == [5 + i for i in range(n_pairs)]
+
+
+def _build_adapter():
+    import subprocess
+
+    exe = os.path.join(ROOT, "tests", "cpp", "adapter_smoke")
+    src = os.path.join(ROOT, "tests", "cpp", "adapter_smoke.cpp")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L" + os.path.join(ROOT, "lidarslam_ros2_b200", "csrc"), "-lb200reg",
+                           "-Wl,-rpath," + os.path.join(ROOT, "lidarslam_ros2_b200", "csrc")])
+    return exe
+
+
+def test_cpp_adapter_compiles_and_fails_loudly_without_gpu():
+    """include/b200reg_pcl.hpp (the C++ host side of the boundary) builds against the C-ABI; without a GPU the
+    engine refuses to construct (exit code 3) instead of falling back to a CPU path."""
+    import subprocess
+
+    import torch
+
+    exe = _build_adapter()
+    rc = subprocess.run([exe], capture_output=True, text=True)
+    if torch.cuda.is_available():
+        assert rc.returncode == 0, rc.stdout
+    else:
+        assert rc.returncode == 3 and "no CUDA device" in rc.stdout, rc.stdout

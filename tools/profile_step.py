@@ -1,0 +1,18 @@
+"""Short headline-workload run for ncu: a few aligns + fitness + voxel build (set target) so that every kernel of the
+hot path appears in the launch list."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import lidarslam_ros2_b200 as m
+from lidarslam_ros2_b200 import synth
+cfg = sys.argv[1] if len(sys.argv) > 1 else "headline"
+n_align = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+src, tgt, _ = synth.registration_pair(cfg, 2.0)
+g = m.NormalDistributionsTransform(); g.setResolution(2.0); g.setTransformationEpsilon(0.01)
+g.setInputTarget(tgt); g.setInputSource(src)
+for _ in range(n_align):
+    T = g.align()
+print("fitness", g.getFitnessScore(), "stats", g.stats())
+ds = m.voxel_grid_filter(src, 0.5)
+print("voxelgrid", ds.shape)
