@@ -181,6 +181,7 @@ class NdtSolver {
   int index_in_smem() const { return index_in_smem_; }
   int launches = 0;
   bool scalar_controller = false;  // developer switch (env B200REG_SCALAR_CTL=1)
+  bool exclusive_sm = true;        // controller CTA claims an SM for itself (env B200REG_SHARED_SM=1 disables)
   bool timing_enabled = false;  // developer instrumentation (env B200REG_TIMING=1)
   void read_timing(unsigned long long* out48x8) const;
   void read_cta_eval_ns(unsigned* out, int n) const;
@@ -192,6 +193,7 @@ class NdtSolver {
   int sm_count_ = 0;
   int grid_ = 0, block_ = 0, index_in_smem_ = 0;
   int max_smem_optin_ = 0;
+  unsigned epoch_ = 0;
   NdtSolverWork* d_work_ = nullptr;
   NdtResult* h_result_ = nullptr;  // pinned
 };

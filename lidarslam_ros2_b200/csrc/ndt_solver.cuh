@@ -42,15 +42,23 @@ constexpr int NDT_TIMING_ROUNDS = 48;
 constexpr int NDT_TIMING_SLOTS = 10;
 // slots (globaltimer ns): 0 CTA0 round start, 1 CTA0 after evaluate, 2 CTA0 partial written, 3 CTA0 arrived,
 //                         4 last CTA detected, 5 partials reduced, 6 controller done, 7 CTA0 released
+struct NdtRoles {        // per-launch role election (see ndt_solver.cu: elect_roles)
+  unsigned ctrl_smid;    // SM id claimed by the controller CTA (0xffffffff = unclaimed)
+  unsigned n_rank;       // evaluator ranks handed out so far
+  unsigned registered;   // CTAs that finished registering
+  unsigned pad;
+};
+
 struct NdtSolverWork {
   unsigned arrive;
   unsigned gen;
   unsigned error;
   unsigned pad;
+  NdtRoles roles[2];     // indexed by launch parity
   NdtControl control;
   NdtState state;
   NdtResult result;
-  double partials[NDT_MAX_CTAS][SLOT_COUNT];
+  alignas(16) double partials[NDT_MAX_CTAS][SLOT_COUNT];
   unsigned long long timing[NDT_TIMING_ROUNDS][NDT_TIMING_SLOTS];
   unsigned cta_eval_ns[NDT_MAX_CTAS];  // timing mode: evaluate duration of every CTA in round 2
 };
@@ -67,6 +75,8 @@ struct NdtLaunch {
   int n_voxels;
   int search_method;
   int mode;    // NdtMode
+  unsigned epoch;         // launch counter of this handle (parity selects the role-election counters)
+  int exclusive_sm;       // 1: the controller CTA claims an SM for itself (CTAs sharing it retire)
   int scalar_controller;  // 1: disable the warp-parallel controller fast path (developer switch)
   int timing;  // 1: record per-phase globaltimer stamps into work->timing (developer instrumentation)
   int resume;  // 1: state/control already in work (after a K2 pass); first round skips the evaluation

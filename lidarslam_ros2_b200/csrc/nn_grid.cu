@@ -62,16 +62,48 @@ __global__ void __launch_bounds__(256) nn_scatter_kernel(const float4* __restric
   sorted[pos] = make_float4(p.x, p.y, p.z, __int_as_float((int)i));
 }
 
-// exclusive scan of a u32 array (in place), n + 1 outputs (last = total). Single block; n is "occupied cells".
-__global__ void __launch_bounds__(1024) scan_u32_kernel(unsigned* data, size_t n) {
+// exclusive scan of a u32 array in place (data[n] receives the total): tile-local scan, scan of the tile sums by one
+// block, then the tile offsets are added back
+constexpr int USCAN_THREADS = 256, USCAN_ITEMS = 8, USCAN_TILE = USCAN_THREADS * USCAN_ITEMS;
+
+__global__ void __launch_bounds__(USCAN_THREADS) uscan_local_kernel(unsigned* data, size_t n, unsigned* tile_sums) {
+  __shared__ unsigned warp_tot[USCAN_THREADS / 32];
+  const size_t base = (size_t)blockIdx.x * USCAN_TILE + (size_t)threadIdx.x * USCAN_ITEMS;
+  unsigned v[USCAN_ITEMS], local = 0;
+#pragma unroll
+  for (int k = 0; k < USCAN_ITEMS; k++) {
+    v[k] = (base + k < n) ? data[base + k] : 0u;
+    local += v[k];
+  }
+  unsigned incl = local;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    unsigned t = __shfl_up_sync(0xffffffffu, incl, d);
+    if (lane >= d) incl += t;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  unsigned off = 0;
+  for (int w = 0; w < warp; w++) off += warp_tot[w];
+  unsigned run = off + incl - local;
+#pragma unroll
+  for (int k = 0; k < USCAN_ITEMS; k++) {
+    if (base + k < n) data[base + k] = run;
+    run += v[k];
+  }
+  if (threadIdx.x == USCAN_THREADS - 1) tile_sums[blockIdx.x] = run;
+}
+
+__global__ void __launch_bounds__(1024) uscan_tiles_kernel(unsigned* tile_sums, int n_tiles, unsigned* total_out) {
   __shared__ unsigned warp_tot[32];
   __shared__ unsigned carry_s;
   if (threadIdx.x == 0) carry_s = 0;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (size_t base = 0; base < n; base += 1024) {
-    size_t i = base + threadIdx.x;
-    unsigned v = (i < n) ? data[i] : 0u;
+  for (int base = 0; base < n_tiles; base += 1024) {
+    int i = base + threadIdx.x;
+    unsigned v = (i < n_tiles) ? tile_sums[i] : 0u;
     unsigned incl = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -83,12 +115,20 @@ __global__ void __launch_bounds__(1024) scan_u32_kernel(unsigned* data, size_t n
     unsigned off = 0;
     for (int w = 0; w < warp; w++) off += warp_tot[w];
     unsigned carry = carry_s;
-    if (i < n) data[i] = carry + off + incl - v;
+    if (i < n_tiles) tile_sums[i] = carry + off + incl - v;
     __syncthreads();
     if (threadIdx.x == 1023) carry_s = carry + off + incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) data[n] = carry_s;
+  if (threadIdx.x == 0) *total_out = carry_s;
+}
+
+__global__ void __launch_bounds__(USCAN_THREADS) uscan_apply_kernel(unsigned* data, size_t n, const unsigned* tile_sums) {
+  const unsigned off = tile_sums[blockIdx.x];
+  const size_t base = (size_t)blockIdx.x * USCAN_TILE + (size_t)threadIdx.x * USCAN_ITEMS;
+#pragma unroll
+  for (int k = 0; k < USCAN_ITEMS; k++)
+    if (base + k < n) data[base + k] += off;
 }
 
 constexpr int NN_MAX_RINGS = 3;  // 7^3 cells; beyond that a query is an outlier and goes to the brute-force pass
@@ -267,7 +307,13 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
   B200_CUDA(cudaMemsetAsync(cell_start.ptr, 0, sizeof(unsigned) * (n_cells_occupied + 1), s));
   B200_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned) * n_cells_occupied, s));
   nn_count_kernel<<<blocks, 256, 0, s>>>(n, cell_of_point.ptr, index.ptr, cell_start.ptr);
-  scan_u32_kernel<<<1, 1024, 0, s>>>(cell_start.ptr, n_cells_occupied);
+  {
+    const int n_tiles = (int)((n_cells_occupied + USCAN_TILE - 1) / USCAN_TILE);
+    scan_tmp.ensure((size_t)n_tiles + 1);
+    uscan_local_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, n_cells_occupied, scan_tmp.ptr);
+    uscan_tiles_kernel<<<1, 1024, 0, s>>>(scan_tmp.ptr, n_tiles, cell_start.ptr + n_cells_occupied);
+    if (n_tiles > 1) uscan_apply_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, n_cells_occupied, scan_tmp.ptr);
+  }
   nn_scatter_kernel<<<blocks, 256, 0, s>>>(pts, n, cell_of_point.ptr, index.ptr, cell_start.ptr, cursor.ptr, sorted.ptr);
   launches += 3;
   B200_CUDA(cudaGetLastError());

@@ -230,3 +230,21 @@ def test_cpp_adapter_end_to_end(b200):
                            "-Wl,-rpath," + os.path.join(root, "lidarslam_ros2_b200", "csrc")])
     out = subprocess.run([exe], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
+
+
+@pytest.mark.parametrize("cfg", ["c2", "headline"])
+def test_align_parity_full_size(b200, oracle_mod, cfg):
+    """BASELINE.json's full sizes (C2: ~60k vs 500k; headline: ~100k vs 1M), res 2.0, node parameters: pose and iteration
+    parity with the CPU path, determinism of repeated solves, and the voxel-count invariant."""
+    from lidarslam_ros2_b200 import synth
+
+    src, tgt, T_gt = synth.registration_pair(cfg, 2.0)
+    g, o = _mk(b200, oracle_mod, src, tgt, 2.0)
+    Tg, To = g.align(), o.align()
+    _check_pose(Tg, To)
+    assert g.getFinalNumIteration() == o.iterations and g.hasConverged() == o.converged
+    assert len(g.voxels()["idx"]) == len(o.voxels()["idx"])
+    assert np.array_equal(g.align(), Tg)  # bitwise deterministic
+    dt, dr = synth.pose_error(Tg, T_gt)
+    assert dt < 0.15 and dr < 5e-3  # and it is a registration: close to the pose the scan was ray-cast from
+    assert abs(g.getFitnessScore(1.0) - o.fitness(1.0)) <= 1e-4 * o.fitness(1.0) + 1e-6
