@@ -255,7 +255,7 @@ int b200reg_create(int kind, int device, b200reg_t* out) {
     h->solver.init(device, h->stream);
     h->solver.timing_enabled = getenv("B200REG_TIMING") != nullptr;
     h->solver.scalar_controller = getenv("B200REG_SCALAR_CTL") != nullptr;
-    h->solver.exclusive_sm = getenv("B200REG_SHARED_SM") == nullptr;
+    h->solver.no_warmup = getenv("B200REG_NO_WARMUP") != nullptr;
     h->gicp_solver.init(device, h->stream);
     if (kind == B200REG_GICP) {
       h->corr_dist = 5.0;  // gicp_omp.h:119

@@ -181,7 +181,7 @@ class NdtSolver {
   int index_in_smem() const { return index_in_smem_; }
   int launches = 0;
   bool scalar_controller = false;  // developer switch (env B200REG_SCALAR_CTL=1)
-  bool exclusive_sm = true;        // controller CTA claims an SM for itself (env B200REG_SHARED_SM=1 disables)
+  bool no_warmup = false;          // developer switch (env B200REG_NO_WARMUP=1)
   bool timing_enabled = false;  // developer instrumentation (env B200REG_TIMING=1)
   void read_timing(unsigned long long* out48x8) const;
   void read_cta_eval_ns(unsigned* out, int n) const;

@@ -29,15 +29,18 @@ namespace b200 {
 
 namespace {
 
-constexpr int SOLVER_THREADS = 256;
+// ONE 768-thread CTA per SM (80 registers/thread fill the register file, so two can never share an SM): 24 warps keep
+// the issue slots of the four schedulers busy, the partial sums of an SM are combined in its own shared memory, and the
+// controller CTA has to ingest 147 rows instead of 441 (its L2 -> SM bandwidth bounds the reduction). The controller
+// CTA owns an SM by construction.
+constexpr int SOLVER_THREADS = 768;
 constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
-#ifndef B200_SOLVER_MIN_CTAS
-#define B200_SOLVER_MIN_CTAS 3
-#endif
-constexpr int SOLVER_MIN_CTAS = B200_SOLVER_MIN_CTAS;  // resident CTAs per SM the register budget is sized for
+constexpr int SOLVER_MIN_CTAS = 1;
 constexpr int SMEM_POINTS = 1024;  // source points of a CTA's chunk staged in shared memory for the whole solve
 constexpr int ACC_SLOTS = 27;      // 6 gradient + 21 upper-triangular Hessian sums per thread (f32, in shared memory)
-constexpr int ACC_STRIDE = SOLVER_THREADS + 1;  // padded row: slot-major reads by 32 lanes hit 32 different banks
+constexpr int ACC_STRIDE = SOLVER_THREADS + 1;
+constexpr int ACC_BYTES = ACC_SLOTS * ACC_STRIDE * 4;
+constexpr int SOLVER_MAX_DYN_SMEM = 64 * 1024 + ACC_BYTES;  // rank index (<= 64 KB) + accumulators  // padded row: slot-major reads by 32 lanes hit 32 different banks
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s device-side watchdog, never reached in normal runs
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -77,19 +80,21 @@ __device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gmem_sr
                "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void st_release_gpu_f64(double* p, double v) {
-  asm volatile("st.release.gpu.global.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
-}
-__device__ __forceinline__ double ld_relaxed_gpu_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.gpu.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-// Every partial row carries, in its last slot, the sequence number of the evaluation that produced it (unique across
-// rounds and launches of a handle, exactly representable as a double). The controller needs no arrival counter: it
-// polls the tags of the rows it is about to sum, so the fixed-order reduction overlaps with the stragglers.
-constexpr int SLOT_TAG = SLOT_COUNT - 1;
-__device__ __forceinline__ double round_tag(unsigned epoch, int round) { return (double)epoch * 1048576.0 + (double)(round + 1); }
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_gpu_v2(const double* p, unsigned long long& a, unsigned long long& b) {
+  asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_gpu_v2(double* p, unsigned long long a, unsigned long long b) {
+  asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ unsigned ctl_sequence(unsigned epoch, int round) { return epoch * 65536u + (unsigned)round + 1u; }
 
 // ---- per-thread accumulators of one evaluation --------------------------------------------------------------
 // The 27 f32 sums of a thread live in SHARED memory (column tid of acc[slot][tid], conflict-free; the warp-level
@@ -364,8 +369,8 @@ struct CtlShared {
   double M[6][8];     // fast-path scratch: H (36 doubles) followed by A^-1 (9)
   double blk[3][12];  // fast-path scratch: Y | v1, S | w, S^-1
   double vec[4][8];   // fast-path scratch: p, g, dp, dir
-  NdtControl scratch; // target of warm-up passes
-  float scratch_T[16];
+  int ready;          // per-round: bit w set once reducing warp w has summed all its partial rows
+  unsigned long long t_warp[32];  // timing mode: when each reducing warp finished
 };
 
 // ---- compact f64 helpers ------------------------------------------------------------------------------------
@@ -381,65 +386,48 @@ __device__ __noinline__ void dsincos(double x, double* s_out, double* c_out) { s
 // next pose -> transform + angle tables, by the whole warp: lanes 0..2 evaluate sin/cos of the three angles, then
 // every lane evaluates up to three of the 69 table entries from their coded form (ndt_math.cuh) and stores them; lane 0
 // forms the 3x4 transform. Nothing here read-modify-writes shared state, so lanes need not run in lockstep.
-// ---- warm-up mode ---------------------------------------------------------------------------------------------
-// While warp 0 of the controller CTA waits for the evaluators it keeps ITS instruction path hot by executing the
-// controller step and the control-block build in warm-up mode: the same instructions run on whatever the shared state
-// currently holds, nothing of the solver state is written, and the lane's two partial-row tags are polled at a few
-// checkpoints so that the pass is abandoned as soon as every row of the warp has been published. Measured on B200
-// (even with the controller alone on its SM): cold step 7.2 us, warmed step 4.2 us.
-struct WarmPoll {
-  const double* tag_a;
-  const double* tag_b;
-  double want;
-  int ok;  // bit 0: row A seen, bit 1: row B seen
-};
-__device__ __forceinline__ bool warm_done(WarmPoll* wp) {
-  if (!(wp->ok & 1) && ld_relaxed_gpu_f64(wp->tag_a) == wp->want) wp->ok |= 1;
-  if (!(wp->ok & 2) && ld_relaxed_gpu_f64(wp->tag_b) == wp->want) wp->ok |= 2;
-  return __all_sync(0xffffffffu, wp->ok == 3);
-}
-#define B200_WARM_CHECKPOINT() \
-  do {                         \
-    if (warm && warm_done(warm)) return true; \
-  } while (0)
-
-__device__ __noinline__ void build_control(CtlShared& cs, int lane, WarmPoll* warm) {
-  const bool dry = warm != nullptr;
+__device__ __noinline__ void build_control(CtlShared& cs, int lane) {
   const double* x_t = cs.st.x_t;
-  const bool want_f64 = !dry && cs.build_f64 != 0;
-  if (lane < 3) {
-    const double ang = x_t[3 + lane];
-    double sd, cd, sfd, cfd;
-    dsincos(ang, &sd, &cd);
-    if (fabs(ang) < 10e-5) {  // ndt_omp_impl.hpp:292-325
-      sd = 0.0;
-      cd = 1.0;
+  const bool want_f64 = cs.build_f64 != 0;
+  if (lane < 6) {
+    // lanes 0..2: f64 sin/cos of the angle (tables); lanes 3..5: of the angle cast to float — the transform uses
+    // cos/sin in float (Eigen::AngleAxis<float>, :811-814): correctly rounded from the f64 value at the float argument
+    const int a = lane < 3 ? lane : lane - 3;
+    const double ang = x_t[3 + a];
+    double sd, cd;
+    dsincos(lane < 3 ? ang : (double)(float)ang, &sd, &cd);
+    if (lane < 3) {
+      if (fabs(ang) < 10e-5) {  // ndt_omp_impl.hpp:292-325
+        sd = 0.0;
+        cd = 1.0;
+      }
+      cs.fac[2 * a] = sd;
+      cs.fac[2 * a + 1] = cd;
+    } else {
+      cs.facf[2 * a] = (float)sd;
+      cs.facf[2 * a + 1] = (float)cd;
     }
-    // the transform uses cos/sin of the angle cast to float, in float (Eigen::AngleAxis<float>, :811-814):
-    // correctly rounded from the f64 value at the float argument
-    dsincos((double)(float)ang, &sfd, &cfd);
-    cs.fac[2 * lane] = sd;
-    cs.fac[2 * lane + 1] = cd;
-    cs.facf[2 * lane] = (float)sfd;
-    cs.facf[2 * lane + 1] = (float)cfd;
-  } else if (lane == 3) {
+  } else if (lane == 6) {
     cs.fac[6] = 1.0;
     cs.fac[7] = 0.0;
   }
   __syncwarp();
-  if (dry && warm_done(warm)) return;
-  NdtControl& c = dry ? cs.scratch : cs.next;
+  NdtControl& c = cs.next;
 #pragma unroll 1
-  for (int e = lane; e < 69; e += 32) {
-    const double v = angle_table_entry(cs.code[e], cs.fac);  // f64 value (H row d1 carries -sy, :359)
-    float fv = (float)v;
-    if (e == 24 + 20) fv = -fv;  // the live f32 table keeps +sy (:381)
-    if (e < 24) c.jang[e] = fv;
-    else c.hang[e - 24] = fv;
-    if (want_f64) {
-      if (e < 24) cs.st.jd[e] = v;
-      else cs.st.hd[e - 24] = v;
+  for (int it = 0; it < 3; it++) {
+    const int e = lane + 32 * it;
+    if (e < 69) {
+      const double v = angle_table_entry(cs.code[e], cs.fac);  // f64 value (H row d1 carries -sy, :359)
+      float fv = (float)v;
+      if (e == 24 + 20) fv = -fv;  // the live f32 table keeps +sy (:381)
+      if (e < 24) c.jang[e] = fv;
+      else c.hang[e - 24] = fv;
+      if (want_f64) {
+        if (e < 24) cs.st.jd[e] = v;
+        else cs.st.hd[e - 24] = v;
+      }
     }
+    __syncwarp();
   }
   if (lane < 3) {
     // T = Translation * Rx * Ry * Rz in float (ndt_omp_impl.hpp:811-814), same product order as pose_to_matrix();
@@ -451,7 +439,7 @@ __device__ __noinline__ void build_control(CtlShared& cs, int lane, WarmPoll* wa
     const float t0 = __fadd_rn(__fmul_rn(a0, fcz), __fmul_rn(a1, fsz));
     const float t1 = __fadd_rn(__fmul_rn(a0, -fsz), __fmul_rn(a1, fcz));
     const float t3 = (float)x_t[lane];
-    float* F = dry ? cs.scratch_T : cs.st.final_T;  // final_transformation_
+    float* F = cs.st.final_T;  // final_transformation_
     c.T[lane * 4 + 0] = t0; c.T[lane * 4 + 1] = t1; c.T[lane * 4 + 2] = a2; c.T[lane * 4 + 3] = t3;
     F[lane * 4 + 0] = t0; F[lane * 4 + 1] = t1; F[lane * 4 + 2] = a2; F[lane * 4 + 3] = t3;
     F[12 + lane] = 0.0f;
@@ -469,8 +457,7 @@ __device__ __noinline__ void build_control(CtlShared& cs, int lane, WarmPoll* wa
 // (:127-129) by 3x3 block elimination with one matrix element per lane, and the prologue of computeStepLengthMT
 // (:761-809). Anything unusual (convergence, ill-conditioned or non-finite Hessian, zero step) returns false BEFORE any
 // solver state is written, and the scalar controller() redoes the round from scratch. Scalars are computed redundantly by every lane; lane 0 alone writes the state.
-__device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, int lane, WarmPoll* warm) {
-  const bool dry = warm != nullptr;
+__device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, int lane) {
   NdtState& st = cs.st;
   const double step_max = L.step_size, step_min = L.trans_eps / 2;
   if (L.mode != NDT_MODE_ALIGN || L.scalar_controller || !((step_max - step_min) > 0)) return false;
@@ -483,7 +470,7 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
   double* dirv = cs.vec[3]; // unit direction
   int nr_it = st.nr_iterations;
   const double a_prev = st.a_t;
-  if (!dry && phase == PH_LS_FIRST && (nr_it > L.max_iterations || (nr_it && (fabs(a_prev) < L.trans_eps)))) return false;
+  if (phase == PH_LS_FIRST && (nr_it > L.max_iterations || (nr_it && (fabs(a_prev) < L.trans_eps)))) return false;
   if (phase == PH_LS_FIRST) nr_it += 1;
   // scratch fill: the full symmetric H (two elements per lane), pose and gradient (lanes 0..5)
   double* Hs = &cs.M[0][0];  // 36 doubles: H row-major
@@ -501,7 +488,6 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
     gv[lane] = tot[SLOT_G + lane];
   }
   __syncwarp();
-  B200_WARM_CHECKPOINT();
   double amax = 0.0;
   bool finite = true;
 #pragma unroll 1
@@ -528,7 +514,6 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
     if (lane < 9) Ai[lane] = adj * ddiv(1.0, det);
   }
   __syncwarp();
-  B200_WARM_CHECKPOINT();
   if (lane < 9) {  // Y = A^-1 B
     Yv[lane] = Ai[i3 * 3 + 0] * Hs[0 * 6 + 3 + j3] + Ai[i3 * 3 + 1] * Hs[1 * 6 + 3 + j3] + Ai[i3 * 3 + 2] * Hs[2 * 6 + 3 + j3];
   } else if (lane < 12) {  // v1 = A^-1 b1,  b1 = -g[0:3]
@@ -543,7 +528,6 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
     Sv[lane] = -gv[3 + i] - (Hs[0 * 6 + 3 + i] * Yv[9] + Hs[1 * 6 + 3 + i] * Yv[10] + Hs[2 * 6 + 3 + i] * Yv[11]);
   }
   __syncwarp();
-  B200_WARM_CHECKPOINT();
   {
     const double adj = Sv[ja * 3 + ia] * Sv[jb * 3 + ib] - Sv[ja * 3 + ib] * Sv[jb * 3 + ia];
     const double det = Sv[0] * (Sv[4] * Sv[8] - Sv[5] * Sv[7]) - Sv[1] * (Sv[3] * Sv[8] - Sv[5] * Sv[6]) +
@@ -557,7 +541,6 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
   __syncwarp();
   if (lane < 3) dpv[lane] = Yv[9 + lane] - (Yv[lane * 3 + 0] * dpv[3] + Yv[lane * 3 + 1] * dpv[4] + Yv[lane * 3 + 2] * dpv[5]);  // x1
   __syncwarp();
-  B200_WARM_CHECKPOINT();
   double n2 = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; i++) n2 += dpv[i] * dpv[i];
@@ -579,7 +562,6 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
   a_t = fmin(a_t, step_max);
   a_t = fmax(a_t, step_min);
   // ---- write phase ----
-  if (dry) return true;
   const double score = tot[SLOT_SCORE];
   if (lane < 6) {
     const double d = dirv[lane] * sgn;
@@ -822,9 +804,6 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
   NdtSolverWork* W = L.work;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned n_eval = (unsigned)n_eval_i;
-  unsigned my_gen = 0;
-  if (tid == 0) my_gen = ld_relaxed_gpu(&W->gen);
-
   // state: fresh, or restored from global after a K2 pass
   if (L.resume) {
     const int* src = reinterpret_cast<const int*>(&W->state);
@@ -844,56 +823,58 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
     st.a_t = 0;
     W->result.error = 2;  // "not finished"; finish() sets 0, the watchdog 1, a K2 request 100
   }
-  if (tid == 0) cs.done = 0;
+  if (tid == 0) {
+    cs.done = 0;
+    cs.ready = 0;
+  }
   if (tid < 69) cs.code[tid] = kAngleTableCode[tid];
   __syncthreads();
 
+  const int all_ready = (1 << SOLVER_WARPS) - 2;
   for (int round = 0;; round++) {
-    // ---- wait for the evaluators, then reduce in fixed order. Warp w owns rows w, w+8, ...: every lane polls the
-    // sequence tags of two of them (all of a warp's <= 64 tags are polled concurrently, no arrival counter), then the
-    // warp sums its rows with 16-byte loads: one load instruction covers TWO rows (lanes 0..15 the first, 16..31 the
-    // second, two slots per lane), 16 loads in flight -----------------------------------------------------------
-    {
-      const double want_tag = round_tag(L.epoch, round);
-      const int rowA = warp + SOLVER_WARPS * lane, rowB = warp + SOLVER_WARPS * (lane + 32);
-      const bool needA = rowA < (int)n_eval, needB = rowB < (int)n_eval;
-      WarmPoll wp;
-      wp.tag_a = &W->partials[needA ? rowA : 0][SLOT_TAG];
-      wp.tag_b = &W->partials[needB ? rowB : 0][SLOT_TAG];
-      wp.want = want_tag;
-      wp.ok = (needA ? 0 : 1) | (needB ? 0 : 2);
-      const bool warmup = warp == 0 && !L.scalar_controller && L.mode == NDT_MODE_ALIGN;
-      const long long t0 = clock64();
-      while (!warm_done(&wp)) {
-        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
-          if (lane == 0) {
-            W->result.error = 1;
-            cs.done = 3;
-          }
-          break;
-        }
-        if (warmup) {
-          (void)controller_fast(L, cs, lane, &wp);
-          __syncwarp();
-          build_control(cs, lane, &wp);
-          __syncwarp();
-        }
-      }
-      fence_acq_rel_gpu();
-      B200_STAMP(tid == 0, round, 4);
-      const int half = lane >> 4, c2 = (lane & 15) * 2;  // this lane: slots c2, c2+1 of row (2*pair + half)
+    if (warp != 0) {
+      // ---- warps 1..23: fixed-order reduction of the evaluators' partial rows --------------------------------------
+      // Warp w owns rows w-1, w-1+23, ... in batches of 16: one 16-byte load instruction covers TWO rows (lanes 0..15
+      // the first, lanes 16..31 the second, two slots per lane), 8 in flight; the loads double as the arrival poll — a
+      // slot still holding NDT_PARTIAL_EMPTY is simply re-loaded. Consumed rows are re-armed for round + 2.
+      double* buf = &W->partials[round & 1][0][0];
+      const int half = lane >> 4, c2 = (lane & 15) * 2;
+      const int stride = SOLVER_WARPS - 1;
       double s0 = 0, s1 = 0;
-      for (int base = 0; base * SOLVER_WARPS + warp < (int)n_eval; base += 32) {  // 32 rows of this warp per batch
-        double2 v[16];
+      bool failed = false;
+      const long long t0 = clock64();
+      for (int base = 0; (warp - 1) + stride * base < (int)n_eval && !failed; base += 16) {
+        unsigned long long va[8], vb[8];
+        unsigned pend = 0;
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-          const int row = warp + SOLVER_WARPS * (base + 2 * u + half);
-          v[u] = row < (int)n_eval ? __ldcg(reinterpret_cast<const double2*>(&W->partials[row][c2])) : make_double2(0.0, 0.0);
+        for (int u = 0; u < 8; u++) {
+          const int row = (warp - 1) + stride * (base + 2 * u + half);
+          va[u] = 0ull;  // bits of +0.0
+          vb[u] = 0ull;
+          if (row < (int)n_eval) {
+            ld_relaxed_gpu_v2(buf + (size_t)row * SLOT_COUNT + c2, va[u], vb[u]);
+            if (va[u] == NDT_PARTIAL_EMPTY || vb[u] == NDT_PARTIAL_EMPTY) pend |= 1u << u;
+          }
         }
+        while (__any_sync(0xffffffffu, pend != 0)) {
 #pragma unroll
-        for (int u = 0; u < 16; u++) {
-          s0 += v[u].x;
-          s1 += v[u].y;
+          for (int u = 0; u < 8; u++) {
+            if ((pend >> u) & 1u) {
+              const int row = (warp - 1) + stride * (base + 2 * u + half);
+              ld_relaxed_gpu_v2(buf + (size_t)row * SLOT_COUNT + c2, va[u], vb[u]);
+              if (va[u] != NDT_PARTIAL_EMPTY && vb[u] != NDT_PARTIAL_EMPTY) pend &= ~(1u << u);
+            }
+          }
+          if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+            failed = true;
+            break;
+          }
+        }
+        if (failed) break;
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          s0 += __longlong_as_double((long long)va[u]);
+          s1 += __longlong_as_double((long long)vb[u]);
         }
       }
       // even rows (half 0) + odd rows (half 1), fixed order
@@ -902,38 +883,87 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
         warp_part[warp][c2] = s0 + o0;
         warp_part[warp][c2 + 1] = s1 + o1;
       }
-    }
-    __syncthreads();
-    if (tid < SLOT_COUNT) {
-      double t = 0;
+      if (__any_sync(0xffffffffu, failed) && lane == 0) {
+        W->result.error = 1;
+        cs.done = 3;
+      }
+      if (L.timing && lane == 0) cs.t_warp[warp] = globaltimer_ns();
+      __threadfence_block();
+      __syncwarp();
+      if (lane == 0) atomicOr(&cs.ready, 1 << warp);
+      // re-arm the consumed rows for round + 2 — after the flag, so that no fence of the signalling path has to wait
+      // for these stores; they are performed before this warp meets the end-of-round barrier
+      for (int i = half; (warp - 1) + stride * i < (int)n_eval; i += 2) {
+        const int row = (warp - 1) + stride * i;
+        st_relaxed_gpu_v2(buf + (size_t)row * SLOT_COUNT + c2, NDT_PARTIAL_EMPTY, NDT_PARTIAL_EMPTY);
+      }
+      fence_acq_rel_gpu();
+    } else {
+      // ---- warp 0: wait for the reducing warps (a shared-memory word), then run the controller step ------------
+      // (On its own SM the step costs the same whether or not the warp pre-executes it while waiting — measured — so
+      // it simply spins.)
+      const long long t0 = clock64();
+      while (__shfl_sync(0xffffffffu, *(volatile int*)&cs.ready, 0) != all_ready) {
+        if (clock64() - t0 > 2 * SPIN_TIMEOUT_CYCLES) {  // the reducing warps time out first and set cs.done
+          if (lane == 0) cs.done = 3;
+          break;
+        }
+      }
+      __threadfence_block();
+      B200_STAMP(lane == 0, round, 4);
+      if (L.timing && lane == 0 && round < NDT_TIMING_ROUNDS) {
+        unsigned long long tmax = 0, tmin = ~0ull;
+        for (int w = 1; w < SOLVER_WARPS; w++) {
+          tmax = max(tmax, cs.t_warp[w]);
+          tmin = min(tmin, cs.t_warp[w]);
+        }
+        W->timing[round][10] = tmin;
+        W->timing[round][11] = tmax;
+      }
+      {
+        double t = 0;
 #pragma unroll
-      for (int w = 0; w < SOLVER_WARPS; w++) t += warp_part[w][tid];
-      cs.tot[tid] = t;
-    }
-    __syncthreads();
-    if (cs.done == 3) break;
-    B200_STAMP(tid == 0, round, 5);
-    // ---- controller step (warp 0, uniform) + publication of the next control block -----------------------------
-    if (warp == 0) {
+        for (int w = 1; w < SOLVER_WARPS; w++) t += warp_part[w][lane];
+        cs.tot[lane] = t;
+      }
+      __syncwarp();
+      B200_STAMP(lane == 0, round, 5);
       if (lane == 0) cs.build = 0;
       __syncwarp();
-      const bool handled = controller_fast(L, cs, lane, nullptr);  // warp-uniform result
-      if (!handled && lane == 0) controller(L, cs, W);
-      __syncwarp();
-      if (cs.build) build_control(cs, lane, nullptr);
-      __syncwarp();
-      const int* src = reinterpret_cast<const int*>(&cs.next);
-      int* dst = reinterpret_cast<int*>(&W->control);
-      for (int k = lane; k < NDT_CONTROL_WORDS; k += 32) dst[k] = src[k];
-      B200_STAMP(lane == 0, round, 6);
-      __syncwarp();
-      if (lane == 0) {
-        st_release_gpu(&W->gen, my_gen + 1);  // release: orders the control block before the new generation
-        my_gen += 1;
+      if (cs.done == 3 || round >= NDT_MAX_ROUNDS) {  // watchdog: tell the evaluators to leave
+        if (lane == 0) {
+          W->result.error = 1;
+          cs.done = 3;
+          cs.next.mode = EVAL_DONE;
+        }
+      } else {
+        const bool handled = controller_fast(L, cs, lane);  // warp-uniform result
+        if (!handled && lane == 0) controller(L, cs, W);
+        __syncwarp();
+        B200_STAMP(lane == 0, round, 8);
+        if (cs.build) build_control(cs, lane);
+        B200_STAMP(lane == 0, round, 9);
       }
+      __syncwarp();
+      {  // publish the next control block: {payload, sequence} words, every replica
+        const unsigned* src = reinterpret_cast<const unsigned*>(&cs.next);
+        const unsigned long long seq = (unsigned long long)ctl_sequence(L.epoch, round) << 32;
+        for (int k = lane; k < NDT_CONTROL_WORDS; k += 32) {
+          const unsigned long long v = seq | src[k];
+#pragma unroll
+          for (int c = 0; c < NDT_CTL_COPIES; c++) st_relaxed_gpu_u64(&W->ctl_ll[c][k], v);
+        }
+      }
+      B200_STAMP(lane == 0, round, 6);
+      if (lane == 0) cs.ready = 0;
     }
     __syncthreads();
     if (cs.done) break;
+  }
+  if (cs.done == 2) {  // leaving for a K2 pass: the next launch reads the control block from the work area
+    const int* src = reinterpret_cast<const int*>(&cs.next);
+    int* dst = reinterpret_cast<int*>(&W->control);
+    for (int k = tid; k < NDT_CONTROL_WORDS; k += SOLVER_THREADS) dst[k] = src[k];
   }
   if (cs.done == 2) {  // leaving for a K2 pass: park the state in global memory
     const int* src = reinterpret_cast<const int*>(&cs.st);
@@ -944,104 +974,31 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
 }
 
 // =====================================================================================================
-// role election
-// =====================================================================================================
-// The controller step is a ~2 us dependent instruction chain executed by one warp; when evaluator CTAs share its SM
-// they stream ~20 KB of code through the SM's instruction caches every evaluation and the controller pays ~2.5 us of
-// instruction fetch per step (measured). So the controller claims an SM: the first CTA to win an atomicCAS on
-// roles.ctrl_smid becomes the controller, every other CTA that finds itself on that SM retires immediately, and the
-// remaining CTAs take dense evaluator ranks from an atomic counter. Which CTA gets which rank varies from launch to
-// launch; the partition of the points into chunks and the order of every summation depend on the RANK only, so results
-// stay bitwise reproducible.
-struct Role {
-  int kind;    // 0 evaluator, 1 controller, 2 retired
-  int rank;    // evaluator rank
-  int n_eval;  // number of evaluators
-};
-
-__device__ __forceinline__ unsigned read_smid() {
-  unsigned v;
-  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
-  return v;
-}
-
-__device__ Role elect_roles(const NdtLaunch& L, NdtSolverWork* W, int* smem_role3) {
-  if (threadIdx.x == 0) {
-    int kind = 0, rank = 0, n_eval = 0;
-    if (!L.exclusive_sm) {  // fixed roles: last CTA controls
-      kind = (blockIdx.x == gridDim.x - 1) ? 1 : 0;
-      rank = blockIdx.x;
-      n_eval = gridDim.x - 1;
-    } else {
-      NdtRoles* R = &W->roles[L.epoch & 1u];
-      const unsigned me = read_smid();
-      const unsigned prev = atomicCAS(&R->ctrl_smid, 0xffffffffu, me);
-      if (prev == 0xffffffffu) {
-        kind = 1;
-      } else if (prev == me) {
-        kind = 2;
-      } else {
-        kind = 0;
-        rank = (int)atomicAdd(&R->n_rank, 1u);
-      }
-      __threadfence();
-      atomicAdd(&R->registered, 1u);
-      const long long t0 = clock64();
-      while (ld_relaxed_gpu(&R->registered) != gridDim.x) {
-        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
-          W->result.error = 1;
-          kind = 2;
-          break;
-        }
-      }
-      fence_acq_rel_gpu();
-      n_eval = (int)ld_relaxed_gpu(&R->n_rank);
-      if (kind == 1) {  // clear the other parity's counters for the next launch
-        NdtRoles* N = &W->roles[(L.epoch + 1u) & 1u];
-        N->ctrl_smid = 0xffffffffu;
-        N->n_rank = 0;
-        N->registered = 0;
-      }
-    }
-    smem_role3[0] = kind;
-    smem_role3[1] = rank;
-    smem_role3[2] = n_eval;
-  }
-  __syncthreads();
-  Role r;
-  r.kind = smem_role3[0];
-  r.rank = smem_role3[1];
-  r.n_eval = smem_role3[2];
-  return r;
-}
-
-// =====================================================================================================
 // the persistent kernel
 // =====================================================================================================
 template <int METHOD>
 __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_kernel(const __grid_constant__ NdtLaunch L) {
-  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
   __shared__ double warp_part[SOLVER_WARPS][SLOT_COUNT];
 
   NdtSolverWork* W = L.work;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  __shared__ int role3[3];
-  const Role role = elect_roles(L, W, role3);
-  if (role.kind == 2) return;  // shares the controller's SM: retire and leave the SM to the controller
-  if (role.kind == 1) {        // ---- the controller CTA ----
+  const int n_eval_ctas = (int)gridDim.x - 1;
+  if ((int)blockIdx.x == n_eval_ctas) {  // ---- the controller CTA (the last one) ----
     CtlShared& cs = *reinterpret_cast<CtlShared*>(dyn_smem);
-    controller_cta(L, cs, warp_part, role.n_eval);
+    controller_cta(L, cs, warp_part, n_eval_ctas);
     return;
   }
-  const int my_rank = role.rank;
+  const int my_rank = (int)blockIdx.x;
 
   // ---- evaluator CTAs --------------------------------------------------------------------------------------
   __shared__ __align__(16) NdtControl ctl;
   __shared__ int abort_flag;
   __shared__ __align__(8) unsigned long long tma_bar;
-  __shared__ float acc_s[ACC_SLOTS][ACC_STRIDE];
   __shared__ float4 pts_s[SMEM_POINTS];
+  // dynamic shared memory: [rank index, L.acc_offset bytes][per-thread f32 accumulators]
+  float (*acc_s)[ACC_STRIDE] = reinterpret_cast<float (*)[ACC_STRIDE]>(dyn_smem + L.acc_offset);
   const RankWord* idx = L.index_in_smem ? reinterpret_cast<const RankWord*>(dyn_smem) : L.index;
 
   // stage the voxel rank index into shared memory with TMA bulk copies (once per launch)
@@ -1066,7 +1023,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
   // hit the same voxels, so a warp's record loads coalesce), unit u going to evaluator u mod n_eval: every CTA gets a
   // mix of near and far rings, which evens out the per-CTA evaluation time (measured 2.3 .. 5.1 us with contiguous
   // chunks — the evaluation is issue-bound and the barrier waits for the slowest CTA).
-  const int n_eval = role.n_eval;
+  const int n_eval = n_eval_ctas;
   const int n_units = (L.n_src + 31) >> 5;
   const int my_units = (n_units > my_rank) ? (n_units - my_rank + n_eval - 1) / n_eval : 0;
   const int n_local = my_units * 32;  // local slots (the last unit of the scan may be ragged)
@@ -1077,11 +1034,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
     pts_s[j] = (gi < L.n_src) ? L.src[gi] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding slot of the ragged last unit
   }
 
-  unsigned my_gen = 0;
-  if (tid == 0) {
-    my_gen = ld_relaxed_gpu(&W->gen);
-    abort_flag = 0;
-  }
+  if (tid == 0) abort_flag = 0;
   {  // round-0 control: from the launch parameters (fresh solve) or from the work area (resume after K2)
     const int* src = L.resume ? reinterpret_cast<const int*>(&W->control) : reinterpret_cast<const int*>(&L.init);
     int* dst = reinterpret_cast<int*>(&ctl);
@@ -1131,7 +1084,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
     }
     skip_eval = false;
     B200_STAMP(stamp0, round, 1);
-    if (L.timing && tid == 0 && round == 2) W->cta_eval_ns[my_rank] = (unsigned)(globaltimer_ns() - t_round);
+    if (L.timing && tid == 0 && round == 2) {
+      W->cta_eval_ns[my_rank][0] = (unsigned)t_round;
+      W->cta_eval_ns[my_rank][1] = (unsigned)globaltimer_ns();
+    }
 
     // ---- (2) per-warp reduction: lane L sums slot L over the warp's 32 columns in fixed order (f64), CTA partial --
     if (acc.first) {
@@ -1149,8 +1105,15 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
       double v = 0.0;
       if (lane >= SLOT_G && lane < SLOT_G + ACC_SLOTS) {
         const float* row = &acc_s[lane - SLOT_G][warp * 32];
-#pragma unroll 8
-        for (int t = 0; t < 32; t++) v += (double)row[t];
+        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // four independent chains, fixed order
+#pragma unroll
+        for (int t = 0; t < 32; t += 4) {
+          v0 += (double)row[t];
+          v1 += (double)row[t + 1];
+          v2 += (double)row[t + 2];
+          v3 += (double)row[t + 3];
+        }
+        v = (v0 + v1) + (v2 + v3);
       } else if (lane == SLOT_SCORE) {
         v = sc;
       } else if (lane == SLOT_HITS) {
@@ -1159,38 +1122,47 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
       warp_part[warp][lane] = v;
     }
     __syncthreads();
-    if (tid < SLOT_COUNT) {  // warp 0: 31 sums, then the sequence tag with release semantics
-      double s = 0;
+    if (tid < SLOT_COUNT) {  // warp 0: one plain 8-byte store per slot; a written slot can never equal NDT_PARTIAL_EMPTY
+      double sa = 0, sb = 0, sc2 = 0, sd = 0;  // four independent chains, fixed order
 #pragma unroll
-      for (int w = 0; w < SOLVER_WARPS; w++) s += warp_part[w][tid];
-      if (tid != SLOT_TAG) W->partials[my_rank][tid] = s;
-      __syncwarp();
-      if (tid == SLOT_TAG) st_release_gpu_f64(&W->partials[my_rank][SLOT_TAG], round_tag(L.epoch, round));
+      for (int w = 0; w < SOLVER_WARPS; w += 4) {
+        sa += warp_part[w][tid];
+        sb += warp_part[w + 1][tid];
+        sc2 += warp_part[w + 2][tid];
+        sd += warp_part[w + 3][tid];
+      }
+      const double s = (sa + sb) + (sc2 + sd);
+      st_relaxed_gpu_u64(reinterpret_cast<unsigned long long*>(&W->partials[round & 1][my_rank][tid]),
+                         (unsigned long long)__double_as_longlong(s));
+      if (L.timing && round == 2 && tid == 0) W->cta_eval_ns[my_rank][2] = (unsigned)globaltimer_ns();
     }
     B200_STAMP(stamp0, round, 2);
+    B200_STAMP(stamp0, round, 3);
 
-    // ---- (3) arrive (release) and wait for the controller CTA to publish the next control block ------------
-    if (tid == 0) {
-      B200_STAMP(stamp0, round, 3);
-      long long t0 = clock64();
-      while (ld_relaxed_gpu(&W->gen) == my_gen) {
+    // ---- (3) wait for the controller CTA's next control block: thread k polls word k until it carries this round's
+    // sequence number (one 64-bit load brings payload and validity together) ---------------------------------------
+    if (tid < NDT_CONTROL_WORDS) {
+      const unsigned long long* wsrc = &W->ctl_ll[my_rank % NDT_CTL_COPIES][tid];
+      const unsigned want = ctl_sequence(L.epoch, round);
+      const long long t0 = clock64();
+      unsigned long long v;
+      for (;;) {
+        v = ld_relaxed_gpu_u64(wsrc);
+        if ((unsigned)(v >> 32) == want) break;
         if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
           W->result.error = 1;
           abort_flag = 1;
           break;
         }
       }
-      fence_acq_rel_gpu();
-      my_gen += 1;
+      reinterpret_cast<unsigned*>(&ctl)[tid] = (unsigned)v;
       B200_STAMP(stamp0, round, 7);
     }
-    __syncthreads();
-    {  // next round's control block (written by the controller CTA; read through L2)
-      const int* src = reinterpret_cast<const int*>(&W->control);
-      int* dst = reinterpret_cast<int*>(&ctl);
-      for (int k = tid; k < NDT_CONTROL_WORDS; k += SOLVER_THREADS) dst[k] = __ldcg(src + k);
-    }
   }
+}
+
+__global__ void arm_partials_kernel(unsigned long long* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = NDT_PARTIAL_EMPTY;
 }
 
 using KernelFn = void (*)(const NdtLaunch);
@@ -1222,18 +1194,18 @@ void NdtSolver::init(int device, cudaStream_t s) {
   max_smem_optin_ = (int)prop.sharedMemPerBlockOptin;
   B200_CUDA(cudaMalloc(&d_work_, sizeof(NdtSolverWork)));
   B200_CUDA(cudaMemset(d_work_, 0, sizeof(NdtSolverWork)));
-  {
-    NdtRoles init[2] = {{0xffffffffu, 0, 0, 0}, {0xffffffffu, 0, 0, 0}};
-    B200_CUDA(cudaMemcpy(d_work_->roles, init, sizeof(init), cudaMemcpyHostToDevice));
-  }
+  arm_partials_kernel<<<296, 256>>>(reinterpret_cast<unsigned long long*>(&d_work_->partials[0][0][0]),
+                                    (size_t)2 * NDT_MAX_CTAS * SLOT_COUNT);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaDeviceSynchronize());
   B200_CUDA(cudaMallocHost(&h_result_, sizeof(NdtResult)));
   std::memset(h_result_, 0, sizeof(NdtResult));
   for (int m = 0; m < 4; m++)
-    B200_CUDA(cudaFuncSetAttribute(kernel_for(m), cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+    B200_CUDA(cudaFuncSetAttribute(kernel_for(m), cudaFuncAttributeMaxDynamicSharedMemorySize, SOLVER_MAX_DYN_SMEM));
 }
 
 void NdtSolver::read_cta_eval_ns(unsigned* out, int n) const {
-  B200_CUDA(cudaMemcpy(out, d_work_->cta_eval_ns, sizeof(unsigned) * n, cudaMemcpyDeviceToHost));
+  B200_CUDA(cudaMemcpy(out, d_work_->cta_eval_ns, sizeof(unsigned) * 4 * n, cudaMemcpyDeviceToHost));
 }
 void NdtSolver::read_timing(unsigned long long* out) const {
   B200_CUDA(cudaMemcpy(out, d_work_->timing, sizeof(unsigned long long) * NDT_TIMING_ROUNDS * NDT_TIMING_SLOTS,
@@ -1244,9 +1216,11 @@ const double* NdtSolver::state_hd() const { return d_work_->state.hd; }
 const float* NdtSolver::control_T() const { return d_work_->control.T; }
 
 void NdtSolver::reset_barrier() {
-  B200_CUDA(cudaMemsetAsync(d_work_, 0, 16, stream_));  // arrive, gen, error, pad
-  NdtRoles init[2] = {{0xffffffffu, 0, 0, 0}, {0xffffffffu, 0, 0, 0}};
-  B200_CUDA(cudaMemcpyAsync(d_work_->roles, init, sizeof(init), cudaMemcpyHostToDevice, stream_));
+  // after a watchdog abort: clear the error word, re-arm every partial slot and the role-election counters
+  B200_CUDA(cudaMemsetAsync(d_work_, 0, 16, stream_));
+  arm_partials_kernel<<<296, 256, 0, stream_>>>(reinterpret_cast<unsigned long long*>(&d_work_->partials[0][0][0]),
+                                                (size_t)2 * NDT_MAX_CTAS * SLOT_COUNT);
+  B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaStreamSynchronize(stream_));
 }
 
@@ -1267,8 +1241,8 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   L.resume = resume;
   L.timing = timing_enabled ? 1 : 0;
   L.scalar_controller = scalar_controller ? 1 : 0;
+  L.no_warmup = no_warmup ? 1 : 0;
   L.epoch = epoch_++;
-  L.exclusive_sm = exclusive_sm ? 1 : 0;
   L.max_iterations = cfg.max_iterations;
   L.resolution = cfg.resolution;
   L.radius2 = static_cast<float>((double)cfg.resolution * (double)cfg.resolution);
@@ -1304,21 +1278,23 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   L.init.mode = EVAL_DERIV;
   L.init.compute_hessian = compute_hessian;
 
-  // shared-memory staging of the rank index when it fits
-  const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 15) & ~(size_t)15;
+  // dynamic shared memory: the rank index when it fits (<= 64 KB), then the per-thread accumulators; the controller
+  // CTA overlays its own state on the same bytes
+  const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 127) & ~(size_t)127;
   L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= 64 * 1024) ? 1 : 0;
-  size_t dyn_smem = std::max(L.index_in_smem ? index_bytes : (size_t)0, sizeof(CtlShared));
-  dyn_smem = (dyn_smem + 15) & ~(size_t)15;
+  L.acc_offset = L.index_in_smem ? (int)index_bytes : 0;
+  size_t dyn_smem = std::max((size_t)L.acc_offset + ACC_BYTES, sizeof(CtlShared));
+  dyn_smem = (dyn_smem + 127) & ~(size_t)127;
 
   KernelFn fn = kernel_for(cfg.search_method);
   int per_sm = 0;
   B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SOLVER_THREADS, dyn_smem));
   if (per_sm < 1) throw CudaError("ndt_solver_kernel does not fit on an SM");
-  const int max_ctas = std::min(per_sm * sm_count_, NDT_MAX_CTAS);
-  // evaluator CTAs: one point per thread when the scan is small; otherwise every resident slot, so that each SM gets
-  // the same number of points (the evaluation is issue-bound per SM)
-  const int want = (int)((n_src + SOLVER_THREADS - 1) / SOLVER_THREADS);
-  const int n_eval = (want + 1 > sm_count_) ? (max_ctas - 1) : std::max(1, want);
+  const int max_ctas = std::min(sm_count_, NDT_MAX_CTAS);  // one CTA per SM, all co-resident (cooperative launch)
+  // evaluator CTAs: every SM but the controller's as soon as each gets at least four warps of points (the evaluation
+  // is issue-bound per SM, so spreading thin beats filling CTAs)
+  const int want = (int)((n_src + 127) / 128);
+  const int n_eval = std::max(1, std::min(want, max_ctas - 1));
   grid_ = n_eval + 1;  // + the controller CTA
   block_ = SOLVER_THREADS;
   index_in_smem_ = L.index_in_smem;

@@ -5,7 +5,7 @@
 
 namespace b200 {
 
-constexpr int NDT_MAX_CTAS = 148 * 8;
+constexpr int NDT_MAX_CTAS = 256;  // one CTA per SM
 
 enum EvalMode : int {
   EVAL_DERIV = 0,        // fused derivative pass (K1)
@@ -39,28 +39,32 @@ struct NdtState {
 };
 
 constexpr int NDT_TIMING_ROUNDS = 48;
-constexpr int NDT_TIMING_SLOTS = 10;
+constexpr int NDT_TIMING_SLOTS = 12;
 // slots (globaltimer ns): 0 CTA0 round start, 1 CTA0 after evaluate, 2 CTA0 partial written, 3 CTA0 arrived,
 //                         4 last CTA detected, 5 partials reduced, 6 controller done, 7 CTA0 released
-struct NdtRoles {        // per-launch role election (see ndt_solver.cu: elect_roles)
-  unsigned ctrl_smid;    // SM id claimed by the controller CTA (0xffffffff = unclaimed)
-  unsigned n_rank;       // evaluator ranks handed out so far
-  unsigned registered;   // CTAs that finished registering
-  unsigned pad;
-};
+// Signalling between the evaluator CTAs and the controller CTA carries its own validity ("flag in data", as in NCCL's
+// LL protocol), so neither direction needs a counter, a fence or a second dependent round trip:
+//  * control block, controller -> evaluators: every 32-bit word travels as one 64-bit store {payload, sequence}; an
+//    evaluator thread polls ITS word until the sequence number is the expected one. NDT_CTL_COPIES replicas spread
+//    the pollers over L2 lines.
+//  * partial sums, evaluators -> controller: rows of 32 doubles, double-buffered by round parity; an unwritten slot
+//    holds NDT_PARTIAL_EMPTY (a NaN payload no computation produces). The controller's reduction loads double as the
+//    poll; it re-arms each row after consuming it, two rounds before the row is written again.
+constexpr int NDT_CTL_COPIES = 4;
+constexpr int NDT_CTL_LL_WORDS = 96;  // >= NDT_CONTROL_WORDS, whole 128-byte lines
+constexpr unsigned long long NDT_PARTIAL_EMPTY = 0xFFF8DEADFFF8DEADull;
+constexpr int NDT_MAX_ROUNDS = 60000;  // sequence numbers are epoch * 65536 + round + 1
 
 struct NdtSolverWork {
-  unsigned arrive;
-  unsigned gen;
   unsigned error;
-  unsigned pad;
-  NdtRoles roles[2];     // indexed by launch parity
-  NdtControl control;
+  unsigned pad[3];
+  NdtControl control;    // plain copy of the control block, written only when the kernel leaves for a K2 pass
   NdtState state;
   NdtResult result;
-  alignas(16) double partials[NDT_MAX_CTAS][SLOT_COUNT];
+  alignas(128) unsigned long long ctl_ll[NDT_CTL_COPIES][NDT_CTL_LL_WORDS];
+  alignas(128) double partials[2][NDT_MAX_CTAS][SLOT_COUNT];
   unsigned long long timing[NDT_TIMING_ROUNDS][NDT_TIMING_SLOTS];
-  unsigned cta_eval_ns[NDT_MAX_CTAS];  // timing mode: evaluate duration of every CTA in round 2
+  unsigned cta_eval_ns[NDT_MAX_CTAS][4];  // timing mode, round 2, low 32 bits of globaltimer: start, evaluate end, published
 };
 
 struct NdtLaunch {
@@ -75,9 +79,10 @@ struct NdtLaunch {
   int n_voxels;
   int search_method;
   int mode;    // NdtMode
-  unsigned epoch;         // launch counter of this handle (parity selects the role-election counters)
-  int exclusive_sm;       // 1: the controller CTA claims an SM for itself (CTAs sharing it retire)
+  unsigned epoch;         // launch counter of this handle (high half of the control block's sequence numbers)
+  int acc_offset;         // byte offset of the per-thread accumulators in dynamic shared memory (after the rank index)
   int scalar_controller;  // 1: disable the warp-parallel controller fast path (developer switch)
+  int no_warmup;          // 1: warp 0 of the controller CTA just spins while it waits (developer switch)
   int timing;  // 1: record per-phase globaltimer stamps into work->timing (developer instrumentation)
   int resume;  // 1: state/control already in work (after a K2 pass); first round skips the evaluation
   int index_in_smem;

@@ -25,7 +25,7 @@ for _ in range(int(os.environ.get("DIAG_WARM", "3"))):
     T = g.align()
 st = g.stats()
 print("stats", st)
-buf = np.zeros((48, 10), dtype=np.uint64)
+buf = np.zeros((48, 12), dtype=np.uint64)
 L = _capi.lib()
 L.b200reg_debug_timing.argtypes = [C.c_void_p, C.c_void_p]
 L.b200reg_debug_timing(g._h, buf.ctypes.data_as(C.c_void_p))
@@ -46,21 +46,26 @@ for r in rows:
     print(" ".join(f"{v:22.2f}" for v in r))
 print("median:")
 print(" ".join(f"{v:22.2f}" for v in np.median(rows[1:-1], axis=0)))
-dry1 = (t[:, 8] - t[:, 5]) / 1e3
-dry2 = (t[:, 9] - t[:, 8]) / 1e3
-real = (t[:, 6] - t[:, 9]) / 1e3
-print("controller_fast dry pass 1 us:", np.round(dry1[1:-1], 2))
-print("controller_fast dry pass 2 us:", np.round(dry2[1:-1], 2))
-print("real pass + build_control + publish us:", np.round(real[1:-1], 2))
+print("reducing warps finished (us before warp 0 noticed): first", np.round((t[1:-1, 4] - t[1:-1, 10]) / 1e3, 2), "last", np.round((t[1:-1, 4] - t[1:-1, 11]) / 1e3, 2))
+print("CTA0 published -> last reducing warp done (us):", np.round((t[1:-1, 11].astype(np.int64) - t[1:-1, 2].astype(np.int64)) / 1e3, 2))
+print("controller: step", np.round((t[1:-1, 8] - t[1:-1, 5]) / 1e3, 2), "build_control", np.round((t[1:-1, 9] - t[1:-1, 8]) / 1e3, 2), "publish", np.round((t[1:-1, 6] - t[1:-1, 9]) / 1e3, 2))
 
 nc = st["grid_ctas"] - 1
-ce = np.zeros(nc, dtype=np.uint32)
+ce = np.zeros((nc, 4), dtype=np.uint32)
 L.b200reg_debug_cta_eval_ns.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
 L.b200reg_debug_cta_eval_ns(g._h, ce.ctypes.data_as(C.c_void_p), nc)
-ce = ce / 1e3
-print("per-CTA evaluate us (round 2): min %.2f p10 %.2f median %.2f p90 %.2f max %.2f" % (ce.min(), np.percentile(ce, 10), np.median(ce), np.percentile(ce, 90), ce.max()))
-print("  by CTA index (every 16th):", np.round(ce[::16], 2))
-print("  slowest CTAs:", np.argsort(ce)[-8:], np.round(np.sort(ce)[-8:], 2))
+rel = np.uint32(int(t[1][6]) & 0xffffffff)   # controller published round 1's control block -> round 2 starts
+det = ((np.uint32(int(t[2][4]) & 0xffffffff) - rel).astype(np.int32)) / 1e3
+start = (ce[:, 0] - rel).astype(np.int32) / 1e3
+evend = (ce[:, 1] - rel).astype(np.int32) / 1e3
+pub = (ce[:, 2] - rel).astype(np.int32) / 1e3
+def q(name, v):
+    print(f"  {name:28s} min {v.min():6.2f} p10 {np.percentile(v,10):6.2f} med {np.median(v):6.2f} p90 {np.percentile(v,90):6.2f} max {v.max():6.2f}  (argmax {int(np.argmax(v))})")
+print(f"round 2, per evaluator CTA, us after the controller's release (controller saw all rows at {det:.2f}):")
+q("start (gen seen)", start); q("evaluate end", evend); q("published", pub)
+q("evaluate duration", evend - start); q("cta reduce+publish", pub - evend)
+late = np.argsort(pub)[-6:]
+print("  latest publishers:", late, "start", np.round(start[late], 2), "eval", np.round((evend - start)[late], 2), "pub", np.round(pub[late], 2))
 
 # entrywise (g, H) parity with per-entry scale sqrt(|Hii Hjj|)
 o = oracle.NDT(resolution=res, transformation_epsilon=0.01)
