@@ -57,17 +57,47 @@ def make_workload(name: str, rank: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The timed region of
+    this bench lasts milliseconds, so the sampler polls NVML in-process (nvidia_ml_py) every millisecond; an
+    `nvidia-smi -lms` child, the recipe's literal form, would not deliver a single sample in that time and is only the
+    fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
     def __init__(self, gpu_index: int):
         self.gpu = gpu_index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.sm, self.mask = [], 0
+        self.mx = None
+        self._stop = threading.Event()
+
+    def _nvml_handle(self):
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+        return pynvml, h
 
     def start(self):
+        try:
+            self.nvml, self.h = self._nvml_handle()
+            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
+            self._sample()
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                           "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -76,11 +106,32 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def _sample(self):
+        self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+
+    def _poll(self):
+        while not self._stop.is_set():
+            try:
+                self._sample()
+            except Exception:
+                break
+            time.sleep(0.001)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self) -> dict:
+        if self.nvml is not None:
+            self._stop.set()
+            self.t.join(timeout=1)
+            reasons = sorted(name for bit, name in self.REASONS if self.mask & bit)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
+                    "samples": len(self.sm), "reasons": reasons, "source": "nvml, 1 ms polling inside the timed region"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -99,7 +150,18 @@ class ClockSampler:
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 200"}
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the solver kernel, from the committed ncu --set full
+    capture (profiles/r1_ndt_solver_traffic.json, same workload; bench.py itself never runs under a profiler)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_ndt_solver_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"])
+    except Exception:
+        return None
 
 
 def hbm_peak():
@@ -140,10 +202,24 @@ def run_reference(args, rank, world):
     import oracle
 
     oracle.build()
-    nt = oracle.max_threads()
+    # thread count: whatever is fastest here — all hardware threads, or one per physical core (SMT siblings often hurt
+    # this memory-bound loop); one probe align each after a common warm-up
+    cand = sorted({oracle.max_threads(), max(1, (os.cpu_count() or 2) // 2), max(1, os.cpu_count() or 1)}, reverse=True)
+    best = None
+    for c in cand:
+        n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=c)
+        n.set_target(tgt)
+        n.set_source(scans[0])
+        n.align()  # builds the lazy target kd-tree like PCL's first align
+        t0 = time.perf_counter()
+        n.align()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, c)
+    nt = best[1]
     n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=nt)
     n.set_target(tgt)
-    for w in range(min(args.warmup, 3)):
+    for w in range(max(1, min(args.warmup, 3))):
         n.set_source(scans[w % len(scans)])
         n.align()
     t_total = 0.0
@@ -161,7 +237,7 @@ def run_reference(args, rank, world):
         "config": {"workload": desc, "n_source": int(len(scans[0])), "n_target": int(len(tgt)),
                    "note": "reference cannot be compiled here (PCL/Eigen/FLANN absent): CPU restatement oracle/ (kind=port)"},
         "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": nt, "kind": "port",
-                         "sample": f"{args.steps} full align() calls, {nt} OpenMP threads, host has {os.cpu_count()} cpus"},
+                         "sample": f"{args.steps} full align() calls, {nt} OpenMP threads (fastest of {cand}), host has {os.cpu_count()} cpus"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -388,7 +464,7 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ndt_solver_kernel<DIRECT7> (persistent: all evaluations of one align)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                         "traffic": None, "alg_bytes_per_launch": float(np.mean(alg_bytes)),
+                         "traffic": ncu_traffic(), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
                          "launch_ms": float(np.mean(solve_ms)), "evaluations_per_launch": float(np.mean(evals)),
                          "us_per_evaluation": 1e3 * float(np.sum(solve_ms)) / max(1, int(np.sum(evals))),
                          "hits_per_point": float(np.sum(hits_tot)) / max(1, int(np.sum(evals))) / max(1, len(scans[0]))},

@@ -139,6 +139,7 @@ int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
   }
   B200_CUDA(cudaEventRecord(h->ev0, h->stream));
   h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
+  B200_CUDA(cudaEventRecord(h->ev1, h->stream));  // solve_ms brackets the kernel(s) on the stream, nothing host-side
   h->align_pending = true;
   return B200REG_OK;
 }
@@ -148,6 +149,7 @@ int ndt_align_end(b200reg_t h) {
   h->align_pending = false;
   for (int rounds = 0; rounds < 4096; rounds++) {
     B200_CUDA(cudaStreamSynchronize(h->stream));
+    if (h->solver.result().error == 3) h->solver.fetch_result();
     const NdtResult& r = h->solver.result();
     if (r.error == 100) {
       // the More-Thuente loop ran (only when step_max <= step_min): f64 radius Hessian (K2), then resume
@@ -159,6 +161,7 @@ int ndt_align_end(b200reg_t h) {
       float dummyT[16];
       set_identity(dummyT);
       h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, dummyT, nullptr, 1, 1);
+      B200_CUDA(cudaEventRecord(h->ev1, h->stream));
       continue;
     }
     if (r.error != 0) {
@@ -166,8 +169,6 @@ int ndt_align_end(b200reg_t h) {
       B200_CUDA(cudaStreamSynchronize(h->stream));
       return fail(h, B200REG_ERR_TIMEOUT, "NDT solver kernel watchdog fired (grid barrier timeout)");
     }
-    B200_CUDA(cudaEventRecord(h->ev1, h->stream));
-    B200_CUDA(cudaEventSynchronize(h->ev1));
     B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
     std::memcpy(h->final_T, r.final_T, sizeof(h->final_T));
     h->converged = r.converged;
@@ -255,7 +256,7 @@ int b200reg_create(int kind, int device, b200reg_t* out) {
     h->solver.init(device, h->stream);
     h->solver.timing_enabled = getenv("B200REG_TIMING") != nullptr;
     h->solver.scalar_controller = getenv("B200REG_SCALAR_CTL") != nullptr;
-    h->solver.no_warmup = getenv("B200REG_NO_WARMUP") != nullptr;
+    h->solver.plain_launch = getenv("B200REG_PLAIN_LAUNCH") != nullptr;
     h->gicp_solver.init(device, h->stream);
     if (kind == B200REG_GICP) {
       h->corr_dist = 5.0;  // gicp_omp.h:119
@@ -589,6 +590,7 @@ int b200reg_ndt_derivatives(b200reg_t h, const float* T, const double* p6, int c
     B200_CUDA(cudaEventRecord(h->ev1, h->stream));
     B200_CUDA(cudaStreamSynchronize(h->stream));
     B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
+    if (h->solver.result().error == 3) h->solver.fetch_result();
     const NdtResult& r = h->solver.result();
     if (r.error != 0) {
       h->solver.reset_barrier();

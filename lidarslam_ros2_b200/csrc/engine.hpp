@@ -181,11 +181,12 @@ class NdtSolver {
   int index_in_smem() const { return index_in_smem_; }
   int launches = 0;
   bool scalar_controller = false;  // developer switch (env B200REG_SCALAR_CTL=1)
-  bool no_warmup = false;          // developer switch (env B200REG_NO_WARMUP=1)
+  bool plain_launch = false;       // developer switch (env B200REG_PLAIN_LAUNCH=1): non-cooperative launch
   bool timing_enabled = false;  // developer instrumentation (env B200REG_TIMING=1)
   void read_timing(unsigned long long* out48x8) const;
   void read_cta_eval_ns(unsigned* out, int n) const;
   void reset_barrier();
+  void fetch_result();
 
  private:
   int device_ = 0;
@@ -194,6 +195,7 @@ class NdtSolver {
   int grid_ = 0, block_ = 0, index_in_smem_ = 0;
   int max_smem_optin_ = 0;
   unsigned epoch_ = 0;
+  bool fits_checked_ = false;
   NdtSolverWork* d_work_ = nullptr;
   NdtResult* h_result_ = nullptr;  // pinned
 };

@@ -40,7 +40,8 @@ constexpr int SMEM_POINTS = 1024;  // source points of a CTA's chunk staged in s
 constexpr int ACC_SLOTS = 27;      // 6 gradient + 21 upper-triangular Hessian sums per thread (f32, in shared memory)
 constexpr int ACC_STRIDE = SOLVER_THREADS + 1;
 constexpr int ACC_BYTES = ACC_SLOTS * ACC_STRIDE * 4;
-constexpr int SOLVER_MAX_DYN_SMEM = 64 * 1024 + ACC_BYTES;  // rank index (<= 64 KB) + accumulators  // padded row: slot-major reads by 32 lanes hit 32 different banks
+constexpr int SOLVER_MAX_INDEX_SMEM = 64 * 1024;  // the rank index is staged in shared memory up to this size
+constexpr int SOLVER_MAX_DYN_SMEM = SOLVER_MAX_INDEX_SMEM + ACC_BYTES;  // the rest of the SM stays L1 for the voxel-record gathers (a 100 KB index in shared memory measured slower)  // padded row: slot-major reads by 32 lanes hit 32 different banks
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s device-side watchdog, never reached in normal runs
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -971,6 +972,15 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
     for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += SOLVER_THREADS) dst[k] = src[k];
     if (tid == 0) W->result.error = 100;
   }
+  // the result goes straight to the host (pinned memory mapped into the device address space): the host reads it as
+  // soon as the stream has drained, no device-to-host copy on the critical path
+  __syncthreads();
+  {
+    const int* src = reinterpret_cast<const int*>(&W->result);
+    int* dst = reinterpret_cast<int*>(L.result_host);
+    for (int k = tid; k < (int)(sizeof(NdtResult) / 4); k += SOLVER_THREADS) dst[k] = __ldcg(src + k);
+    __threadfence_system();
+  }
 }
 
 // =====================================================================================================
@@ -991,6 +1001,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
     return;
   }
   const int my_rank = (int)blockIdx.x;
+  if (L.timing && my_rank == 0 && tid == 0) W->timing[NDT_TIMING_ROUNDS - 1][0] = globaltimer_ns();  // kernel entry
 
   // ---- evaluator CTAs --------------------------------------------------------------------------------------
   __shared__ __align__(16) NdtControl ctl;
@@ -1046,6 +1057,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
       if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) break;
     }
   }
+  if (L.timing && my_rank == 0 && tid == 0) W->timing[NDT_TIMING_ROUNDS - 1][1] = globaltimer_ns();  // prologue done
   bool skip_eval = L.resume != 0;
   const bool stamp0 = (my_rank == 0 && tid == 0);
   const float gd2 = (float)L.d2;
@@ -1215,6 +1227,11 @@ const double* NdtSolver::state_jd() const { return d_work_->state.jd; }
 const double* NdtSolver::state_hd() const { return d_work_->state.hd; }
 const float* NdtSolver::control_T() const { return d_work_->control.T; }
 
+void NdtSolver::fetch_result() {  // slow path: the kernel did not get to write the host copy
+  B200_CUDA(cudaMemcpyAsync(h_result_, &d_work_->result, sizeof(NdtResult), cudaMemcpyDeviceToHost, stream_));
+  B200_CUDA(cudaStreamSynchronize(stream_));
+}
+
 void NdtSolver::reset_barrier() {
   // after a watchdog abort: clear the error word, re-arm every partial slot and the role-election counters
   B200_CUDA(cudaMemsetAsync(d_work_, 0, 16, stream_));
@@ -1233,6 +1250,8 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   L.icov_d = map.icov_d.ptr;
   L.centroids = map.centroids.ptr;
   L.work = d_work_;
+  L.result_host = h_result_;
+  h_result_->error = 3;  // "the kernel never wrote a result"
   L.geom = map.geom;
   L.n_src = (int)n_src;
   L.n_voxels = (int)map.n_voxels;
@@ -1241,7 +1260,6 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   L.resume = resume;
   L.timing = timing_enabled ? 1 : 0;
   L.scalar_controller = scalar_controller ? 1 : 0;
-  L.no_warmup = no_warmup ? 1 : 0;
   L.epoch = epoch_++;
   L.max_iterations = cfg.max_iterations;
   L.resolution = cfg.resolution;
@@ -1281,15 +1299,18 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   // dynamic shared memory: the rank index when it fits (<= 64 KB), then the per-thread accumulators; the controller
   // CTA overlays its own state on the same bytes
   const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 127) & ~(size_t)127;
-  L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= 64 * 1024) ? 1 : 0;
+  L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= (size_t)SOLVER_MAX_INDEX_SMEM) ? 1 : 0;
   L.acc_offset = L.index_in_smem ? (int)index_bytes : 0;
   size_t dyn_smem = std::max((size_t)L.acc_offset + ACC_BYTES, sizeof(CtlShared));
   dyn_smem = (dyn_smem + 127) & ~(size_t)127;
 
   KernelFn fn = kernel_for(cfg.search_method);
-  int per_sm = 0;
-  B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SOLVER_THREADS, dyn_smem));
-  if (per_sm < 1) throw CudaError("ndt_solver_kernel does not fit on an SM");
+  if (!fits_checked_) {  // the largest configuration (64 KB index + accumulators) fits or nothing does
+    int per_sm = 0;
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SOLVER_THREADS, SOLVER_MAX_DYN_SMEM));
+    if (per_sm < 1) throw CudaError("ndt_solver_kernel does not fit on an SM");
+    fits_checked_ = true;
+  }
   const int max_ctas = std::min(sm_count_, NDT_MAX_CTAS);  // one CTA per SM, all co-resident (cooperative launch)
   // evaluator CTAs: every SM but the controller's as soon as each gets at least four warps of points (the evaluation
   // is issue-bound per SM, so spreading thin beats filling CTAs)
@@ -1300,9 +1321,12 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   index_in_smem_ = L.index_in_smem;
 
   void* args[] = {&L};
-  B200_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
+  if (plain_launch) {  // developer switch: measure what the cooperative launch costs
+    B200_CUDA(cudaLaunchKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
+  } else {
+    B200_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
+  }
   launches += 1;
-  B200_CUDA(cudaMemcpyAsync(h_result_, &d_work_->result, sizeof(NdtResult), cudaMemcpyDeviceToHost, stream_));
 }
 
 }  // namespace b200

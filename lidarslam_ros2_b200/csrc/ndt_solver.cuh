@@ -74,6 +74,7 @@ struct NdtLaunch {
   const double* icov_d;
   const float4* centroids;
   NdtSolverWork* work;
+  NdtResult* result_host;  // pinned, device-visible host memory: the controller CTA writes the result there on exit
   GridGeom geom;
   int n_src;
   int n_voxels;
@@ -82,7 +83,6 @@ struct NdtLaunch {
   unsigned epoch;         // launch counter of this handle (high half of the control block's sequence numbers)
   int acc_offset;         // byte offset of the per-thread accumulators in dynamic shared memory (after the rank index)
   int scalar_controller;  // 1: disable the warp-parallel controller fast path (developer switch)
-  int no_warmup;          // 1: warp 0 of the controller CTA just spins while it waits (developer switch)
   int timing;  // 1: record per-phase globaltimer stamps into work->timing (developer instrumentation)
   int resume;  // 1: state/control already in work (after a K2 pass); first round skips the evaluation
   int index_in_smem;

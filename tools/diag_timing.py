@@ -50,6 +50,16 @@ print("reducing warps finished (us before warp 0 noticed): first", np.round((t[1
 print("CTA0 published -> last reducing warp done (us):", np.round((t[1:-1, 11].astype(np.int64) - t[1:-1, 2].astype(np.int64)) / 1e3, 2))
 print("controller: step", np.round((t[1:-1, 8] - t[1:-1, 5]) / 1e3, 2), "build_control", np.round((t[1:-1, 9] - t[1:-1, 8]) / 1e3, 2), "publish", np.round((t[1:-1, 6] - t[1:-1, 9]) / 1e3, 2))
 
+print("kernel prologue (entry -> first round) us:", (int(buf[47][1]) - int(buf[47][0])) / 1e3,
+      " entry -> last publish us:", (int(t[E - 1][6]) - int(buf[47][0])) / 1e3, " solve_ms(events) us:", st["solve_ms"] * 1e3)
+import time
+for rep in range(3):
+    t0 = time.perf_counter()
+    for _ in range(200):
+        g.align()
+    dt = (time.perf_counter() - t0) / 200
+    print("host wall per align() us: %.1f   solve_ms us: %.1f" % (dt * 1e6, g.stats()["solve_ms"] * 1e3))
+
 nc = st["grid_ctas"] - 1
 ce = np.zeros((nc, 4), dtype=np.uint32)
 L.b200reg_debug_cta_eval_ns.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
