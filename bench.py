@@ -49,8 +49,8 @@ def make_workload(name: str, rank: int):
     scene = synth.make_scene()
     scans = [src0]
     d = np.pi / 180.0
-    for k in range(1, N_SCANS):  # nearby sensor poses → different scans, same map
-        s = 1.0 + 0.15 * k + 0.07 * rank
+    for k in range(1, N_SCANS):  # nearby sensor poses → different scans, same map; every rank gets the same poses
+        s = 1.0 + 0.15 * k        # (same work per GPU: weak scaling) with its own noise stream
         T = synth.pose_matrix((0.40 * s, -0.25 * s, 0.06), (0.4 * d, -0.3 * d * s, 1.5 * d * s))
         scans.append(synth.make_scan(scene, rings, azim, synth.sensor_pose(T), stream=9000 + 10 * k + 100 * rank))
     return scans, tgt, res, desc
@@ -90,6 +90,8 @@ class ClockSampler:
 
     def start(self):
         try:
+            if os.environ.get("BENCH_NO_NVML"):
+                raise RuntimeError("nvml disabled")
             self.nvml, self.h = self._nvml_handle()
             self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
             self._sample()
@@ -266,6 +268,9 @@ def run_c4(args, rank, local_rank, world, m):
     if mine:  # warm-up on the first pair
         for _ in range(2):
             batch.register_pair(ndt, data[mine[0]][0], data[mine[0]][1])
+    if world > 1:  # warm-up of the collective (NCCL communicator setup happens on first use)
+        batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world,
+                          device=torch.device("cuda", local_rank))
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = ndt.stats()["kernel_launches"]
@@ -421,9 +426,13 @@ def main():
     total_ms = float(np.sum(step_ms))
     clocks = sampler.stop()
     t_total = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    per_rank = torch.tensor([total_ms, float(np.sum(solve_ms)), float(np.sum(evals))], dtype=torch.float64, device="cuda")
+    per_rank_all = [per_rank.clone() for _ in range(world)]
     if world > 1:
         dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
+        dist.all_gather(per_rank_all, per_rank)
     total_ms_max = float(t_total.item())
+    per_rank_rows = [{"step_ms_sum": float(r[0]), "kernel_ms_sum": float(r[1]), "evaluations": int(r[2])} for r in per_rank_all]
 
     # ---- timed: end to end with host buffers -------------------------------------------------------------
     ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -461,6 +470,7 @@ def main():
                     "h2d_bytes_per_step": int(len(scans[0]) * 16), "d2h_bytes_per_step": 64 + 456,
                     "ms_per_step": e2e_ms_max / K},
             "gpu_launches": int(launches),
+            "per_rank": per_rank_rows,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "ndt_solver_kernel<DIRECT7> (persistent: all evaluations of one align)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
