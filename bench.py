@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — scan-to-map registrations/sec (100k-pt scan vs 1M-pt map) on B200, per BASELINE.json.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload headline|c2|c1|c4]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload headline|c2|c1|c3|c4|c5]
 
 One "step" = one NDT registration (pcl::Registration::align semantics) of a synthetic 64-ring scan (~100k points)
 against a 1M-point map, resolution 2.0, DIRECT7, transformation_epsilon 0.01, max 35 iterations, identity guess —
@@ -245,6 +245,118 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def run_c5(args, rank, local_rank, world, m):
+    """BASELINE config 5: streaming scan-to-growing-map. `--frames` synthetic frames of a drive down the canyon (0.5 m per
+    frame, 32 rings x 1875 azimuths ~ 50k points), per frame the reference's frontend callback: VoxelGrid(0.2) +
+    setInputSource + NDT align (res 5.0 as lidarslam.yaml / sm.cpp:28) from the previous pose, map update every 1.5 m
+    (VoxelGrid(0.1), transform, concatenation of the last 10 submaps, setInputTarget). Host buffers in, pose out:
+    this workload is end to end by construction. Inherently sequential -> 1 GPU (rank 0 only)."""
+    import torch
+
+    from lidarslam_ros2_b200 import synth
+    from lidarslam_ros2_b200.scanmatcher import ScanMatcher
+
+    if rank != 0:
+        return
+    rings, azim = 32, 1875
+    frames = list(synth.drive_stream(args.frames, rings=rings, azimuths=azim, step=0.5, workers=min(32, os.cpu_count() or 1)))
+    kw = dict(ndt_resolution=5.0, vg_size_for_input=0.2, vg_size_for_map=0.1, trans_for_mapupdate=1.5, num_targeted_cloud=10)
+    sm = ScanMatcher(device=local_rank, **kw)
+    warm = ScanMatcher(device=local_rank, **kw)
+    for scan, _ in frames[:4]:  # warm-up on a throw-away session (allocations, first-launch costs)
+        warm.receiveCloud(scan)
+    del warm
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sm.registration.stats()["kernel_launches"]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    t0 = time.perf_counter()
+    errs, n_upd, bytes_in = [], 0, 0
+    for scan, T_gt in frames:
+        pose, final, upd = sm.receiveCloud(scan)
+        n_upd += int(upd)
+        bytes_in += scan.shape[0] * 16
+        errs.append(synth.pose_error(final, T_gt)[0])
+    e1.record()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    st = sm.stats()
+    # CPU restatement of the same callback on a bounded prefix of the same stream
+    import oracle
+    import oracle.scanmatcher as osm
+
+    oracle.build()
+    o = osm.ScanMatcher(num_threads=oracle.max_threads(), **kw)
+    n_cpu, t_cpu, dpose = 0, 0.0, 0.0
+    g2 = ScanMatcher(device=local_rank, **kw)
+    for scan, _ in frames[:min(len(frames), args.cpu_frames)]:
+        c0 = time.perf_counter()
+        po, To, _u = o.receive_cloud(scan)
+        t_cpu += time.perf_counter() - c0
+        n_cpu += 1
+        pg, Tg, _u2 = g2.receiveCloud(scan)
+        dpose = max(dpose, synth.pose_error(Tg, To)[0])
+    v = len(frames) / (ms * 1e-3)
+    line = {
+        "metric": "streaming scan-to-growing-map frames/sec", "value": v, "unit": "frames/s", "n_gpus": 1, "steps": len(frames),
+        "warmup": 4, "ms_per_step": ms / len(frames), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 pair math / f64 reduction", "data": "synthetic",
+        "config": {"workload": f"c5: {len(frames)}-frame drive, {rings}x{azim} rays (~{int(np.mean([len(f[0]) for f in frames]))} pts/frame), "
+                               "VoxelGrid 0.2 + NDT res 5.0 per frame, map update every 1.5 m (VoxelGrid 0.1, last 10 submaps)",
+                   "map_updates": n_upd, "submaps": st["n_submaps"], "targeted_points": st["n_targeted"],
+                   "trajectory_error_m": {"max": float(np.max(errs)), "final": float(errs[-1])},
+                   "l2": "every frame is a new host buffer (one H2D copy per frame)"},
+        "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": int(bytes_in / len(frames)), "d2h_bytes_per_step": 56 + 64 + 456,
+                "wall_s": wall},
+        "gpu_launches": int(sm.registration.stats()["kernel_launches"] - launches0 + st["kernel_launches"]),
+        "clocks": clocks,
+        "roofline": None,
+        "cpu_baseline": {"value": n_cpu / t_cpu if t_cpu > 0 else None, "unit": "frames/s", "cores": oracle.max_threads(), "kind": "port",
+                         "sample": f"first {n_cpu} frames of the same stream through oracle/scanmatcher.py", "pose_parity_max_m": dpose},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_c3(args, rank, local_rank, world, m):
+    """BASELINE config 3: GICP align, 64-ring scan (~100k pts) vs 1M-pt map, corr_dist_threshold 5.0 (replicas per rank)."""
+    import torch
+
+    scans, tgt, res, desc = make_workload("headline", rank)
+    g = m.GeneralizedIterativeClosestPoint(device=local_rank)
+    g.setMaxCorrespondenceDistance(5.0)
+    t0 = time.perf_counter()
+    g.setInputTarget(tgt)
+    g.setInputSource(scans[0])
+    g.align()  # first align computes the target covariances (1M points, k = 20) once
+    first_s = time.perf_counter() - t0
+    K = min(args.steps, 10)
+    e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    poses = []
+    torch.cuda.synchronize()
+    for k in range(K):
+        e[k][0].record()
+        g.setInputSource(scans[k % len(scans)])
+        poses.append(g.align())
+        e[k][1].record()
+    torch.cuda.synchronize()
+    ms = float(np.sum([a.elapsed_time(b) for a, b in e]))
+    if rank != 0:
+        return
+    line = {"metric": "GICP scan-to-map registrations/sec", "value": K / (ms * 1e-3), "unit": "registrations/s", "n_gpus": 1,
+            "steps": K, "warmup": 1, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64 covariances / f64 cost", "data": "synthetic",
+            "config": {"workload": "c3: GICP align, 64-ring scan (~100k pts) vs 1M-pt map, corr_dist 5.0, k=20", "n_source": int(len(scans[0])),
+                       "n_target": int(len(tgt)), "first_align_incl_target_covariances_s": first_s,
+                       "iterations": g.getFinalNumIteration() if hasattr(g, "getFinalNumIteration") else None},
+            "e2e": {"value": K / (ms * 1e-3), "unit": "registrations/s", "h2d_bytes_per_step": int(len(scans[0]) * 16), "d2h_bytes_per_step": 64},
+            "gpu_launches": int(g.stats()["kernel_launches"]), "roofline": None, "cpu_baseline": None}
+    print(json.dumps(line), flush=True)
+
+
 def run_c4(args, rank, local_rank, world, m):
     """BASELINE config 4: batched loop-closure NDT — `--pairs` independent scan<->submap pairs (32-ring scan ~60k pts vs
     200k-pt local map, res 2.0, max_iter 100 as graph_based_slam_component.cpp:66), sharded pair i -> rank i mod N,
@@ -322,8 +434,10 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c4"])
+    ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c3", "c4", "c5"])
     ap.add_argument("--pairs", type=int, default=64, help="c4: number of loop-closure candidate pairs (strong scaling)")
+    ap.add_argument("--frames", type=int, default=200, help="c5: frames of the synthetic drive (BASELINE config: 1000)")
+    ap.add_argument("--cpu-frames", type=int, default=6, help="c5: frames of the stream the CPU restatement is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     args = ap.parse_args()
@@ -347,8 +461,8 @@ def main():
     import lidarslam_ros2_b200 as m
 
     args.warmup = max(args.warmup, 3)
-    if args.workload == "c4":
-        run_c4(args, rank, local_rank, world, m)
+    if args.workload in ("c3", "c4", "c5"):
+        {"c3": run_c3, "c4": run_c4, "c5": run_c5}[args.workload](args, rank, local_rank, world, m)
         if world > 1:
             dist.destroy_process_group()
         return

@@ -144,6 +144,52 @@ int b200reg_gicp_num_correspondences(b200reg_t h, int* out);
 /* exact 1-NN of n query points against the target cloud (building block of getFitnessScore / GICP) */
 int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, int* idx, float* d2);
 
+/* ---- scan-matcher frontend session: device-resident map maintenance --------
+ * The callers either side of align() in scanmatcher/src/scanmatcher_component.cpp, rebuilt so that a frame costs ONE
+ * host-to-device copy: the submaps (voxel-filtered, sensor frame) and the targeted cloud stay in HBM.
+ * Poses are position (x, y, z) + quaternion (x, y, z, w) in double, like geometry_msgs/Pose.                       */
+typedef struct b200sm_session* b200sm_t;
+int b200sm_create(int device, b200sm_t* out);
+void b200sm_destroy(b200sm_t s);
+const char* b200sm_last_error(b200sm_t s);
+int b200reg_get_kind(b200reg_t h, int* kind);
+/* node parameters: vg_size_for_input, vg_size_for_map, num_targeted_cloud, trans_for_mapupdate, use_min_max_filter,
+ * scan_min_range, scan_max_range (sm.cpp:34-50; defaults 0.2, 0.1, 10, 1.5, false, 0.1, 100)                        */
+int b200sm_set_params(b200sm_t s, float vg_size_for_input, float vg_size_for_map, int num_targeted_cloud,
+                      double trans_for_mapupdate, int use_min_max_filter, double scan_min_range, double scan_max_range);
+int b200sm_set_initial_pose(b200sm_t s, const double* position3, const double* quat_xyzw); /* sm.cpp:57-69, 127-141 */
+/* cloud_callback range filter (sm.cpp:211-219) + receiveCloud's VoxelGrid(vg_size_for_input) and
+ * registration->setInputSource (sm.cpp:323-328): uploads the frame once and keeps it on the device for a later
+ * b200sm_update_map. *n_filtered = points of the filtered source.                                                    */
+int b200sm_set_scan(b200sm_t s, b200reg_t reg, const float* points, size_t n, size_t stride_bytes,
+                    long intensity_offset_bytes, size_t* n_filtered);
+/* updateMap (sm.cpp:438-491; the first call is initializeMap, sm.cpp:257-297) on the frame given to the last
+ * b200sm_set_scan / b200sm_receive_cloud: VoxelGrid(vg_size_for_map) -> new submap (kept untransformed with its
+ * pose); targeted cloud = transformPointCloud(filtered, final_T [float]) followed by the previous
+ * num_targeted_cloud-1 submaps, newest first, each through its pose matrix [double]. adopt_now != 0 also performs
+ * receiveCloud's registration->setInputTarget(targeted) (sm.cpp:300-322; GICP: VoxelGrid(vg_size_for_input) first). */
+int b200sm_update_map(b200sm_t s, b200reg_t reg, const float* final_T_colmajor16, const double* position3,
+                      const double* quat_xyzw, int adopt_now);
+/* One frame of the frontend: cloud_callback + initializeMap (first frame) + receiveCloud + publishMapAndPose
+ * (sm.cpp:201-235, 299-434): adopt a pending target, filter, setInputSource, align(guess = current pose), pose
+ * bookkeeping, and updateMap when the sensor moved >= trans_for_mapupdate (performed immediately; the new target is
+ * adopted at the start of the next frame — the reference's mapping thread finishing before the next scan).
+ * pose7_out = position + quaternion after the frame; *map_updated = 1 if updateMap ran.                             */
+int b200sm_receive_cloud(b200sm_t s, b200reg_t reg, const float* points, size_t n, size_t stride_bytes,
+                         long intensity_offset_bytes, double* pose7_out, float* final_T_colmajor16_out, int* map_updated);
+/* read-back (parity tests; the node's map / map_array publishers). Clouds are x, y, z, intensity floats. */
+int b200sm_num_submaps(b200sm_t s, size_t* out);
+int b200sm_get_targeted(b200sm_t s, float* out_xyzi, size_t capacity, size_t* n);
+int b200sm_get_submap(b200sm_t s, size_t index, float* out_xyzi, size_t capacity, size_t* n, double* pose_colmajor16,
+                      double* distance);
+int b200sm_get_filtered_scan(b200sm_t s, float* out_xyzi, size_t capacity, size_t* n);
+typedef struct b200sm_stats {
+  size_t n_scan, n_filtered, n_targeted, n_submaps;
+  int kernel_launches;
+  double trans, latest_distance;
+} b200sm_stats;
+int b200sm_get_stats(b200sm_t s, b200sm_stats* out);
+
 #ifdef __cplusplus
 }
 #endif

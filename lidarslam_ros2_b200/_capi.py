@@ -32,8 +32,16 @@ SYMBOLS = [
     "b200reg_get_fitness_score", "b200reg_get_aligned", "b200reg_align_batch",
     "b200reg_voxelgrid", "b200reg_get_stats", "b200reg_ndt_derivatives", "b200reg_ndt_hessian_radius",
     "b200reg_ndt_num_voxels", "b200reg_ndt_get_voxels", "b200reg_nn1",
-    "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences",
+    "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
+    "b200sm_create", "b200sm_destroy", "b200sm_last_error", "b200sm_set_params", "b200sm_set_initial_pose",
+    "b200sm_set_scan", "b200sm_update_map", "b200sm_receive_cloud", "b200sm_num_submaps", "b200sm_get_targeted",
+    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats",
 ]
+
+
+class SmStats(C.Structure):
+    _fields_ = [("n_scan", C.c_size_t), ("n_filtered", C.c_size_t), ("n_targeted", C.c_size_t), ("n_submaps", C.c_size_t),
+                ("kernel_launches", C.c_int), ("trans", C.c_double), ("latest_distance", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -106,9 +114,25 @@ def lib() -> C.CDLL:
     L.b200reg_nn1.argtypes = [vp, vp, sz, sz, vp, vp]
     L.b200reg_gicp_get_covariances.argtypes = [vp, i, vp, C.POINTER(sz)]
     L.b200reg_gicp_num_correspondences.argtypes = [vp, C.POINTER(i)]
+    L.b200reg_get_kind.argtypes = [vp, C.POINTER(i)]
+    L.b200sm_create.argtypes = [i, C.POINTER(vp)]
+    L.b200sm_destroy.argtypes = [vp]
+    L.b200sm_destroy.restype = None
+    L.b200sm_last_error.argtypes = [vp]
+    L.b200sm_last_error.restype = C.c_char_p
+    L.b200sm_set_params.argtypes = [vp, f, f, i, d, i, d, d]
+    L.b200sm_set_initial_pose.argtypes = [vp, vp, vp]
+    L.b200sm_set_scan.argtypes = [vp, vp, vp, sz, sz, C.c_long, C.POINTER(sz)]
+    L.b200sm_update_map.argtypes = [vp, vp, vp, vp, vp, i]
+    L.b200sm_receive_cloud.argtypes = [vp, vp, vp, sz, sz, C.c_long, vp, vp, C.POINTER(i)]
+    L.b200sm_num_submaps.argtypes = [vp, C.POINTER(sz)]
+    L.b200sm_get_targeted.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.b200sm_get_submap.argtypes = [vp, sz, vp, sz, C.POINTER(sz), vp, C.POINTER(d)]
+    L.b200sm_get_filtered_scan.argtypes = [vp, vp, sz, C.POINTER(sz)]
+    L.b200sm_get_stats.argtypes = [vp, C.POINTER(SmStats)]
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name != "b200reg_last_error":
+        if name not in ("b200reg_last_error", "b200sm_last_error", "b200sm_destroy"):
             fn.restype = i
     _lib = L
     return L

@@ -429,6 +429,12 @@ int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, flo
   return worst;
 }
 
+int b200reg_get_kind(b200reg_t h, int* kind) {
+  if (!h || !kind) return B200REG_ERR_ARG;
+  *kind = h->kind;
+  return B200REG_OK;
+}
+
 int b200reg_get_final_transformation(b200reg_t h, float* out16) {
   if (!h || !out16) return B200REG_ERR_ARG;
   row_to_col(h->final_T, out16);

@@ -1,0 +1,119 @@
+"""Host-side mirror of the reference's frontend node for the path around align():
+`ScanMatcherComponent` (scanmatcher/src/scanmatcher_component.cpp) without ROS — cloud callback, initializeMap,
+receiveCloud, publishMapAndPose, updateMap — on top of the `b200sm_*` session of the C-ABI (include/b200reg.h).
+The submaps and the targeted cloud live on the GPU; a frame costs one host-to-device copy.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _capi
+from .registration import B200RegError, GeneralizedIterativeClosestPoint, NormalDistributionsTransform, _as_cloud, _ptr
+
+
+class ScanMatcher:
+    """Parameters carry the reference's names and defaults (scanmatcher_component.cpp:26-50)."""
+
+    def __init__(self, registration_method: str = "NDT", ndt_resolution: float = 5.0, ndt_num_threads: int = 0,
+                 gicp_corr_dist_threshold: float = 5.0, trans_for_mapupdate: float = 1.5, vg_size_for_input: float = 0.2,
+                 vg_size_for_map: float = 0.1, use_min_max_filter: bool = False, scan_min_range: float = 0.1,
+                 scan_max_range: float = 100.0, num_targeted_cloud: int = 10, device: int = 0):
+        self._lib = _capi.lib()
+        if registration_method == "NDT":  # scanmatcher_component.cpp:97-107
+            reg = NormalDistributionsTransform(device=device)
+            reg.setResolution(ndt_resolution)
+            reg.setTransformationEpsilon(0.01)
+            reg.setNeighborhoodSearchMethod(2)  # pclomp::DIRECT7
+            if ndt_num_threads > 0:
+                reg.setNumThreads(ndt_num_threads)
+        elif registration_method == "GICP":  # :108-115
+            reg = GeneralizedIterativeClosestPoint(device=device)
+            reg.setMaxCorrespondenceDistance(gicp_corr_dist_threshold)
+            reg.setTransformationEpsilon(1e-8)
+        else:
+            raise ValueError("registration_method must be NDT or GICP")
+        self.registration = reg
+        h = C.c_void_p()
+        rc = self._lib.b200sm_create(int(device), C.byref(h))
+        if rc != 0:
+            raise B200RegError(rc, "b200sm_create failed (no CUDA device? there is no CPU fallback)")
+        self._h = h
+        self._check(self._lib.b200sm_set_params(self._h, float(vg_size_for_input), float(vg_size_for_map), int(num_targeted_cloud),
+                                                float(trans_for_mapupdate), int(bool(use_min_max_filter)),
+                                                float(scan_min_range), float(scan_max_range)))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.b200sm_destroy(h)
+            self._h = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise B200RegError(rc, self._lib.b200sm_last_error(self._h).decode())
+
+    def setInitialPose(self, position, quat_xyzw):
+        p = np.ascontiguousarray(position, dtype=np.float64)
+        q = np.ascontiguousarray(quat_xyzw, dtype=np.float64)
+        self._check(self._lib.b200sm_set_initial_pose(self._h, _ptr(p), _ptr(q)))
+
+    def receiveCloud(self, points):
+        """One frame (x, y, z[, intensity] rows). Returns (pose7 = position + quaternion xyzw, final 4x4, map_updated)."""
+        p = _as_cloud(points)
+        n, w = p.shape
+        pose = np.zeros(7, dtype=np.float64)
+        fin = np.zeros(16, dtype=np.float32)
+        upd = C.c_int(0)
+        self._check(self._lib.b200sm_receive_cloud(self._h, self.registration._h, _ptr(p), n, 4 * w, 12 if w >= 4 else -1,
+                                                   _ptr(pose), _ptr(fin), C.byref(upd)))
+        return pose, fin.reshape(4, 4).T.copy(), bool(upd.value)
+
+    # ---- the pieces, for callers that drive the steps themselves ----
+    def setScan(self, points) -> int:
+        p = _as_cloud(points)
+        n, w = p.shape
+        m = C.c_size_t(0)
+        self._check(self._lib.b200sm_set_scan(self._h, self.registration._h, _ptr(p), n, 4 * w, 12 if w >= 4 else -1, C.byref(m)))
+        return int(m.value)
+
+    def updateMap(self, final_transformation, position, quat_xyzw, adopt_now: bool = True):
+        T = np.ascontiguousarray(np.asarray(final_transformation, dtype=np.float32).T).reshape(16)
+        p = np.ascontiguousarray(position, dtype=np.float64)
+        q = np.ascontiguousarray(quat_xyzw, dtype=np.float64)
+        self._check(self._lib.b200sm_update_map(self._h, self.registration._h, _ptr(T), _ptr(p), _ptr(q), int(adopt_now)))
+
+    # ---- read-back ----
+    def stats(self) -> dict:
+        st = _capi.SmStats()
+        self._check(self._lib.b200sm_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _capi.SmStats._fields_}
+
+    def numSubmaps(self) -> int:
+        v = C.c_size_t(0)
+        self._check(self._lib.b200sm_num_submaps(self._h, C.byref(v)))
+        return int(v.value)
+
+    def targetedCloud(self) -> np.ndarray:
+        n = C.c_size_t(0)
+        self._check(self._lib.b200sm_get_targeted(self._h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        self._check(self._lib.b200sm_get_targeted(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def filteredScan(self) -> np.ndarray:
+        n = C.c_size_t(0)
+        self._check(self._lib.b200sm_get_filtered_scan(self._h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        self._check(self._lib.b200sm_get_filtered_scan(self._h, _ptr(out), n.value, C.byref(n)))
+        return out
+
+    def submap(self, index: int):
+        n = C.c_size_t(0)
+        pose = np.zeros(16, dtype=np.float64)
+        dist = C.c_double(0)
+        self._check(self._lib.b200sm_get_submap(self._h, index, None, 0, C.byref(n), _ptr(pose), C.byref(dist)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        self._check(self._lib.b200sm_get_submap(self._h, index, _ptr(out), n.value, C.byref(n), _ptr(pose), C.byref(dist)))
+        return out, pose.reshape(4, 4).T.copy(), float(dist.value)

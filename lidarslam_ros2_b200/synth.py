@@ -238,6 +238,40 @@ def sensor_pose(T_rel: np.ndarray, x_along: float = 0.0) -> np.ndarray:
     return S0 @ T_rel
 
 
+def _drive_world_pose(k: int, step: float, x_start: float, yaw_amp_deg: float) -> np.ndarray:
+    d = math.pi / 180.0
+    yaw = yaw_amp_deg * d * math.sin(2.0 * math.pi * k / 40.0)
+    T = pose_matrix((step * k, 0.3 * math.sin(2.0 * math.pi * k / 60.0), 0.0), (0.0, 0.0, yaw))
+    return sensor_pose(T, x_start)
+
+
+def drive_frame(k: int, rings: int = 16, azimuths: int = 625, step: float = 0.5, x_start: float = -60.0,
+                yaw_amp_deg: float = 1.0, stream: int = 7000):
+    """Frame k of the config-5 drive (reproducible on its own): (scan in the sensor frame, T_rel_k) where T_rel_k is the
+    k-th sensor pose relative to the first one — the ground truth of the frontend's k-th pose, which starts at identity."""
+    scene = make_scene()
+    S0 = _drive_world_pose(0, step, x_start, yaw_amp_deg)
+    Sk = _drive_world_pose(k, step, x_start, yaw_amp_deg)
+    scan = make_scan(scene, rings, azimuths, Sk, stream=stream + k)
+    return scan, np.linalg.inv(S0) @ Sk
+
+
+def drive_stream(n_frames: int, rings: int = 16, azimuths: int = 625, step: float = 0.5, x_start: float = -60.0,
+                 yaw_amp_deg: float = 1.0, stream: int = 7000, workers: int = 1):
+    """Config 5: a sensor driving down the canyon, `step` metres per frame with a slow yaw weave and a small lateral
+    drift. Yields (scan, T_rel_k) per frame; workers > 1 ray-casts the frames in a process pool."""
+    if workers <= 1:
+        for k in range(n_frames):
+            yield drive_frame(k, rings, azimuths, step, x_start, yaw_amp_deg, stream)
+        return
+    from concurrent.futures import ProcessPoolExecutor
+
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        futs = [ex.submit(drive_frame, k, rings, azimuths, step, x_start, yaw_amp_deg, stream) for k in range(n_frames)]
+        for f in futs:
+            yield f.result()
+
+
 _SCAN_SHAPES = {"10k": (16, 625), "60k": (32, 1875), "100k": (64, 1563)}
 
 

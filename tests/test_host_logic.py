@@ -18,7 +18,7 @@ def test_cabi_library_exports_every_declared_symbol():
     from lidarslam_ros2_b200 import _capi
 
     header = open(os.path.join(ROOT, "include", "b200reg.h")).read()
-    declared = set(re.findall(r"\b(b200reg_[a-z0-9_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(b200(?:reg|sm)_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     assert os.path.exists(_capi.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
     lib = C.CDLL(_capi.LIB_PATH)

@@ -1,0 +1,116 @@
+"""Frontend session: device-resident map maintenance + per-frame scan preparation, against the
+CPU restatement oracle/scanmatcher.py of scanmatcher_component.cpp."""
+import numpy as np
+import pytest
+
+import oracle
+import oracle.scanmatcher as osm
+from lidarslam_ros2_b200 import synth
+
+
+def _sorted(c):
+    c = np.asarray(c)
+    return c[np.lexsort((c[:, 2], c[:, 1], c[:, 0]))]
+
+
+# ---------------------------------------------------------------- CPU: the oracle itself
+def test_pose_math_roundtrip():
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        q = rng.normal(size=4)
+        q /= np.linalg.norm(q)
+        M = osm.pose_matrix([1.0, -2.0, 0.5], q)
+        assert np.allclose(M[:3, :3] @ M[:3, :3].T, np.eye(3), atol=1e-12)
+        q2 = osm.quat_from_matrix(M[:3, :3])
+        assert min(np.abs(q2 - q).max(), np.abs(q2 + q).max()) < 1e-12
+    # the largest-diagonal branches (trace <= 0)
+    for q in ([1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0], [0.7, 0.7, 0.1, 0.05]):
+        q = np.array(q, dtype=float) / np.linalg.norm(q)
+        q2 = osm.quat_from_matrix(osm.pose_matrix([0, 0, 0], q)[:3, :3])
+        assert min(np.abs(q2 - q).max(), np.abs(q2 + q).max()) < 1e-12
+
+
+def test_transforms_match_matrix_product():
+    rng = np.random.default_rng(5)
+    c = rng.normal(size=(200, 4)).astype(np.float32) * 20
+    M = osm.pose_matrix([3.0, -1.0, 0.2], [0.01, -0.02, 0.3, 0.95] / np.linalg.norm([0.01, -0.02, 0.3, 0.95]))
+    ref = (c[:, :3].astype(np.float64) @ M[:3, :3].T + M[:3, 3])
+    assert np.abs(osm.transform_f64(c, M)[:, :3] - ref).max() < 1e-5
+    assert np.abs(osm.transform_f32(c, M.astype(np.float32))[:, :3] - ref).max() < 1e-4
+    assert np.array_equal(osm.transform_f64(c, M)[:, 3], c[:, 3])  # intensity is copied
+
+
+def test_oracle_frontend_tracks_the_drive():
+    sm = osm.ScanMatcher(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.3, num_targeted_cloud=4, num_threads=8)
+    n_upd = 0
+    for k, (scan, T_gt) in enumerate(synth.drive_stream(8, rings=16, azimuths=300, step=0.6)):
+        pose, final, upd = sm.receive_cloud(scan)
+        n_upd += int(upd)
+        dt, dr = synth.pose_error(final, T_gt)
+        assert dt < 0.5 and dr < 0.02, (k, dt, dr)  # a 16-ring scan against a map of a few sparse scans: bounded drift
+    assert n_upd >= 2 and len(sm.submaps) == 1 + n_upd
+    # targeted = newest scan + at most num_targeted_cloud-1 previous submaps
+    assert len(sm.targeted) <= sum(len(c) for c, _, _ in sm.submaps[-4:])
+
+
+# ---------------------------------------------------------------- GPU: parity through the C-ABI
+@pytest.mark.gpu
+@pytest.mark.parametrize("use_filter", [False, True])
+def test_frontend_stream_parity(use_filter):
+    from lidarslam_ros2_b200.scanmatcher import ScanMatcher
+
+    kw = dict(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.3, num_targeted_cloud=3,
+              use_min_max_filter=use_filter, scan_min_range=2.0, scan_max_range=60.0)
+    g = ScanMatcher(**kw)
+    o = osm.ScanMatcher(num_threads=oracle.max_threads(), **kw)
+    n_upd = 0
+    for k, (scan, T_gt) in enumerate(synth.drive_stream(10, rings=16, azimuths=400, step=0.6)):
+        pg, Tg, ug = g.receiveCloud(scan)
+        po, To, uo = o.receive_cloud(scan)
+        assert ug == uo, k
+        n_upd += int(ug)
+        dt, dr = synth.pose_error(Tg, To)
+        assert dt < 1e-3 and dr < 1e-3, (k, dt, dr)  # north_star tolerance
+        assert np.abs(pg - po).max() < 1e-3
+        fs = g.filteredScan()
+        assert len(fs) == len(o.filtered)
+        assert np.abs(_sorted(fs) - _sorted(o.filtered)).max() < 1e-4
+    assert n_upd >= 2
+    assert g.numSubmaps() == len(o.submaps)
+    # the device-resident targeted cloud: same points (VoxelGrid centroids agree to float rounding; order is defined)
+    tg, to = g.targetedCloud(), o.targeted
+    assert tg.shape == to.shape
+    # poses of GPU and CPU differ by <= 1e-3 m, and so do the transformed newest-scan points
+    assert np.abs(tg - to).max() < 5e-3
+    for i in range(g.numSubmaps()):
+        c, M, dist = g.submap(i)
+        co, Mo, disto = o.submaps[i]
+        assert c.shape == co.shape and np.abs(c - co).max() < 1e-4
+        assert np.abs(M - Mo).max() < 2e-3 and abs(dist - disto) < 2e-3
+
+
+@pytest.mark.gpu
+def test_update_map_bitwise_given_the_same_inputs():
+    """updateMap alone, fed identical poses: transform arithmetic is bit-exact, VoxelGrid centroids to rounding."""
+    from lidarslam_ros2_b200.scanmatcher import ScanMatcher
+
+    g = ScanMatcher(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.25, num_targeted_cloud=3)
+    o = osm.ScanMatcher(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.25, num_targeted_cloud=3, num_threads=4)
+    rng = np.random.default_rng(11)
+    for k, (scan, T_gt) in enumerate(synth.drive_stream(5, rings=16, azimuths=300, step=1.0)):
+        q = osm.quat_from_matrix(T_gt[:3, :3])
+        pos = T_gt[:3, 3] + 1e-3 * rng.normal(size=3)
+        final = osm.pose_matrix(pos, q).astype(np.float32)
+        cloud = np.concatenate([scan, rng.uniform(0, 255, size=(len(scan), 1)).astype(np.float32)], axis=1)
+        g.setScan(cloud)
+        g.updateMap(final, pos, q, adopt_now=True)
+        o.update_map(cloud, final, pos, q)
+        tg, to = g.targetedCloud(), o.targeted
+        assert tg.shape == to.shape
+        m = len(o.submaps[-1][0])
+        # previous submaps were filtered identically on both sides only up to float rounding of the centroids, so
+        # compare the transformed points with a rounding-level tolerance, and the structure (counts, order) exactly
+        assert np.abs(tg - to).max() < 2e-4, k
+        assert np.array_equal(np.isfinite(tg), np.isfinite(to))
+        c, M, _ = g.submap(k)
+        assert len(c) == m and np.array_equal(M, o.submaps[k][1])
