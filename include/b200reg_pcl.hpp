@@ -15,6 +15,7 @@
 #include <array>
 #include <cfloat>
 #include <cstddef>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -94,6 +95,7 @@ class Registration {
     b200reg_has_converged(h_.get(), &c);
     return c != 0;
   }
+  b200reg_t handle() const { return h_.get(); }  // for ScanMatcherSession
   double getFitnessScore(double max_range = DBL_MAX) {
     double v = DBL_MAX;
     check(b200reg_get_fitness_score(h_.get(), max_range, &v));
@@ -161,6 +163,7 @@ class RegistrationBase : public pcl::Registration<PointSource, PointTarget> {
     if (cloud && !cloud->empty()) b200reg_set_input_source(h_.get(), &cloud->points[0].x, cloud->size(), sizeof(PointSource));
   }
   // pcl::Registration::getFitnessScore walks a host kd-tree over the target; answer from the GPU instead
+  b200reg_t handle() const { return h_.get(); }  // for ScanMatcherSession
   double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
     double v = std::numeric_limits<double>::max();
     b200reg_get_fitness_score(h_.get(), max_range, &v);
@@ -228,5 +231,51 @@ class GeneralizedIterativeClosestPoint : public RegistrationBase<PointSource, Po
 };
 
 #endif  // B200REG_WITH_PCL
+
+// ---- frontend session: device-resident map maintenance (b200sm_*, include/b200reg.h) -------------------------------
+// What ScanMatcherComponent keeps per node instead of targeted_cloud_ / map_array_msg_.submaps[i].cloud on the host:
+// one call per frame (receiveCloud) or the individual steps (setScan / updateMap). `Reg` is any of the registration
+// classes above (it only needs the C handle).
+class ScanMatcherSession {
+ public:
+  explicit ScanMatcherSession(int device = 0) {
+    b200sm_t s = nullptr;
+    if (b200sm_create(device, &s) != B200REG_OK) throw std::runtime_error("b200sm_create: no CUDA device (there is no CPU fallback)");
+    s_.reset(s, [](b200sm_t p) { b200sm_destroy(p); });
+  }
+  void setParams(float vg_size_for_input, float vg_size_for_map, int num_targeted_cloud, double trans_for_mapupdate,
+                 bool use_min_max_filter = false, double scan_min_range = 0.1, double scan_max_range = 100.0) {
+    check(b200sm_set_params(s_.get(), vg_size_for_input, vg_size_for_map, num_targeted_cloud, trans_for_mapupdate,
+                            use_min_max_filter ? 1 : 0, scan_min_range, scan_max_range));
+  }
+  void setInitialPose(const double position[3], const double quat_xyzw[4]) { check(b200sm_set_initial_pose(s_.get(), position, quat_xyzw)); }
+  // points: n structs of `stride` bytes with x, y, z floats first and the intensity float at `intensity_offset` (or -1)
+  // pose7 = position + quaternion (x, y, z, w); final16 column-major like Eigen::Matrix4f::data()
+  bool receiveCloud(b200reg_t reg, const float* points, size_t n, size_t stride, long intensity_offset, double pose7[7], float final16[16]) {
+    int updated = 0;
+    check(b200sm_receive_cloud(s_.get(), reg, points, n, stride, intensity_offset, pose7, final16, &updated));
+    return updated != 0;
+  }
+  size_t setScan(b200reg_t reg, const float* points, size_t n, size_t stride, long intensity_offset) {
+    size_t m = 0;
+    check(b200sm_set_scan(s_.get(), reg, points, n, stride, intensity_offset, &m));
+    return m;
+  }
+  void updateMap(b200reg_t reg, const float final16[16], const double position[3], const double quat_xyzw[4], bool adopt_now = true) {
+    check(b200sm_update_map(s_.get(), reg, final16, position, quat_xyzw, adopt_now ? 1 : 0));
+  }
+  size_t numSubmaps() const {
+    size_t n = 0;
+    b200sm_num_submaps(s_.get(), &n);
+    return n;
+  }
+  b200sm_t handle() const { return s_.get(); }
+
+ private:
+  void check(int rc) const {
+    if (rc != B200REG_OK) throw std::runtime_error(std::string("b200sm: ") + b200sm_last_error(s_.get()));
+  }
+  std::shared_ptr<b200sm_session> s_;
+};
 
 }  // namespace b200reg
