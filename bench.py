@@ -581,7 +581,7 @@ def main():
                        "grid_ctas": ndt.stats()["grid_ctas"], "block_threads": ndt.stats()["block_threads"],
                        "index_in_smem": ndt.stats()["index_in_smem"]},
             "e2e": {"value": world * K / (e2e_ms_max * 1e-3), "unit": "registrations/s",
-                    "h2d_bytes_per_step": int(len(scans[0]) * 16), "d2h_bytes_per_step": 64 + 456,
+                    "h2d_bytes_per_step": int(pinned_scans[0].numel() * 4), "d2h_bytes_per_step": 64 + 456,
                     "ms_per_step": e2e_ms_max / K},
             "gpu_launches": int(launches),
             "per_rank": per_rank_rows,

@@ -32,6 +32,7 @@ struct b200reg_engine {
 
   DeviceBuffer<float4> d_target, d_source, d_aligned;
   PinnedBuffer<float4> staging;
+  CloudUploader uploader;
   size_t n_target = 0, n_source = 0;
   bool have_target = false, have_source = false;
   bool map_valid = false, nn_valid = false;
@@ -214,8 +215,8 @@ int set_cloud(b200reg_t h, bool target, const float* base, size_t n, size_t stri
     dst.ensure(n);
     B200_CUDA(cudaMemcpyAsync(dst.ptr, dev, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
   } else {
-    upload_cloud(base, n, stride, dst, h->staging, h->stream);
-    // the staging buffer is reused by the next upload: wait for the copy engine
+    upload_cloud(base, n, stride, dst, h->uploader, h->stream);
+    // the caller may reuse its buffer (and the staging copy is reused by the next upload): wait for the copy engine
     B200_CUDA(cudaStreamSynchronize(h->stream));
   }
   if (target) {
@@ -647,7 +648,7 @@ int b200reg_ndt_calculate_score(b200reg_t h, const float* base, size_t n, size_t
     ensure_map(h);
     *out = 0;
     if (n == 0 || h->map.n_voxels == 0) return (int)B200REG_OK;
-    upload_cloud(base, n, stride_bytes, h->query_buf, h->staging, h->stream);
+    upload_cloud(base, n, stride_bytes, h->query_buf, h->uploader, h->stream);
     ndt_score(h->map, h->query_buf.ptr, n, h->ndt, h->scratch_d.ptr, h->stream);
     h->other_launches += 1;
     double s = 0;
@@ -738,7 +739,7 @@ int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, i
     if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
     if (n == 0) return (int)B200REG_OK;
     ensure_nn(h);
-    upload_cloud(base, n, stride_bytes, h->query_buf, h->staging, h->stream);
+    upload_cloud(base, n, stride_bytes, h->query_buf, h->uploader, h->stream);
     h->nn_idx.ensure(n);
     h->nn_d2.ensure(n);
     nn1_query(h->nn, h->query_buf.ptr, n, nullptr, h->nn_idx.ptr, h->nn_d2.ptr, h->stream);

@@ -1,0 +1,53 @@
+// Point-cloud wire format -> device layout. The reference hands clouds around as arrays of
+// fixed-size records — pcl::PointCloud<PointXYZI> (32-byte points) or the data block of a sensor_msgs/PointCloud2
+// (point_step bytes per point, x/y/z/intensity float32 fields at their offsets; pcl::fromROSMsg,
+// scanmatcher_component.cpp:202, 457) — and re-packs them on the CPU. Here the raw records go to the GPU in ONE bulk
+// copy (straight from the caller's buffer when it is pinned, else through a pinned staging copy made with memcpy) and a
+// kernel unpacks them into the float4 (x, y, z, w) layout every other kernel reads.
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace b200 {
+
+namespace {
+__global__ void unpack_points_kernel(const unsigned char* __restrict__ raw, size_t n, size_t stride, long w_off, float w_default,
+                                     float4* __restrict__ dst) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const unsigned char* p = raw + i * stride;  // records are 4-byte aligned (float fields)
+  const float* f = reinterpret_cast<const float*>(p);
+  float4 v;
+  v.x = f[0];
+  v.y = f[1];
+  v.z = f[2];
+  v.w = w_off >= 0 ? *reinterpret_cast<const float*>(p + w_off) : w_default;
+  dst[i] = v;
+}
+}  // namespace
+
+void CloudUploader::upload(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst, cudaStream_t s) {
+  if (n == 0) return;
+  const size_t bytes = n * stride;
+  raw.ensure(bytes);
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();  // older drivers report unregistered memory as an error
+  const void* src = host;
+  if (!pinned) {
+    staging.ensure(bytes);
+    std::memcpy(staging.ptr, host, bytes);
+    src = staging.ptr;
+  }
+  B200_CUDA(cudaMemcpyAsync(raw.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+  unpack_points_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(raw.ptr, n, stride, w_off, w_default, dst);
+  B200_CUDA(cudaGetLastError());
+  launches += 1;
+}
+
+void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst, CloudUploader& up, cudaStream_t s) {
+  dst.ensure(n);
+  up.upload(base, n, stride_bytes, -1, 1.0f, dst.ptr, s);
+}
+
+}  // namespace b200

@@ -75,8 +75,15 @@ Bounds cloud_bounds(const float4* pts, size_t n, unsigned* d_scratch8, cudaStrea
 bool make_grid_geom(const Bounds& b, float leaf, GridGeom& g);
 
 // upload an arbitrary-stride host cloud into a float4 device buffer (w = 1)
-void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst,
-                  PinnedBuffer<float4>& staging, cudaStream_t s);
+// strided host records -> float4 on the device: one bulk H2D copy of the raw bytes + an unpack kernel (cloud_codec.cu)
+struct CloudUploader {
+  DeviceBuffer<unsigned char> raw;
+  PinnedBuffer<unsigned char> staging;  // only used when the caller's buffer is pageable
+  int launches = 0;
+  // w_off >= 0: byte offset of the float that goes to .w (intensity); otherwise .w = w_default
+  void upload(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst, cudaStream_t s);
+};
+void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst, CloudUploader& up, cudaStream_t s);
 
 // ---- NDT voxel map (K3) -------------------------------------------------------------------------------
 struct VoxelMap {

@@ -7,12 +7,13 @@
 //   into the evaluation.
 //
 // B200 design (not a translation of the OpenMP loop):
-//   * ONE cooperative kernel launch per align(). Evaluator CTAs keep their source points in REGISTERS for the
-//     whole solve and loop   evaluate -> CTA partial -> arrive -> wait for the next pose;   one dedicated
-//     CONTROLLER CTA keeps the Newton / More-Thuente state in shared memory and loops
-//     wait for all arrivals -> fixed-order f64 reduction of the partials -> 6x6 solve -> next pose + angle
-//     tables -> release.  The ~5-40 sequential evaluations of a registration cost no launches, no host round
-//     trips and no global-memory state traffic.
+//   * ONE cooperative kernel launch per align(), one 768-thread CTA per SM. Evaluator CTAs keep their source points in
+//     SHARED MEMORY for the whole solve and loop   evaluate -> CTA partial row -> wait for the next pose;   the last
+//     CTA is the CONTROLLER: it keeps the Newton / More-Thuente state in shared memory and loops
+//     fixed-order f64 reduction of the partial rows (its loads are the arrival poll) -> 6x6 solve -> next pose +
+//     angle tables -> publish.  The ~5-40 sequential evaluations of a registration cost no launches, no host round
+//     trips and no global-memory state traffic; both signalling directions carry their validity in the data words
+//     (ndt_solver.cuh), so a hop is one store plus one polling load — no counter, fence or second round trip.
 //   * per (point, voxel) pair only e, s = C x' and the sums S += e s, M += e C, Q += e s s^T are formed; the
 //     gradient / Hessian contribution J^T(.)J is applied once per POINT (J, H_E depend on the point only):
 //     ~35 FMA per pair + ~140 per point instead of ~600 MAC per pair in the reference.

@@ -40,7 +40,7 @@ struct NdtState {
 
 constexpr int NDT_TIMING_ROUNDS = 48;
 constexpr int NDT_TIMING_SLOTS = 12;
-// slots (globaltimer ns): 0 CTA0 round start, 1 CTA0 after evaluate, 2 CTA0 partial written, 3 CTA0 arrived,
+// slots (globaltimer ns): 0 CTA0 round start, 1 CTA0 after evaluate, 2/3 CTA0 partial row stored,
 //                         4 last CTA detected, 5 partials reduced, 6 controller done, 7 CTA0 released
 // Signalling between the evaluator CTAs and the controller CTA carries its own validity ("flag in data", as in NCCL's
 // LL protocol), so neither direction needs a counter, a fence or a second dependent round trip:

@@ -106,7 +106,7 @@ struct b200sm_session {
   DeviceBuffer<float4> upload, scan;  // uploaded frame; after the optional range filter (`scan` aliases upload when off)
   const float4* d_scan = nullptr;
   size_t n_scan = 0;
-  PinnedBuffer<float4> staging;
+  CloudUploader uploader;
   DeviceBuffer<unsigned> counter;
   VoxelGridFilter vg_input, vg_map, vg_target;
   size_t n_filtered = 0;
@@ -189,14 +189,8 @@ void matrix_to_quat_d(const double* R /* row-major 9 */, double* q /* x y z w */
 
 void upload_frame(b200sm_t s, const float* points, size_t n, size_t stride, long intensity_off) {
   s->upload.ensure(n);
-  s->staging.ensure(n);
-  const char* b = reinterpret_cast<const char*>(points);
-  for (size_t i = 0; i < n; i++) {
-    const float* f = reinterpret_cast<const float*>(b + i * stride);
-    const float inten = intensity_off >= 0 ? *reinterpret_cast<const float*>(b + i * stride + intensity_off) : 0.0f;
-    s->staging.ptr[i] = make_float4(f[0], f[1], f[2], inten);
-  }
-  B200_CUDA(cudaMemcpyAsync(s->upload.ptr, s->staging.ptr, n * sizeof(float4), cudaMemcpyHostToDevice, s->stream));
+  s->uploader.upload(points, n, stride, intensity_off, 0.0f, s->upload.ptr, s->stream);  // one H2D copy per frame
+  s->launches += 1;
   s->d_scan = s->upload.ptr;
   s->n_scan = n;
   if (s->use_min_max_filter) {

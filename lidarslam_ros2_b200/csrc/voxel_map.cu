@@ -180,19 +180,6 @@ bool make_grid_geom(const Bounds& b, float leaf, GridGeom& g) {
   return true;
 }
 
-void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst,
-                  PinnedBuffer<float4>& staging, cudaStream_t s) {
-  dst.ensure(n);
-  staging.ensure(n);
-  const char* b = reinterpret_cast<const char*>(base);
-  float4* st = staging.ptr;
-  for (size_t i = 0; i < n; i++) {
-    const float* f = reinterpret_cast<const float*>(b + i * stride_bytes);
-    st[i] = make_float4(f[0], f[1], f[2], 1.0f);
-  }
-  B200_CUDA(cudaMemcpyAsync(dst.ptr, st, n * sizeof(float4), cudaMemcpyHostToDevice, s));
-}
-
 // =====================================================================================================
 // voxel map build
 // =====================================================================================================
