@@ -368,9 +368,6 @@ struct CtlShared {
   double fac[8];      // sx, cx, sy, cy, sz, cz, 1, 0 of the pose being built (f64, with the 1e-4 snap)
   float facf[8];      // f32 sin/cos of the same angles (for the transform)
   unsigned code[72];  // shared-memory copy of kAngleTableCode
-  double M[6][8];     // fast-path scratch: H (36 doubles) followed by A^-1 (9)
-  double blk[3][12];  // fast-path scratch: Y | v1, S | w, S^-1
-  double vec[4][8];   // fast-path scratch: p, g, dp, dir
   int ready;          // per-round: bit w set once reducing warp w has summed all its partial rows
   unsigned long long t_warp[32];  // timing mode: when each reducing warp finished
 };
@@ -415,8 +412,8 @@ __device__ __noinline__ void build_control(CtlShared& cs, int lane) {
   }
   __syncwarp();
   NdtControl& c = cs.next;
-#pragma unroll 1
-  for (int it = 0; it < 3; it++) {
+#pragma unroll
+  for (int it = 0; it < 3; it++) {  // unrolled: the three entries of a lane are independent chains
     const int e = lane + 32 * it;
     if (e < 69) {
       const double v = angle_table_entry(cs.code[e], cs.fac);  // f64 value (H row d1 carries -sy, :359)
@@ -429,23 +426,23 @@ __device__ __noinline__ void build_control(CtlShared& cs, int lane) {
         else cs.st.hd[e - 24] = v;
       }
     }
-    __syncwarp();
   }
-  if (lane < 3) {
+  if (lane >= 5 && lane < 8) {
     // T = Translation * Rx * Ry * Rz in float (ndt_omp_impl.hpp:811-814), same product order as pose_to_matrix();
-    // lane r forms row r
+    // lane 5 + r forms row r (lanes 0..4 carry three table entries, the others two)
+    const int row = lane - 5;
     const float fsx = cs.facf[0], fcx = cs.facf[1], fsy = cs.facf[2], fcy = cs.facf[3], fsz = cs.facf[4], fcz = cs.facf[5];
-    const float a0 = lane == 0 ? fcy : (lane == 1 ? fsx * fsy : -fcx * fsy);
-    const float a1 = lane == 0 ? 0.0f : (lane == 1 ? fcx : fsx);
-    const float a2 = lane == 0 ? fsy : (lane == 1 ? -fsx * fcy : fcx * fcy);
+    const float a0 = row == 0 ? fcy : (row == 1 ? fsx * fsy : -fcx * fsy);
+    const float a1 = row == 0 ? 0.0f : (row == 1 ? fcx : fsx);
+    const float a2 = row == 0 ? fsy : (row == 1 ? -fsx * fcy : fcx * fcy);
     const float t0 = __fadd_rn(__fmul_rn(a0, fcz), __fmul_rn(a1, fsz));
     const float t1 = __fadd_rn(__fmul_rn(a0, -fsz), __fmul_rn(a1, fcz));
-    const float t3 = (float)x_t[lane];
+    const float t3 = (float)x_t[row];
     float* F = cs.st.final_T;  // final_transformation_
-    c.T[lane * 4 + 0] = t0; c.T[lane * 4 + 1] = t1; c.T[lane * 4 + 2] = a2; c.T[lane * 4 + 3] = t3;
-    F[lane * 4 + 0] = t0; F[lane * 4 + 1] = t1; F[lane * 4 + 2] = a2; F[lane * 4 + 3] = t3;
-    F[12 + lane] = 0.0f;
-    if (lane == 0) {
+    c.T[row * 4 + 0] = t0; c.T[row * 4 + 1] = t1; c.T[row * 4 + 2] = a2; c.T[row * 4 + 3] = t3;
+    F[row * 4 + 0] = t0; F[row * 4 + 1] = t1; F[row * 4 + 2] = a2; F[row * 4 + 3] = t3;
+    F[12 + row] = 0.0f;
+    if (row == 0) {
       F[15] = 1.0f;
       c.mode = EVAL_DERIV;
       c.compute_hessian = cs.build_hessian;
@@ -466,93 +463,59 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
   const int phase = st.phase;
   if (phase != PH_INITIAL && phase != PH_LS_FIRST) return false;
   const double* tot = cs.tot;
-  double* pv = cs.vec[0];   // updated pose
-  double* gv = cs.vec[1];   // gradient
-  double* dpv = cs.vec[2];  // Newton step
-  double* dirv = cs.vec[3]; // unit direction
   int nr_it = st.nr_iterations;
   const double a_prev = st.a_t;
   if (phase == PH_LS_FIRST && (nr_it > L.max_iterations || (nr_it && (fabs(a_prev) < L.trans_eps)))) return false;
   if (phase == PH_LS_FIRST) nr_it += 1;
-  // scratch fill: the full symmetric H (two elements per lane), pose and gradient (lanes 0..5)
-  double* Hs = &cs.M[0][0];  // 36 doubles: H row-major
-  double* Ai = Hs + 36;      // 9: inverse of the translation block A = H[0:3, 0:3]
-  double* Yv = cs.blk[0];    // 9: Y = A^-1 B, then [9..11]: v1 = A^-1 b1
-  double* Sv = cs.blk[1];    // 9: Schur complement S = D - B^T Y, then [9..11]: w = b2 - B^T v1
-  double* Si = cs.blk[2];    // 9: S^-1
-#pragma unroll 1
-  for (int e = lane; e < 36; e += 32) {
-    const int rr = e / 6, cc = e - rr * 6;
-    Hs[e] = tot[SLOT_H + tri_index(min(rr, cc), max(rr, cc))];
+  // Every lane solves the 6x6 Newton system H x = -g redundantly IN REGISTERS: symmetric elimination (LDL^T, no
+  // pivoting — H is definite wherever Newton is meaningful) on the upper triangle, straight-line code with plenty of
+  // independent FMAs and not a single shared-memory round trip or warp synchronisation between the dependent steps.
+  // A pivot that collapses relative to the largest diagonal entry (or a NaN) hands the round to the scalar controller,
+  // whose pivoted LU / SVD reproduce JacobiSVD::solve's behaviour for rank-deficient systems.
+  double A[6][6], rhs[6];  // (the gradient and the pose are re-read from shared memory later: registers are capped at 80)
+  double dmax = 0.0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+#pragma unroll
+    for (int c = r; c < 6; c++) A[r][c] = tot[SLOT_H + tri_index(r, c)];
+    rhs[r] = -tot[SLOT_G + r];
+    dmax = fmax(dmax, fabs(A[r][r]));
   }
-  if (lane < 6) {
-    pv[lane] = (phase == PH_LS_FIRST) ? st.p[lane] + st.dir[lane] * a_prev : st.p[lane];
-    gv[lane] = tot[SLOT_G + lane];
+  bool ok = dmax > 0.0 && dmax <= 1.7e308;
+  double inv[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    ok = ok && (fabs(A[k][k]) > 1e-10 * dmax);  // false for NaN
+    inv[k] = 1.0 / A[k][k];
+#pragma unroll
+    for (int r = k + 1; r < 6; r++) {
+      const double l = A[k][r] * inv[k];
+#pragma unroll
+      for (int c = r; c < 6; c++) A[r][c] = fma(-l, A[k][c], A[r][c]);
+      rhs[r] = fma(-l, rhs[k], rhs[r]);
+    }
   }
-  __syncwarp();
-  double amax = 0.0;
-  bool finite = true;
-#pragma unroll 1
-  for (int e = lane; e < 36; e += 32) {
-    const double v = fabs(Hs[e]);
-    finite = finite && (v <= 1.7e308);  // false for NaN / inf
-    amax = fmax(amax, v);
+  if (!ok) return false;
+  double x[6];
+#pragma unroll
+  for (int k = 5; k >= 0; k--) {
+    double t = rhs[k];
+#pragma unroll
+    for (int c = k + 1; c < 6; c++) t = fma(-A[k][c], x[c], t);
+    x[k] = t * inv[k];
   }
-#pragma unroll 1
-  for (int d = 16; d > 0; d >>= 1) amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, d));
-  if (!__all_sync(0xffffffffu, finite) || !(amax > 0.0)) return false;
-  // Newton system H x = -g solved by block elimination on the 3x3 blocks  H = [A B; B^T D]  with closed-form 3x3
-  // inverses, one matrix element per lane (the same x as JacobiSVD::solve whenever both A and the Schur complement are
-  // well conditioned; otherwise → scalar path: pivoted LU, then SVD).
-  const int i3 = lane / 3 % 3, j3 = lane % 3;                      // element (i3, j3) of a 3x3 for lanes 0..8
-  const int ja = (j3 + 1) % 3, jb = (j3 + 2) % 3, ia = (i3 + 1) % 3, ib = (i3 + 2) % 3;
-  {
-    // adj(A)(i,j) = A(j+1,i+1) A(j+2,i+2) - A(j+1,i+2) A(j+2,i+1)   (indices mod 3)
-    const double adj = Hs[ja * 6 + ia] * Hs[jb * 6 + ib] - Hs[ja * 6 + ib] * Hs[jb * 6 + ia];
-    const double det = Hs[0] * (Hs[7] * Hs[14] - Hs[8] * Hs[13]) - Hs[1] * (Hs[6] * Hs[14] - Hs[8] * Hs[12]) +
-                       Hs[2] * (Hs[6] * Hs[13] - Hs[7] * Hs[12]);
-    const double sc = fmax(fmax(fabs(Hs[0]), fabs(Hs[7])), fabs(Hs[14]));
-    if (!(fabs(det) > 1e-9 * sc * sc * sc)) return false;
-    if (lane < 9) Ai[lane] = adj * ddiv(1.0, det);
-  }
-  __syncwarp();
-  if (lane < 9) {  // Y = A^-1 B
-    Yv[lane] = Ai[i3 * 3 + 0] * Hs[0 * 6 + 3 + j3] + Ai[i3 * 3 + 1] * Hs[1 * 6 + 3 + j3] + Ai[i3 * 3 + 2] * Hs[2 * 6 + 3 + j3];
-  } else if (lane < 12) {  // v1 = A^-1 b1,  b1 = -g[0:3]
-    const int i = lane - 9;
-    Yv[lane] = -(Ai[i * 3 + 0] * gv[0] + Ai[i * 3 + 1] * gv[1] + Ai[i * 3 + 2] * gv[2]);
-  }
-  __syncwarp();
-  if (lane < 9) {  // S = D - B^T Y
-    Sv[lane] = Hs[(3 + i3) * 6 + 3 + j3] - (Hs[0 * 6 + 3 + i3] * Yv[0 * 3 + j3] + Hs[1 * 6 + 3 + i3] * Yv[1 * 3 + j3] + Hs[2 * 6 + 3 + i3] * Yv[2 * 3 + j3]);
-  } else if (lane < 12) {  // w = b2 - B^T v1,  b2 = -g[3:6]
-    const int i = lane - 9;
-    Sv[lane] = -gv[3 + i] - (Hs[0 * 6 + 3 + i] * Yv[9] + Hs[1 * 6 + 3 + i] * Yv[10] + Hs[2 * 6 + 3 + i] * Yv[11]);
-  }
-  __syncwarp();
-  {
-    const double adj = Sv[ja * 3 + ia] * Sv[jb * 3 + ib] - Sv[ja * 3 + ib] * Sv[jb * 3 + ia];
-    const double det = Sv[0] * (Sv[4] * Sv[8] - Sv[5] * Sv[7]) - Sv[1] * (Sv[3] * Sv[8] - Sv[5] * Sv[6]) +
-                       Sv[2] * (Sv[3] * Sv[7] - Sv[4] * Sv[6]);
-    const double sc = fmax(fmax(fabs(Sv[0]), fabs(Sv[4])), fabs(Sv[8]));
-    if (!(fabs(det) > 1e-9 * sc * sc * sc)) return false;
-    if (lane < 9) Si[lane] = adj * ddiv(1.0, det);
-  }
-  __syncwarp();
-  if (lane < 3) dpv[3 + lane] = Si[lane * 3 + 0] * Sv[9] + Si[lane * 3 + 1] * Sv[10] + Si[lane * 3 + 2] * Sv[11];  // x2 = S^-1 w
-  __syncwarp();
-  if (lane < 3) dpv[lane] = Yv[9 + lane] - (Yv[lane * 3 + 0] * dpv[3] + Yv[lane * 3 + 1] * dpv[4] + Yv[lane * 3 + 2] * dpv[5]);  // x1
-  __syncwarp();
   double n2 = 0.0;
 #pragma unroll
-  for (int i = 0; i < 6; i++) n2 += dpv[i] * dpv[i];
-  const double norm = dsqrt(n2);
+  for (int i = 0; i < 6; i++) n2 = fma(x[i], x[i], n2);
+  const double norm = sqrt(n2);
   if (norm == 0 || norm != norm) return false;
-  if (lane < 6) dirv[lane] = ddiv(dpv[lane], norm);
-  __syncwarp();
-  double dd = 0.0;
-#pragma unroll 1
-  for (int k = 0; k < 6; k++) dd += gv[k] * dirv[k];
+  const double rn = 1.0 / norm;
+  double dir[6], dd = 0.0;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    dir[k] = x[k] * rn;
+    dd = fma(tot[SLOT_G + k], dir[k], dd);
+  }
   double d_phi_0 = -dd;
   double sgn = 1.0;
   if (d_phi_0 >= 0) {
@@ -563,16 +526,20 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
   double a_t = norm;
   a_t = fmin(a_t, step_max);
   a_t = fmax(a_t, step_min);
-  // ---- write phase ----
+  // ---- write phase (nothing of the solver state was touched before this point) ----
   const double score = tot[SLOT_SCORE];
-  if (lane < 6) {
-    const double d = dirv[lane] * sgn;
-    st.p[lane] = pv[lane];
-    st.g[lane] = gv[lane];
-    st.dir[lane] = d;
-    st.x_t[lane] = pv[lane] + d * a_t;
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    if (lane == k) {  // static register indexing: lane k owns component k
+      const double d = dir[k] * sgn;
+      const double pk = (phase == PH_LS_FIRST) ? st.p[k] + st.dir[k] * a_prev : st.p[k];
+      st.p[k] = pk;
+      st.g[k] = tot[SLOT_G + k];
+      st.dir[k] = d;
+      st.x_t[k] = pk + d * a_t;
+    }
   }
-  if (lane == 0) {
+  if (lane == 6) {
     const long long hits = (long long)(tot[SLOT_HITS] + 0.5);
     st.score = score;
     st.hits_last = hits;
