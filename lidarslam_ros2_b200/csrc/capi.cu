@@ -516,15 +516,10 @@ int b200reg_voxelgrid(int device, const float* in, size_t n, size_t stride_bytes
     *m = 0;
     if (n == 0) return B200REG_OK;
     F.in.ensure(n);
-    F.staging.ensure(n);
+    static CloudUploader* uploaders[64] = {nullptr};
+    if (!uploaders[device]) uploaders[device] = new CloudUploader();
     const char* b = reinterpret_cast<const char*>(in);
-    for (size_t i = 0; i < n; i++) {
-      const float* f = reinterpret_cast<const float*>(b + i * stride_bytes);
-      float inten = intensity_offset_bytes >= 0 ? *reinterpret_cast<const float*>(b + i * stride_bytes + intensity_offset_bytes)
-                                                : 0.0f;
-      F.staging.ptr[i] = make_float4(f[0], f[1], f[2], inten);
-    }
-    B200_CUDA(cudaMemcpyAsync(F.in.ptr, F.staging.ptr, n * sizeof(float4), cudaMemcpyHostToDevice, s));
+    uploaders[device]->upload(in, n, stride_bytes, intensity_offset_bytes, 0.0f, F.in.ptr, s);  // raw records, unpacked on the device
     long long cnt = F.filter_device(F.in.ptr, n, leaf, s);
     char* ob = reinterpret_cast<char*>(out);
     if (cnt < 0) {  // overflow guard: PCL returns the input cloud unchanged

@@ -221,7 +221,7 @@ struct CostParams {
 };
 
 __global__ void __launch_bounds__(256) gicp_cost_kernel(CostParams P, double* __restrict__ partials, unsigned* __restrict__ ticket,
-                                                        double* __restrict__ result) {
+                                                        double* __restrict__ result, double* __restrict__ result_host) {
   double acc[14];
 #pragma unroll
   for (int k = 0; k < 14; k++) acc[k] = 0.0;
@@ -274,12 +274,22 @@ __global__ void __launch_bounds__(256) gicp_cost_kernel(CostParams P, double* __
   __syncthreads();
   if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
   __syncthreads();
-  if (last) {  // the last CTA sums the per-CTA partials in CTA order: deterministic
+  if (last) {  // the last CTA sums the per-CTA partials in a fixed order (16 interleaved chains per slot): deterministic
     __threadfence();
+    __shared__ double red[16][16];
+    const int slot = threadIdx.x & 15, part = threadIdx.x >> 4;
+    double s = 0;
+    if (slot < 14)
+      for (unsigned b = part; b < gridDim.x; b += 16) s += __ldcg(&partials[(size_t)b * K7_SLOTS + slot]);
+    red[part][slot] = s;
+    __syncthreads();
     if (threadIdx.x < 14) {
-      double s = 0;
-      for (unsigned b = 0; b < gridDim.x; b++) s += __ldcg(&partials[(size_t)b * K7_SLOTS + threadIdx.x]);
-      result[threadIdx.x] = s;
+      double t = 0;
+#pragma unroll
+      for (int q = 0; q < 16; q++) t += red[q][threadIdx.x];
+      result[threadIdx.x] = t;
+      result_host[threadIdx.x] = t;  // pinned host memory mapped into the device address space: no D2H copy to wait for
+      __threadfence_system();
     }
     if (threadIdx.x == 0) *ticket = 0;
   }
@@ -397,9 +407,9 @@ void GicpSolver::fdf(const float* T16, bool want_grad, double* f, double* g_t3, 
   for (int k = 0; k < 12; k++) P.T[k] = T16[k];
   P.n = (int)n_source_;
   P.want_grad = want_grad ? 1 : 0;
-  const int blocks = (int)std::min<size_t>((n_source_ + 255) / 256, 148 * 4);
-  gicp_cost_kernel<<<std::max(blocks, 1), 256, 0, stream_>>>(P, partials_.ptr, counter_.ptr + 1, result_.ptr);
-  B200_CUDA(cudaMemcpyAsync(h_result_, result_.ptr, K7_SLOTS * sizeof(double), cudaMemcpyDeviceToHost, stream_));
+  const int blocks = (int)std::min<size_t>((n_source_ + 255) / 256, 148 * 2);
+  gicp_cost_kernel<<<std::max(blocks, 1), 256, 0, stream_>>>(P, partials_.ptr, counter_.ptr + 1, result_.ptr, h_result_);
+  B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaStreamSynchronize(stream_));
   launches += 1;
   evaluations_ += 1;

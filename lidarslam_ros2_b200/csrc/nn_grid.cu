@@ -166,8 +166,9 @@ __global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4*
   if (!resolved) unresolved_list[atomicAdd(unresolved_count, 1u)] = (int)i;
 }
 
-// Phase 2: one CTA per unresolved query scans the whole (cell-sorted) cloud; lexicographic (d2, index) minimum, so the
-// result does not depend on the scan order.
+// Phase 2: one CTA per unresolved query. With a finite search radius the CTA shares the cells of the cube of that
+// radius; without one it scans the whole (cell-sorted) cloud. Lexicographic (d2, index) minimum, so the result does
+// not depend on the visiting order.
 __global__ void __launch_bounds__(256) nn1_bruteforce_kernel(NnQueryParams P, const float4* __restrict__ queries,
                                                              const unsigned* __restrict__ unresolved_count,
                                                              const int* __restrict__ unresolved_list, int* out_idx,
@@ -181,14 +182,39 @@ __global__ void __launch_bounds__(256) nn1_bruteforce_kernel(NnQueryParams P, co
     nn_query_point(P, queries[qi], qx, qy, qz);
     float best = FLT_MAX;
     int best_i = -1;
-    for (int k = threadIdx.x; k < P.n_points; k += blockDim.x) {
-      const float4 t = __ldg(P.V.sorted + k);
+    auto consider = [&](float4 t) {
       const float d2 = nn_dist2(qx, qy, qz, t);
       const int ti = __float_as_int(t.w);
       if (d2 < best || (d2 == best && ti < best_i)) {
         best = d2;
         best_i = ti;
       }
+    };
+    if (P.max_d2 < 3.0e38f) {
+      // the caller only wants neighbours within sqrt(max_d2): the CTA shares the cells of the cube of that radius
+      // around the query's cell (every point within the radius lies in it, also for queries outside the grid)
+      const NnGeom& g = P.V.g;
+      const int R = (int)ceilf(sqrtf(P.max_d2) * g.inv_h) + 1;
+      const int cx = nn_cell_coord(qx, g.origin[0], g.inv_h, g.dims[0]);
+      const int cy = nn_cell_coord(qy, g.origin[1], g.inv_h, g.dims[1]);
+      const int cz = nn_cell_coord(qz, g.origin[2], g.inv_h, g.dims[2]);
+      const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dims[0] - 1);
+      const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dims[1] - 1);
+      const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dims[2] - 1);
+      const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
+      const long long cells = (long long)nx * ny * nz;
+      for (long long c = threadIdx.x; c < cells; c += blockDim.x) {
+        const int x = x0 + (int)(c % nx), y = y0 + (int)((c / nx) % ny), z = z0 + (int)(c / ((long long)nx * ny));
+        const int cell = x + g.dims[0] * (y + g.dims[1] * z);
+        const uint2 w = __ldg(reinterpret_cast<const uint2*>(P.V.index + (cell >> 5)));
+        const unsigned bit = cell & 31;
+        if (!((w.x >> bit) & 1u)) continue;
+        const unsigned rk = w.y + __popc(w.x & ((1u << bit) - 1u));
+        const unsigned st = __ldg(P.V.cell_start + rk), en = __ldg(P.V.cell_start + rk + 1);
+        for (unsigned k = st; k < en; k++) consider(__ldg(P.V.sorted + k));
+      }
+    } else {
+      for (int k = threadIdx.x; k < P.n_points; k += blockDim.x) consider(__ldg(P.V.sorted + k));
     }
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) {
