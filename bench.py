@@ -261,30 +261,33 @@ def run_c5(args, rank, local_rank, world, m):
     rings, azim = 32, 1875
     frames = list(synth.drive_stream(args.frames, rings=rings, azimuths=azim, step=0.5, workers=min(32, os.cpu_count() or 1)))
     kw = dict(ndt_resolution=5.0, vg_size_for_input=0.2, vg_size_for_map=0.1, trans_for_mapupdate=1.5, num_targeted_cloud=10)
-    sm = ScanMatcher(device=local_rank, **kw)
     warm = ScanMatcher(device=local_rank, **kw)
-    for scan, _ in frames[:4]:  # warm-up on a throw-away session (allocations, first-launch costs)
+    for scan, _ in frames[:8]:  # warm-up on a throw-away session (allocations, first-launch costs)
         warm.receiveCloud(scan)
-    del warm
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = sm.registration.stats()["kernel_launches"]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    e0.record()
-    t0 = time.perf_counter()
-    errs, n_upd, bytes_in = [], 0, 0
-    for scan, T_gt in frames:
-        pose, final, upd = sm.receiveCloud(scan)
-        n_upd += int(upd)
-        bytes_in += scan.shape[0] * 16
-        errs.append(synth.pose_error(final, T_gt)[0])
-    e1.record()
-    torch.cuda.synchronize()
-    wall = time.perf_counter() - t0
-    ms = e0.elapsed_time(e1)
+    passes = []
+    for rep in range(3):  # three passes over the stream, each on a fresh session; the MEDIAN pass is reported
+        sm = ScanMatcher(device=local_rank, **kw)
+        launches0 = sm.registration.stats()["kernel_launches"]
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        t0 = time.perf_counter()
+        errs, n_upd, bytes_in = [], 0, 0
+        for scan, T_gt in frames:
+            pose, final, upd = sm.receiveCloud(scan)
+            n_upd += int(upd)
+            bytes_in += scan.shape[0] * scan.shape[1] * 4
+            errs.append(synth.pose_error(final, T_gt)[0])
+        e1.record()
+        torch.cuda.synchronize()
+        passes.append({"ms": e0.elapsed_time(e1), "wall": time.perf_counter() - t0, "errs": errs, "n_upd": n_upd, "bytes_in": bytes_in,
+                       "st": sm.stats(), "launches": int(sm.registration.stats()["kernel_launches"] - launches0 + sm.stats()["kernel_launches"])})
     clocks = sampler.stop()
-    st = sm.stats()
+    passes.sort(key=lambda p: p["ms"])
+    mid = passes[1]
+    ms, wall, errs, n_upd, bytes_in, st = mid["ms"], mid["wall"], mid["errs"], mid["n_upd"], mid["bytes_in"], mid["st"]
     # CPU restatement of the same callback on a bounded prefix of the same stream
     import oracle
     import oracle.scanmatcher as osm
@@ -309,10 +312,11 @@ def run_c5(args, rank, local_rank, world, m):
                                "VoxelGrid 0.2 + NDT res 5.0 per frame, map update every 1.5 m (VoxelGrid 0.1, last 10 submaps)",
                    "map_updates": n_upd, "submaps": st["n_submaps"], "targeted_points": st["n_targeted"],
                    "trajectory_error_m": {"max": float(np.max(errs)), "final": float(errs[-1])},
-                   "l2": "every frame is a new host buffer (one H2D copy per frame)"},
+                   "l2": "every frame is a new host buffer (one H2D copy per frame)",
+                   "passes_ms_per_frame": [p["ms"] / len(frames) for p in passes]},
         "e2e": {"value": v, "unit": "frames/s", "h2d_bytes_per_step": int(bytes_in / len(frames)), "d2h_bytes_per_step": 56 + 64 + 456,
                 "wall_s": wall},
-        "gpu_launches": int(sm.registration.stats()["kernel_launches"] - launches0 + st["kernel_launches"]),
+        "gpu_launches": mid["launches"],
         "clocks": clocks,
         "roofline": None,
         "cpu_baseline": {"value": n_cpu / t_cpu if t_cpu > 0 else None, "unit": "frames/s", "cores": oracle.max_threads(), "kind": "port",

@@ -1,5 +1,6 @@
 // Host-side engine classes behind the C-ABI (include/b200reg.h). C++17, CUDA runtime only — no torch types.
 #pragma once
+#include <algorithm>
 #include <cuda_runtime.h>
 
 #include <cstring>
@@ -25,11 +26,12 @@ struct DeviceBuffer {
     ptr = nullptr;
     cap = 0;
   }
-  // grow-only; contents are NOT preserved
+  // grow-only; contents are NOT preserved. Geometric growth: a buffer that creeps up (the targeted cloud of the
+  // frontend session, the per-frame scratch) must not pay a cudaFree + cudaMalloc pair on every call.
   void ensure(size_t n) {
     if (n <= cap) return;
+    const size_t want = std::max(n + n / 8 + 64, cap + cap / 2);
     release();
-    size_t want = n + n / 8 + 64;
     B200_CUDA(cudaMalloc(&ptr, want * sizeof(T)));
     cap = want;
   }

@@ -80,8 +80,28 @@ __global__ void transform_f64_kernel(const float4* __restrict__ in, size_t n, Ma
   out[i] = q;
 }
 
+// Submap clouds live in a chunked device arena: one cudaMalloc per ~64 MB instead of one per map update (cudaMalloc costs
+// tens to hundreds of microseconds and occasionally milliseconds — it would dominate a 0.5 ms frame).
+struct SubmapArena {
+  static constexpr size_t CHUNK_POINTS = (size_t)4 << 20;
+  std::vector<std::unique_ptr<DeviceBuffer<float4>>> chunks;
+  size_t used = 0, cap = 0;
+  float4* alloc(size_t n) {
+    if (chunks.empty() || used + n > cap) {
+      chunks.emplace_back(new DeviceBuffer<float4>());
+      cap = std::max(CHUNK_POINTS, n);
+      chunks.back()->ensure(cap);
+      cap = chunks.back()->cap;
+      used = 0;
+    }
+    float4* p = chunks.back()->ptr + used;
+    used += (n + 15) & ~(size_t)15;  // keep 256-byte alignment
+    return p;
+  }
+};
+
 struct Submap {
-  DeviceBuffer<float4> cloud;  // VoxelGrid(vg_size_for_map) of the scan, sensor frame
+  float4* cloud = nullptr;     // VoxelGrid(vg_size_for_map) of the scan, sensor frame (arena memory)
   size_t n = 0;
   double pose[16];             // row-major 4x4: Translation * Quaternion of the pose the scan was taken at
   double distance = 0;
@@ -110,6 +130,7 @@ struct b200sm_session {
   DeviceBuffer<unsigned> counter;
   VoxelGridFilter vg_input, vg_map, vg_target;
   size_t n_filtered = 0;
+  SubmapArena arena;
   std::vector<std::unique_ptr<Submap>> submaps;
   DeviceBuffer<float4> targeted;
   size_t n_targeted = 0;
@@ -255,7 +276,7 @@ int update_map(b200sm_t s, const float* final_T, const double* position, const d
     const Submap& sub = *s->submaps[n_sub - 1 - i];
     Mat34d Td;
     for (int k = 0; k < 12; k++) Td.m[k] = sub.pose[k];
-    if (sub.n) transform_f64_kernel<<<(int)((sub.n + 255) / 256), 256, 0, s->stream>>>(sub.cloud.ptr, sub.n, Td, s->targeted.ptr + off);
+    if (sub.n) transform_f64_kernel<<<(int)((sub.n + 255) / 256), 256, 0, s->stream>>>(sub.cloud, sub.n, Td, s->targeted.ptr + off);
     off += sub.n;
     s->launches += 1;
   }
@@ -264,9 +285,9 @@ int update_map(b200sm_t s, const float* final_T, const double* position, const d
   s->launches += 1;
   // the new submap keeps the FILTERED, untransformed cloud and the pose (:465-481)
   std::unique_ptr<Submap> sub(new Submap());
-  sub->cloud.ensure(std::max<size_t>(m, 1));
+  sub->cloud = s->arena.alloc(std::max<size_t>(m, 1));
   sub->n = m;
-  if (m) B200_CUDA(cudaMemcpyAsync(sub->cloud.ptr, filtered, m * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+  if (m) B200_CUDA(cudaMemcpyAsync(sub->cloud, filtered, m * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
   pose_to_matrix_d(position, quat, sub->pose);
   sub->distance = s->latest_distance;
   s->submaps.push_back(std::move(sub));
@@ -471,7 +492,7 @@ int b200sm_get_submap(b200sm_t s, size_t index, float* out_xyzi, size_t capacity
       for (int r = 0; r < 4; r++)
         for (int c = 0; c < 4; c++) pose_colmajor16[c * 4 + r] = sub.pose[r * 4 + c];
     if (distance) *distance = sub.distance;
-    return read_back(s, sub.cloud.ptr, sub.n, out_xyzi, capacity, n);
+    return read_back(s, sub.cloud, sub.n, out_xyzi, capacity, n);
   });
 }
 

@@ -8,7 +8,7 @@ mkdir -p $out
 timeout 600 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; tail -2 $out/pytest_gpu_$tag.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; tail -2 $out/smoke_$tag.log
 timeout 400 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; tail -c 600 $out/bench_$tag.json
-timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; tail -c 400 $out/bench_ref_$tag.json
+timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; tail -c 400 $out/bench_ref_$tag.json
 # launch list of the profile command (cold-cache, serialised: compare shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
   python tools/profile_step.py headline 3 > $out/prof_step_$tag.log 2>&1
@@ -18,3 +18,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page raw --csv > $out/ndt_solver_raw_$tag.csv 2>/dev/null
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page details --csv > $out/ndt_solver_details_$tag.csv 2>/dev/null
 ls -la $out | tail -12
+timeout 300 python bench.py --workload c3 > $out/bench_c3_$tag.json 2> $out/bench_c3_$tag.err; tail -c 300 $out/bench_c3_$tag.json
+timeout 400 python bench.py --workload c5 --frames 120 > $out/bench_c5_$tag.json 2> $out/bench_c5_$tag.err; tail -c 300 $out/bench_c5_$tag.json
