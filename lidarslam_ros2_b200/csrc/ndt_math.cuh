@@ -110,6 +110,40 @@ B200_HD double angle_table_entry(unsigned word, const double* f) {
   return angle_table_term(word & 0x7ffu, f) + angle_table_term((word >> 11) & 0x7ffu, f);
 }
 
+// Symmetric 6x6 solve  H x = b  by LDL^T elimination on the UPPER triangle, no pivoting, entirely in registers:
+// U[r][c] (c >= r) holds the upper triangle of H on entry. Returns false when a pivot collapses relative to the largest
+// diagonal entry or anything is non-finite (the caller then takes the pivoted-LU / SVD path that reproduces
+// JacobiSVD::solve, ndt_omp_impl.hpp:127-129). Straight-line code: the controller warp of the solver executes it once per
+// Newton iteration (ndt_solver.cu, controller_fast).
+B200_HD bool ldlt_solve6_upper(double (&U)[6][6], double (&rhs)[6], double (&x)[6]) {
+  double dmax = 0.0;
+#pragma unroll
+  for (int r = 0; r < 6; r++) dmax = fmax(dmax, fabs(U[r][r]));
+  bool ok = dmax > 0.0 && dmax <= 1.7e308;
+  double inv[6];
+#pragma unroll
+  for (int k = 0; k < 6; k++) {
+    ok = ok && (fabs(U[k][k]) > 1e-10 * dmax);  // false for NaN
+    inv[k] = 1.0 / U[k][k];
+#pragma unroll
+    for (int r = k + 1; r < 6; r++) {
+      const double l = U[k][r] * inv[k];
+#pragma unroll
+      for (int c = r; c < 6; c++) U[r][c] = fma(-l, U[k][c], U[r][c]);
+      rhs[r] = fma(-l, rhs[k], rhs[r]);
+    }
+  }
+  if (!ok) return false;
+#pragma unroll
+  for (int k = 5; k >= 0; k--) {
+    double t = rhs[k];
+#pragma unroll
+    for (int c = k + 1; c < 6; c++) t = fma(-U[k][c], x[c], t);
+    x[k] = t * inv[k];
+  }
+  return true;
+}
+
 // sin/cos of a moderate angle (|x| << 1e5; Euler angles live in [-pi, pi]) to < 1 ulp: Cody-Waite reduction by pi/2
 // and the fdlibm kernel polynomials. Compact on purpose: the device-side controller is instruction-fetch bound (ndt_solver.cu).
 B200_HD void sincos_compact(double x, double* s_out, double* c_out) {

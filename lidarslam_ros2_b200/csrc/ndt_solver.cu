@@ -472,38 +472,14 @@ __device__ __noinline__ bool controller_fast(const NdtLaunch& L, CtlShared& cs, 
   // independent FMAs and not a single shared-memory round trip or warp synchronisation between the dependent steps.
   // A pivot that collapses relative to the largest diagonal entry (or a NaN) hands the round to the scalar controller,
   // whose pivoted LU / SVD reproduce JacobiSVD::solve's behaviour for rank-deficient systems.
-  double A[6][6], rhs[6];  // (the gradient and the pose are re-read from shared memory later: registers are capped at 80)
-  double dmax = 0.0;
+  double A[6][6], rhs[6], x[6];  // (the gradient and the pose are re-read from shared memory later: registers are capped at 80)
 #pragma unroll
   for (int r = 0; r < 6; r++) {
 #pragma unroll
     for (int c = r; c < 6; c++) A[r][c] = tot[SLOT_H + tri_index(r, c)];
     rhs[r] = -tot[SLOT_G + r];
-    dmax = fmax(dmax, fabs(A[r][r]));
   }
-  bool ok = dmax > 0.0 && dmax <= 1.7e308;
-  double inv[6];
-#pragma unroll
-  for (int k = 0; k < 6; k++) {
-    ok = ok && (fabs(A[k][k]) > 1e-10 * dmax);  // false for NaN
-    inv[k] = 1.0 / A[k][k];
-#pragma unroll
-    for (int r = k + 1; r < 6; r++) {
-      const double l = A[k][r] * inv[k];
-#pragma unroll
-      for (int c = r; c < 6; c++) A[r][c] = fma(-l, A[k][c], A[r][c]);
-      rhs[r] = fma(-l, rhs[k], rhs[r]);
-    }
-  }
-  if (!ok) return false;
-  double x[6];
-#pragma unroll
-  for (int k = 5; k >= 0; k--) {
-    double t = rhs[k];
-#pragma unroll
-    for (int c = k + 1; c < 6; c++) t = fma(-A[k][c], x[c], t);
-    x[k] = t * inv[k];
-  }
+  if (!ldlt_solve6_upper(A, rhs, x)) return false;
   double n2 = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; i++) n2 = fma(x[i], x[i], n2);

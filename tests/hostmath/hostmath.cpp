@@ -21,6 +21,16 @@ void hm_sincos_compact(double x, double* sc2) { b200::sincos_compact(x, sc2, sc2
 void hm_pose_to_matrix(const double* p6, float* T12) { b200::pose_to_matrix(p6, T12); }
 void hm_euler_angles_012(const float* R9, float* out3) { b200::euler_angles_012(R9, out3); }
 void hm_solve6(const double* H36, const double* b6, double* x6) { b200::solve6(H36, b6, x6); }
+int hm_ldlt_solve6(const double* H36, const double* b6, double* x6) {
+  double U[6][6], rhs[6], x[6] = {0, 0, 0, 0, 0, 0};
+  for (int r = 0; r < 6; r++) {
+    for (int c = 0; c < 6; c++) U[r][c] = H36[r * 6 + c];
+    rhs[r] = b6[r];
+  }
+  const bool ok = b200::ldlt_solve6_upper(U, rhs, x);
+  for (int k = 0; k < 6; k++) x6[k] = x[k];
+  return ok ? 1 : 0;
+}
 void hm_solve6_svd(const double* H36, const double* b6, double* x6) { b200::solve6_svd(H36, b6, x6); }
 double hm_mt_trial(const double* v9) { return b200::mt_trial_value(v9[0], v9[1], v9[2], v9[3], v9[4], v9[5], v9[6], v9[7], v9[8]); }
 int hm_mt_update(double* v6, const double* t3) {

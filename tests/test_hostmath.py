@@ -82,6 +82,31 @@ def test_solve6_matches_svd(hm, oracle_mod):
     assert np.all(x == 0)
 
 
+def test_ldlt_solve6_matches_svd_on_definite_systems(hm, oracle_mod):
+    """The controller's in-register Newton solve (ndt_math.cuh ldlt_solve6_upper): same x as JacobiSVD::solve on the
+    negative-definite Hessians Newton works with; refuses (returns 0) collapsed pivots and non-finite input so that the
+    pivoted-LU / SVD path takes over."""
+    rng = np.random.default_rng(8)
+    scale = np.array([1, 1, 1, 40, 40, 40.0])
+    for k in range(200):
+        A = rng.normal(size=(6, 6))
+        H = -(A @ A.T + 0.05 * np.eye(6)) * scale[:, None] * scale[None, :]  # NDT's score Hessian is negative definite
+        b = rng.normal(size=6) * scale
+        x = np.zeros(6)
+        assert hm.hm_ldlt_solve6(_p(np.ascontiguousarray(H)), _p(b), _p(x)) == 1
+        ref = oracle_mod.svd6_solve(H, b)
+        np.testing.assert_allclose(x, ref, rtol=1e-6 * np.linalg.cond(H) / 1e3 + 1e-9, atol=1e-10 * np.abs(ref).max())
+    x = np.zeros(6)
+    assert hm.hm_ldlt_solve6(_p(np.diag([4.0, 3.0, 2.0, 1.0, 0.0, 0.0])), _p(np.ones(6)), _p(x)) == 0  # rank deficient
+    assert hm.hm_ldlt_solve6(_p(np.zeros((6, 6))), _p(np.ones(6)), _p(x)) == 0
+    Hn = -np.eye(6)
+    Hn[2, 4] = Hn[4, 2] = np.nan
+    assert hm.hm_ldlt_solve6(_p(Hn), _p(np.ones(6)), _p(x)) == 0
+    Hi = -np.eye(6)
+    Hi[0, 0] = np.inf
+    assert hm.hm_ldlt_solve6(_p(Hi), _p(np.ones(6)), _p(x)) == 0
+
+
 def test_more_thuente_helpers_match_oracle(hm, oracle_mod):
     rng = np.random.default_rng(4)
     for _ in range(300):
