@@ -1,14 +1,25 @@
-// Host-side BFGS driver of the GICP engine (product code; the oracle keeps its own copy under oracle/).
+// BFGS driver of the GICP engine (product code; the oracle keeps its own copy under oracle/).
 // Implements the minimiser the reference calls at gicp_omp_impl.hpp:209-230 — PCL 1.12 `BFGS<Functor>`
 // (pcl/registration/bfgs.h, external), a port of GSL's vector_bfgs2 + Fletcher bracketing/sectioning line search
-// (multimin/linear_minimize.c) — with sigma=0.01, rho=0.01, tau1=9, tau2=0.05, tau3=0.5, order=3. Each functor
-// evaluation is one K7 reduction kernel on the GPU (gicp.cu); the 6-vector state machine itself stays on the host.
+// (multimin/linear_minimize.c) — with sigma=0.01, rho=0.01, tau1=9, tau2=0.05, tau3=0.5, order=3.
+// The 6-vector state machine is __host__ __device__ and templated on the functor: the host instantiation drives one K7
+// reduction kernel per functor evaluation; the device instantiation runs inside the persistent inner-loop kernel
+// (gicp.cu: every thread of the controller CTA executes it redundantly and identically, so that the whole CTA takes part
+// in each functor evaluation).
 #pragma once
-#include <cmath>
+#include <math.h>
+
 #include <functional>
-#include <limits>
+
+#if defined(__CUDACC__)
+#define B200_BFGS_HD __host__ __device__
+#else
+#define B200_BFGS_HD
+#endif
 
 namespace b200 {
+
+constexpr double BFGS_DBL_EPSILON = 2.220446049250313e-16;
 
 enum BfgsStatus { BFGS_NegativeGradientEpsilon = -3, BFGS_NotStarted = -2, BFGS_Running = -1, BFGS_Success = 0, BFGS_NoProgress = 1 };
 
@@ -18,7 +29,8 @@ struct BfgsFunctor6 {
   std::function<void(const double*, double&, double*)> fdf;
 };
 
-class Bfgs6 {
+template <class Functor>
+class Bfgs6T {
  public:
   static constexpr int N = 6;
   struct Parameters {
@@ -30,9 +42,9 @@ class Bfgs6 {
   double gradient[N];
   int n_f = 0, n_df = 0, n_fdf = 0;  // instrumentation
 
-  explicit Bfgs6(BfgsFunctor6& fn) : functor(fn) {}
+  B200_BFGS_HD explicit Bfgs6T(Functor& fn) : functor(fn) {}
 
-  BfgsStatus minimizeInit(double* x) {
+  B200_BFGS_HD BfgsStatus minimizeInit(double* x) {
     delta_f = 0;
     for (int i = 0; i < N; i++) dx[i] = 0;
     functor.fdf(x, f, gradient);
@@ -47,7 +59,7 @@ class Bfgs6 {
     return BFGS_NotStarted;
   }
 
-  BfgsStatus minimizeOneStep(double* x) {
+  B200_BFGS_HD BfgsStatus minimizeOneStep(double* x) {
     double alpha = 0.0, alpha1;
     double f0 = f;
     if (pnorm == 0.0 || g0norm == 0.0 || fp0 == 0) {
@@ -55,10 +67,10 @@ class Bfgs6 {
       return BFGS_NoProgress;
     }
     if (delta_f < 0) {
-      double del = std::max(-delta_f, 10 * std::numeric_limits<double>::epsilon() * std::fabs(f0));
-      alpha1 = std::min(1.0, 2.0 * del / (-fp0));
+      double del = fmax(-delta_f, 10 * BFGS_DBL_EPSILON * fabs(f0));
+      alpha1 = fmin(1.0, 2.0 * del / (-fp0));
     } else {
-      alpha1 = std::fabs(parameters.step_size);
+      alpha1 = fabs(parameters.step_size);
     }
     BfgsStatus status = lineSearch(parameters.rho, parameters.sigma, parameters.tau1, parameters.tau2,
                                    parameters.tau3, parameters.order, alpha1, alpha);
@@ -96,23 +108,23 @@ class Bfgs6 {
   }
 
   // pre-1.11 PCL semantic `testGradient(epsilon)`: Success iff |g| < epsilon (see gicp.hpp header note)
-  BfgsStatus testGradient(double epsilon) const {
+  B200_BFGS_HD BfgsStatus testGradient(double epsilon) const {
     if (epsilon < 0) return BFGS_NegativeGradientEpsilon;
     return norm(gradient) < epsilon ? BFGS_Success : BFGS_Running;
   }
 
  private:
-  BfgsFunctor6& functor;
+  Functor& functor;
   double delta_f = 0, fp0 = 0, pnorm = 0, g0norm = 0;
   double x0[N], g0[N], dx[N], p[N];
   double f_alpha = 0, df_alpha = 0, x_alpha[N], g_alpha[N];
   double f_cache_key = 0, df_cache_key = 0, x_cache_key = 0, g_cache_key = 0;
 
-  static void copy(double* d, const double* s) { for (int i = 0; i < N; i++) d[i] = s[i]; }
-  static double dot(const double* a, const double* b) { double s = 0; for (int i = 0; i < N; i++) s += a[i] * b[i]; return s; }
-  static double norm(const double* a) { return std::sqrt(dot(a, a)); }
+  B200_BFGS_HD static void copy(double* d, const double* s) { for (int i = 0; i < N; i++) d[i] = s[i]; }
+  B200_BFGS_HD static double dot(const double* a, const double* b) { double s = 0; for (int i = 0; i < N; i++) s += a[i] * b[i]; return s; }
+  B200_BFGS_HD static double norm(const double* a) { return sqrt(dot(a, a)); }
 
-  void changeDirection() {
+  B200_BFGS_HD void changeDirection() {
     copy(x_alpha, x0);
     x_cache_key = 0;
     f_alpha = f;
@@ -122,13 +134,13 @@ class Bfgs6 {
     df_alpha = slope();
     df_cache_key = 0;
   }
-  void moveTo(double alpha) {
+  B200_BFGS_HD void moveTo(double alpha) {
     if (alpha == x_cache_key) return;
     for (int i = 0; i < N; i++) x_alpha[i] = x0[i] + alpha * p[i];
     x_cache_key = alpha;
   }
-  double slope() const { return dot(g_alpha, p); }
-  double applyF(double alpha) {
+  B200_BFGS_HD double slope() const { return dot(g_alpha, p); }
+  B200_BFGS_HD double applyF(double alpha) {
     if (alpha == f_cache_key) return f_alpha;
     moveTo(alpha);
     f_alpha = functor.f(x_alpha);
@@ -136,7 +148,7 @@ class Bfgs6 {
     f_cache_key = alpha;
     return f_alpha;
   }
-  double applyDF(double alpha) {
+  B200_BFGS_HD double applyDF(double alpha) {
     if (alpha == df_cache_key) return df_alpha;
     moveTo(alpha);
     if (alpha != g_cache_key) {
@@ -148,7 +160,7 @@ class Bfgs6 {
     df_cache_key = alpha;
     return df_alpha;
   }
-  void applyFDF(double alpha, double& fo, double& dfo) {
+  B200_BFGS_HD void applyFDF(double alpha, double& fo, double& dfo) {
     if (alpha == f_cache_key && alpha == df_cache_key) {
       fo = f_alpha;
       dfo = df_alpha;
@@ -169,7 +181,7 @@ class Bfgs6 {
     fo = f_alpha;
     dfo = df_alpha;
   }
-  void updatePosition(double alpha, double* x) {
+  B200_BFGS_HD void updatePosition(double alpha, double* x) {
     double fa, dfa;
     applyFDF(alpha, fa, dfa);
     f = f_alpha;
@@ -177,15 +189,15 @@ class Bfgs6 {
     copy(gradient, g_alpha);
   }
 
-  static double cubic(double c0, double c1, double c2, double c3, double z) { return c0 + z * (c1 + z * (c2 + z * c3)); }
-  static void check_extremum(double c0, double c1, double c2, double c3, double z, double& zmin, double& fmin) {
+  B200_BFGS_HD static double cubic(double c0, double c1, double c2, double c3, double z) { return c0 + z * (c1 + z * (c2 + z * c3)); }
+  B200_BFGS_HD static void check_extremum(double c0, double c1, double c2, double c3, double z, double& zmin, double& fmin) {
     double y = cubic(c0, c1, c2, c3, z);
     if (y < fmin) {
       zmin = z;
       fmin = y;
     }
   }
-  static int solve_quadratic(double a, double b, double c, double& x0, double& x1) {
+  B200_BFGS_HD static int solve_quadratic(double a, double b, double c, double& x0, double& x1) {
     if (a == 0) {
       if (b == 0) return 0;
       x0 = -c / b;
@@ -194,12 +206,12 @@ class Bfgs6 {
     double disc = b * b - 4 * a * c;
     if (disc > 0) {
       if (b == 0) {
-        double r = std::sqrt(-c / a);
+        double r = sqrt(-c / a);
         x0 = -r;
         x1 = r;
       } else {
         double sgnb = (b > 0 ? 1 : -1);
-        double temp = -0.5 * (b + sgnb * std::sqrt(disc));
+        double temp = -0.5 * (b + sgnb * sqrt(disc));
         double r1 = temp / a, r2 = c / temp;
         if (r1 < r2) { x0 = r1; x1 = r2; } else { x0 = r2; x1 = r1; }
       }
@@ -211,7 +223,7 @@ class Bfgs6 {
     }
     return 0;
   }
-  static double interp_quad(double f0, double fp0, double f1, double zl, double zh, double& zmin_out) {
+  B200_BFGS_HD static double interp_quad(double f0, double fp0, double f1, double zl, double zh, double& zmin_out) {
     double fl = f0 + zl * (fp0 + zl * (f1 - f0 - fp0));
     double fh = f0 + zh * (fp0 + zh * (f1 - f0 - fp0));
     double c = 2 * (f1 - f0 - fp0);
@@ -227,7 +239,7 @@ class Bfgs6 {
     zmin_out = zmin;
     return fmin;
   }
-  static double interp_cubic(double f0, double fp0, double f1, double fp1, double zl, double zh, double& zmin_out) {
+  B200_BFGS_HD static double interp_cubic(double f0, double fp0, double f1, double fp1, double zl, double zh, double& zmin_out) {
     double eta = 3 * (f1 - f0) - 2 * fp0 - fp1;
     double xi = fp0 + fp1 - 2 * (f1 - f0);
     double c0 = f0, c1 = fp0, c2 = eta, c3 = xi;
@@ -244,16 +256,20 @@ class Bfgs6 {
     zmin_out = zmin;
     return fmin;
   }
-  static double interpolate(double a, double fa, double fpa, double b, double fb, double fpb, double xmin, double xmax,
+  B200_BFGS_HD static double interpolate(double a, double fa, double fpa, double b, double fb, double fpb, double xmin, double xmax,
                             int order) {
     double y, ymin = (xmin - a) / (b - a), ymax = (xmax - a) / (b - a);
-    if (ymin > ymax) std::swap(ymin, ymax);
-    if (order > 2 && !std::isnan(fpb)) interp_cubic(fa, fpa * (b - a), fb, fpb * (b - a), ymin, ymax, y);
+    if (ymin > ymax) {
+      const double t = ymin;
+      ymin = ymax;
+      ymax = t;
+    }
+    if (order > 2 && (fpb == fpb)) interp_cubic(fa, fpa * (b - a), fb, fpb * (b - a), ymin, ymax, y);
     else interp_quad(fa, fpa * (b - a), fb, ymin, ymax, y);
     return a + y * (b - a);
   }
 
-  BfgsStatus lineSearch(double rho, double sigma, double tau1, double tau2, double tau3, int order, double alpha1,
+  B200_BFGS_HD BfgsStatus lineSearch(double rho, double sigma, double tau1, double tau2, double tau3, int order, double alpha1,
                         double& alpha_new) {
     double f0, fp0l, falpha, falpha_prev, fpalpha = 0, fpalpha_prev, delta, alpha_next;
     double alpha = alpha1, alpha_prev = 0.0;
@@ -269,11 +285,11 @@ class Bfgs6 {
       falpha = applyF(alpha);
       if (falpha > f0 + alpha * rho * fp0l || falpha >= falpha_prev) {
         a = alpha_prev; fa = falpha_prev; fpa = fpalpha_prev;
-        b = alpha; fb = falpha; fpb = std::numeric_limits<double>::quiet_NaN();
+        b = alpha; fb = falpha; fpb = nan("");
         break;
       }
       fpalpha = applyDF(alpha);
-      if (std::fabs(fpalpha) <= -sigma * fp0l) {
+      if (fabs(fpalpha) <= -sigma * fp0l) {
         alpha_new = alpha;
         return BFGS_Success;
       }
@@ -299,12 +315,12 @@ class Bfgs6 {
         alpha = interpolate(a, fa, fpa, b, fb, fpb, lower, upper, order);
       }
       falpha = applyF(alpha);
-      if ((a - alpha) * fpa <= std::numeric_limits<double>::epsilon()) return BFGS_NoProgress;
+      if ((a - alpha) * fpa <= BFGS_DBL_EPSILON) return BFGS_NoProgress;
       if (falpha > f0 + rho * alpha * fp0l || falpha >= fa) {
-        b = alpha; fb = falpha; fpb = std::numeric_limits<double>::quiet_NaN();
+        b = alpha; fb = falpha; fpb = nan("");
       } else {
         fpalpha = applyDF(alpha);
-        if (std::fabs(fpalpha) <= -sigma * fp0l) {
+        if (fabs(fpalpha) <= -sigma * fp0l) {
           alpha_new = alpha;
           return BFGS_Success;
         }
@@ -319,5 +335,7 @@ class Bfgs6 {
     return BFGS_Success;
   }
 };
+
+using Bfgs6 = Bfgs6T<BfgsFunctor6>;  // host instantiation: std::function callbacks that launch K7
 
 }  // namespace b200

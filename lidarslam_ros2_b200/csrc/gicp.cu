@@ -4,7 +4,7 @@
 // Replaces pclomp::GeneralizedIterativeClosestPoint (Thirdparty/ndt_omp_ros2/include/pclomp/gicp_omp_impl.hpp):
 //   computeCovariances :48-122 (K5), computeTransformation :369-515 (outer loop; correspondence search :420-456 = K6),
 //   OptimizationFunctorWithIndices operator()/df/fdf :244-366 (K7), estimateRigidTransformationBFGS :180-241 with PCL's
-//   BFGS (GSL vector_bfgs2; external) restated in bfgs_host.hpp, computeRDerivative :125-177, applyState :517-528.
+//   BFGS (GSL vector_bfgs2; external) restated in bfgs6.hpp, computeRDerivative :125-177, applyState :517-528.
 // Nearest neighbours come from the exact cell-grid search of nn_search.cuh instead of FLANN kd-trees.
 // Algorithmic HBM bytes: K6/K7 per evaluation m*(16+16+48); K5 N*(16 + k*16) + visited cells.
 #include <algorithm>
@@ -12,7 +12,7 @@
 #include <cstring>
 #include <vector>
 
-#include "bfgs_host.hpp"
+#include "bfgs6.hpp"
 #include "gicp.hpp"
 #include "nn_search.cuh"
 

@@ -2,8 +2,74 @@
 // with g++ so that tests/test_hostmath.py can check it on the CPU. Not a compute fallback: nothing here touches
 // point clouds.
 #include "../../lidarslam_ros2_b200/csrc/ndt_math.cuh"
+#include "../../lidarslam_ros2_b200/csrc/bfgs6.hpp"
+#include "../../oracle/bfgs.hpp"
+
+namespace {
+// smooth non-quadratic test objective for the BFGS restatements (6 unknowns)
+struct TestObjective {
+  double c[6], w[6];
+  double f(const double* x) const {
+    double s = 0;
+    for (int i = 0; i < 6; i++) s += w[i] * (x[i] - c[i]) * (x[i] - c[i]);
+    return s + 0.1 * (x[0] * x[1]) * (x[0] * x[1]) + 0.5 * (1.0 - cos(x[3] - x[4]));
+  }
+  void df(const double* x, double* g) const {
+    for (int i = 0; i < 6; i++) g[i] = 2 * w[i] * (x[i] - c[i]);
+    g[0] += 0.2 * x[0] * x[1] * x[1];
+    g[1] += 0.2 * x[0] * x[0] * x[1];
+    g[3] += 0.5 * sin(x[3] - x[4]);
+    g[4] -= 0.5 * sin(x[3] - x[4]);
+  }
+  void fdf(const double* x, double& fo, double* g) const {
+    fo = f(x);
+    df(x, g);
+  }
+};
+}  // namespace
 
 extern "C" {
+// runs the product's templated BFGS (plain functor, the form the device instantiation uses) and the oracle's BFGS on the same
+// objective; out: x_product[6], x_oracle[6], {f, n_f, n_df, n_fdf, inner} x 2
+void hm_bfgs_compare(const double* c6, const double* w6, const double* x0, int max_inner, double grad_tol, double* out22) {
+  TestObjective obj;
+  for (int i = 0; i < 6; i++) { obj.c[i] = c6[i]; obj.w[i] = w6[i]; }
+  {
+    b200::Bfgs6T<TestObjective> b(obj);
+    double x[6];
+    for (int i = 0; i < 6; i++) x[i] = x0[i];
+    int inner = 0, result = b.minimizeInit(x);
+    result = b200::BFGS_Running;
+    do {
+      inner++;
+      result = b.minimizeOneStep(x);
+      if (result) break;
+      result = b.testGradient(grad_tol);
+    } while (result == b200::BFGS_Running && inner < max_inner);
+    for (int i = 0; i < 6; i++) out22[i] = x[i];
+    out22[12] = b.f; out22[13] = b.n_f; out22[14] = b.n_df; out22[15] = b.n_fdf; out22[16] = inner;
+  }
+  {
+    oracle::BfgsFunctor6 fn;
+    fn.f = [&](const double* x) { return obj.f(x); };
+    fn.df = [&](const double* x, double* g) { obj.df(x, g); };
+    fn.fdf = [&](const double* x, double& f, double* g) { obj.fdf(x, f, g); };
+    oracle::BFGS6 b(fn);
+    double x[6];
+    for (int i = 0; i < 6; i++) x[i] = x0[i];
+    int inner = 0, result = b.minimizeInit(x);
+    result = oracle::BFGS_Running;
+    do {
+      inner++;
+      result = b.minimizeOneStep(x);
+      if (result) break;
+      result = b.testGradient(grad_tol);
+    } while (result == oracle::BFGS_Running && inner < max_inner);
+    for (int i = 0; i < 6; i++) out22[6 + i] = x[i];
+    out22[17] = b.f; out22[18] = b.n_f; out22[19] = b.n_df; out22[20] = b.n_fdf; out22[21] = inner;
+  }
+}
+
 void hm_angle_tables(const double* p6, float* jang24, float* hang45, double* jd24, double* hd45) {
   b200::angle_tables(p6, jang24, hang45, jd24, hd45);
 }

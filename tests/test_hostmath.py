@@ -14,12 +14,14 @@ def hm():
     src = os.path.join(HERE, "hostmath", "hostmath.cpp")
     lib = os.path.join(HERE, "hostmath", "libhostmath.so")
     deps = [src, os.path.join(HERE, "..", "lidarslam_ros2_b200", "csrc", "ndt_math.cuh"),
-            os.path.join(HERE, "..", "lidarslam_ros2_b200", "csrc", "angle_table_code.inc")]
+            os.path.join(HERE, "..", "lidarslam_ros2_b200", "csrc", "angle_table_code.inc"),
+            os.path.join(HERE, "..", "lidarslam_ros2_b200", "csrc", "bfgs6.hpp"), os.path.join(HERE, "..", "oracle", "bfgs.hpp")]
     if not os.path.exists(lib) or any(os.path.getmtime(d) > os.path.getmtime(lib) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fPIC", "-shared", "-x", "c++", src, "-o", lib])
     L = C.CDLL(lib)
     L.hm_mt_trial.restype = C.c_double
     L.hm_gauss.argtypes = [C.c_double, C.c_float, C.c_void_p]
+    L.hm_bfgs_compare.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_void_p]
     return L
 
 
@@ -142,3 +144,18 @@ def test_compact_sincos_within_one_ulp(hm):
         hm.hm_sincos_compact(float(x), _p(out))
         for got, ref in ((out[0], np.sin(x)), (out[1], np.cos(x))):
             assert abs(got - ref) <= 1.01 * np.spacing(abs(ref)) + 3e-17, (x, got, ref)
+
+
+def test_templated_bfgs_matches_oracle_bfgs(hm):
+    """csrc/bfgs6.hpp (host/device template, plain functor — the form the persistent GICP kernel instantiates) against
+    oracle/bfgs.hpp on a smooth non-quadratic objective: same iterates, same number of functor evaluations."""
+    rng = np.random.default_rng(21)
+    for k in range(25):
+        c = rng.normal(size=6)
+        w = rng.uniform(0.5, 20.0, size=6)
+        x0 = c + rng.normal(size=6) * 0.5
+        out = np.zeros(22)
+        hm.hm_bfgs_compare(_p(c), _p(w), _p(x0), 20, 1e-2, _p(out))
+        np.testing.assert_array_equal(out[:6], out[6:12])
+        np.testing.assert_array_equal(out[12:17], out[17:22])
+        assert out[16] >= 1 and np.abs(out[:6] - c).max() < 0.5
