@@ -220,40 +220,42 @@ struct CostParams {
   int want_grad;
 };
 
+// one correspondence's contribution to the 14 sums (operator() :264-270; fdf / df :347-360)
+__device__ __forceinline__ void cost_point(const CostParams& P, const float* T, int want_grad, int i, double (&acc)[14]) {
+  const int c = P.corr[i];
+  if (c < 0) return;
+  const float4 ps = P.moved[i];
+  const float4 pt = __ldg(P.target + c);
+  const float px = T[0] * ps.x + T[1] * ps.y + T[2] * ps.z + T[3];
+  const float py = T[4] * ps.x + T[5] * ps.y + T[6] * ps.z + T[7];
+  const float pz = T[8] * ps.x + T[9] * ps.y + T[10] * ps.z + T[11];
+  const float r0 = px - pt.x, r1 = py - pt.y, r2 = pz - pt.z;
+  const float* M = P.maha + (size_t)i * 9;
+  if (!want_grad) {  // operator(): f32 residual, f32 M * res, f64 accumulation (:264-270)
+    const float m0 = M[0] * r0 + M[1] * r1 + M[2] * r2;
+    const float m1 = M[3] * r0 + M[4] * r1 + M[5] * r2;
+    const float m2 = M[6] * r0 + M[7] * r1 + M[8] * r2;
+    acc[0] += (double)(r0 * m0 + r1 * m1 + r2 * m2);
+  } else {  // fdf / df: residual to f64, temp = M(f64) * res (:347-360)
+    const double d0 = (double)r0, d1 = (double)r1, d2 = (double)r2;
+    const double t0 = (double)M[0] * d0 + (double)M[1] * d1 + (double)M[2] * d2;
+    const double t1 = (double)M[3] * d0 + (double)M[4] * d1 + (double)M[5] * d2;
+    const double t2 = (double)M[6] * d0 + (double)M[7] * d1 + (double)M[8] * d2;
+    acc[1] += d0 * t0 + d1 * t1 + d2 * t2;
+    acc[2] += t0; acc[3] += t1; acc[4] += t2;
+    const double bx = ps.x, by = ps.y, bz = ps.z;  // base_transformation_ = identity (:393)
+    acc[5] += bx * t0; acc[6] += bx * t1; acc[7] += bx * t2;
+    acc[8] += by * t0; acc[9] += by * t1; acc[10] += by * t2;
+    acc[11] += bz * t0; acc[12] += bz * t1; acc[13] += bz * t2;
+  }
+}
+
 __global__ void __launch_bounds__(256) gicp_cost_kernel(CostParams P, double* __restrict__ partials, unsigned* __restrict__ ticket,
                                                         double* __restrict__ result, double* __restrict__ result_host) {
   double acc[14];
 #pragma unroll
   for (int k = 0; k < 14; k++) acc[k] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) {
-    const int c = P.corr[i];
-    if (c < 0) continue;
-    const float4 ps = P.moved[i];
-    const float4 pt = __ldg(P.target + c);
-    const float* T = P.T;
-    const float px = T[0] * ps.x + T[1] * ps.y + T[2] * ps.z + T[3];
-    const float py = T[4] * ps.x + T[5] * ps.y + T[6] * ps.z + T[7];
-    const float pz = T[8] * ps.x + T[9] * ps.y + T[10] * ps.z + T[11];
-    const float r0 = px - pt.x, r1 = py - pt.y, r2 = pz - pt.z;
-    const float* M = P.maha + (size_t)i * 9;
-    if (!P.want_grad) {  // operator(): f32 residual, f32 M * res, f64 accumulation (:264-270)
-      const float m0 = M[0] * r0 + M[1] * r1 + M[2] * r2;
-      const float m1 = M[3] * r0 + M[4] * r1 + M[5] * r2;
-      const float m2 = M[6] * r0 + M[7] * r1 + M[8] * r2;
-      acc[0] += (double)(r0 * m0 + r1 * m1 + r2 * m2);
-    } else {  // fdf / df: residual to f64, temp = M(f64) * res (:347-360)
-      const double d0 = (double)r0, d1 = (double)r1, d2 = (double)r2;
-      const double t0 = (double)M[0] * d0 + (double)M[1] * d1 + (double)M[2] * d2;
-      const double t1 = (double)M[3] * d0 + (double)M[4] * d1 + (double)M[5] * d2;
-      const double t2 = (double)M[6] * d0 + (double)M[7] * d1 + (double)M[8] * d2;
-      acc[1] += d0 * t0 + d1 * t1 + d2 * t2;
-      acc[2] += t0; acc[3] += t1; acc[4] += t2;
-      const double bx = ps.x, by = ps.y, bz = ps.z;  // base_transformation_ = identity (:393)
-      acc[5] += bx * t0; acc[6] += bx * t1; acc[7] += bx * t2;
-      acc[8] += by * t0; acc[9] += by * t1; acc[10] += by * t2;
-      acc[11] += bz * t0; acc[12] += bz * t1; acc[13] += bz * t2;
-    }
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n; i += gridDim.x * blockDim.x) cost_point(P, P.T, P.want_grad, i, acc);
   __shared__ double sm[8][K7_SLOTS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -361,6 +363,282 @@ void r_derivative(const double* x, const double* R, double* g) {
   g[5] = inner(dPsi);
 }
 
+
+// =====================================================================================================================
+// Persistent inner loop: estimateRigidTransformationBFGS (gicp_omp_impl.hpp:180-241) for one set of correspondences in ONE
+// cooperative launch. The host-driven path above pays a kernel launch and a stream synchronisation for each of the ~65
+// functor evaluations of an outer iteration; here evaluator CTAs keep their chunk of correspondences and loop
+//   wait for the next transform -> 14 partial sums -> publish a row,
+// while EVERY thread of the controller CTA runs the BFGS state machine (bfgs6.hpp) redundantly and identically: each functor
+// evaluation is a CTA-wide step — publish the transform, sum the evaluators' rows in a fixed order (the loads are the
+// arrival poll), continue. Signalling is the flag-in-data scheme of the NDT solver (ndt_solver.cuh): {payload, sequence}
+// control words, self-validating partial rows double-buffered by round parity.
+// =====================================================================================================================
+constexpr int GI_THREADS = 256;
+constexpr int GI_MAX_CTAS = 256;
+constexpr int GI_CTL_WORDS = 14;  // T[12] (float bits), want_grad, mode
+constexpr int GI_CTL_COPIES = 4;
+constexpr unsigned long long GI_EMPTY = 0xFFF8DEADFFF8DEADull;
+constexpr long long GI_TIMEOUT_CYCLES = 4000000000LL;
+enum { GI_MODE_RUN = 0, GI_MODE_EXIT = 1 };
+
+}  // namespace
+
+struct GicpInnerWork {
+  alignas(128) unsigned long long ctl[GI_CTL_COPIES][16];
+  alignas(128) double rows[2][GI_MAX_CTAS][K7_SLOTS];
+  unsigned error;
+};
+
+namespace {
+
+struct GicpInnerLaunch {
+  CostParams P;  // P.T / P.want_grad are unused here: the controller publishes them per evaluation
+  GicpInnerWork* work;
+  GicpInnerResult* result_host;
+  double x0[6];
+  double m;  // number of correspondences (the functor's normalisation, gicp_omp_impl.hpp:270, 363-365)
+  double gradient_tol;
+  int max_inner;
+  unsigned epoch;
+};
+
+__device__ __forceinline__ unsigned long long gi_ld(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void gi_st(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// gicp_omp_impl.hpp:517-528 (Z * Y * X Euler order, f32), device edition of apply_state()
+__device__ void apply_state_dev(float* t, const double* x) {
+  const float cx = cosf((float)x[3]), sx = sinf((float)x[3]);
+  const float cy = cosf((float)x[4]), sy = sinf((float)x[4]);
+  const float cz = cosf((float)x[5]), sz = sinf((float)x[5]);
+  const float Rz[9] = {cz, -sz, 0, sz, cz, 0, 0, 0, 1}, Ry[9] = {cy, 0, sy, 0, 1, 0, -sy, 0, cy}, Rx[9] = {1, 0, 0, 0, cx, -sx, 0, sx, cx};
+  float A[9], R[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float a = 0;
+      for (int k = 0; k < 3; k++) a = __fadd_rn(a, __fmul_rn(Rz[i * 3 + k], Ry[k * 3 + j]));
+      A[i * 3 + j] = a;
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float a = 0;
+      for (int k = 0; k < 3; k++) a = __fadd_rn(a, __fmul_rn(A[i * 3 + k], Rx[k * 3 + j]));
+      R[i * 3 + j] = a;
+    }
+  // base = identity: R * I = R
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) t[r * 4 + c] = R[r * 3 + c];
+  t[3] = (float)x[0];
+  t[7] = (float)x[1];
+  t[11] = (float)x[2];
+}
+
+// gicp_omp_impl.hpp:125-177
+__device__ void r_derivative_dev(const double* x, const double* R, double* g) {
+  const double phi = x[3], theta = x[4], psi = x[5];
+  const double cphi = cos(phi), sphi = sin(phi), ctheta = cos(theta), stheta = sin(theta), cpsi = cos(psi), spsi = sin(psi);
+  const double dPhi[9] = {0, sphi * spsi + cphi * cpsi * stheta, cphi * spsi - cpsi * sphi * stheta,
+                          0, -cpsi * sphi + cphi * spsi * stheta, -cphi * cpsi - sphi * spsi * stheta,
+                          0, cphi * ctheta, -ctheta * sphi};
+  const double dTheta[9] = {-cpsi * stheta, cpsi * ctheta * sphi, cphi * cpsi * ctheta,
+                            -spsi * stheta, ctheta * sphi * spsi, cphi * ctheta * spsi,
+                            -ctheta, -sphi * stheta, -cphi * stheta};
+  const double dPsi[9] = {-ctheta * spsi, -cphi * cpsi - sphi * spsi * stheta, cpsi * sphi - cphi * spsi * stheta,
+                          cpsi * ctheta, -cphi * spsi + cpsi * sphi * stheta, sphi * spsi + cphi * cpsi * stheta,
+                          0, 0, 0};
+  double r3 = 0, r4 = 0, r5 = 0;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {  // matricesInnerProd (gicp_omp.h:316-326)
+      r3 += dPhi[j * 3 + i] * R[i * 3 + j];
+      r4 += dTheta[j * 3 + i] * R[i * 3 + j];
+      r5 += dPsi[j * 3 + i] * R[i * 3 + j];
+    }
+  g[3] = r3;
+  g[4] = r4;
+  g[5] = r5;
+}
+
+// the functor the controller CTA's BFGS drives: every thread of the CTA calls it with identical arguments
+struct GicpDeviceFunctor {
+  const GicpInnerLaunch* L;
+  double (*red)[K7_SLOTS];  // shared [16][16]
+  double* tot;              // shared [16]
+  int n_eval;
+  int round;                // evaluations published so far (identical in every thread)
+  int failed;
+
+  __device__ void evaluate(const double* x, int want_grad, double& f, double* g) {
+    GicpInnerWork* W = L->work;
+    const int tid = threadIdx.x;
+    float T[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    apply_state_dev(T, x);
+    // publish {payload, sequence}: thread k owns word k
+    if (tid < GI_CTL_WORDS) {
+      const unsigned payload = tid < 12 ? __float_as_uint(T[tid]) : (tid == 12 ? (unsigned)want_grad : (unsigned)GI_MODE_RUN);
+      const unsigned long long v = ((unsigned long long)(L->epoch * 65536u + (unsigned)round + 1u) << 32) | payload;
+#pragma unroll
+      for (int c = 0; c < GI_CTL_COPIES; c++) gi_st(&W->ctl[c][tid], v);
+    }
+    // fixed-order reduction of the evaluators' rows; the loads are the arrival poll; consumed words are re-armed
+    const int slot = tid & 15, part = tid >> 4;
+    double* buf = &W->rows[round & 1][0][0];
+    double s = 0;
+    const long long t0 = clock64();
+    for (int b = part; b < n_eval; b += 16) {
+      unsigned long long* w = reinterpret_cast<unsigned long long*>(buf + (size_t)b * K7_SLOTS + slot);
+      unsigned long long v = gi_ld(w);
+      while (v == GI_EMPTY && !failed) {
+        if (clock64() - t0 > GI_TIMEOUT_CYCLES) {
+          failed = 1;
+          W->error = 1;
+          break;
+        }
+        v = gi_ld(w);
+      }
+      s += __longlong_as_double((long long)v);
+      gi_st(w, GI_EMPTY);
+    }
+    __syncthreads();  // previous evaluation's readers of red/tot are done
+    red[part][slot] = s;
+    __syncthreads();
+    if (tid < K7_SLOTS) {
+      double t = 0;
+#pragma unroll
+      for (int q = 0; q < 16; q++) t += red[q][tid];
+      tot[tid] = t;
+    }
+    __threadfence();  // re-arming stores are performed before the next control words go out
+    __syncthreads();
+    failed = __syncthreads_or(failed);
+    round += 1;
+    const double m = L->m;
+    if (!want_grad) {
+      f = tot[0] / m;
+      return;
+    }
+    f = tot[1] / m;
+    double R[9];
+    for (int k = 0; k < 3; k++) g[k] = tot[2 + k] * (2.0 / m);
+    for (int k = 0; k < 9; k++) R[k] = tot[5 + k] * (2.0 / m);
+    r_derivative_dev(x, R, g);
+  }
+  __device__ double f(const double* x) {
+    double v;
+    evaluate(x, 0, v, nullptr);
+    return v;
+  }
+  __device__ void fdf(const double* x, double& fo, double* g) { evaluate(x, 1, fo, g); }
+  __device__ void df(const double* x, double* g) {
+    double fo;
+    evaluate(x, 1, fo, g);
+  }
+};
+
+__global__ void __launch_bounds__(GI_THREADS) gicp_inner_kernel(const __grid_constant__ GicpInnerLaunch L) {
+  GicpInnerWork* W = L.work;
+  const int tid = threadIdx.x;
+  const int n_eval = (int)gridDim.x - 1;
+  if ((int)blockIdx.x == n_eval) {  // ---- controller CTA: every thread runs the same BFGS ----
+    __shared__ double red[16][K7_SLOTS];
+    __shared__ double tot[K7_SLOTS];
+    GicpDeviceFunctor fn{&L, red, tot, n_eval, 0, 0};
+    Bfgs6T<GicpDeviceFunctor> bfgs(fn);
+    double x[6];
+    for (int k = 0; k < 6; k++) x[k] = L.x0[k];
+    int inner = 0;
+    int result = bfgs.minimizeInit(x);
+    result = BFGS_Running;
+    do {  // gicp_omp_impl.hpp:215-230
+      inner++;
+      result = bfgs.minimizeOneStep(x);
+      if (result) break;
+      result = bfgs.testGradient(L.gradient_tol);
+    } while (result == BFGS_Running && inner < L.max_inner && !fn.failed);
+    // tell the evaluators to leave
+    if (tid < GI_CTL_WORDS) {
+      const unsigned payload = tid == 13 ? (unsigned)GI_MODE_EXIT : 0u;
+      const unsigned long long v = ((unsigned long long)(L.epoch * 65536u + (unsigned)fn.round + 1u) << 32) | payload;
+#pragma unroll
+      for (int c = 0; c < GI_CTL_COPIES; c++) gi_st(&W->ctl[c][tid], v);
+    }
+    if (tid == 0) {
+      GicpInnerResult* r = L.result_host;
+      for (int k = 0; k < 6; k++) r->x[k] = x[k];
+      r->f = bfgs.f;
+      r->status = result;
+      r->inner = inner;
+      r->evaluations = fn.round;
+      r->error = fn.failed ? 1 : 0;
+      __threadfence_system();
+    }
+    return;
+  }
+  // ---- evaluator CTAs ----
+  __shared__ unsigned ctl[16];
+  __shared__ double sm[GI_THREADS / 32][K7_SLOTS];
+  __shared__ int abort_flag;
+  if (tid == 0) abort_flag = 0;
+  const int rank = (int)blockIdx.x;
+  const int chunk = (L.P.n + n_eval - 1) / n_eval;
+  const int i0 = rank * chunk, i1 = min(L.P.n, i0 + chunk);
+  const int lane = tid & 31, warp = tid >> 5;
+  __syncthreads();
+  for (int round = 0;; round++) {
+    if (tid < GI_CTL_WORDS) {
+      const unsigned long long* w = &W->ctl[rank % GI_CTL_COPIES][tid];
+      const unsigned want = L.epoch * 65536u + (unsigned)round + 1u;
+      const long long t0 = clock64();
+      unsigned long long v;
+      for (;;) {
+        v = gi_ld(w);
+        if ((unsigned)(v >> 32) == want) break;
+        if (clock64() - t0 > GI_TIMEOUT_CYCLES) {
+          W->error = 1;
+          abort_flag = 1;
+          break;
+        }
+      }
+      ctl[tid] = (unsigned)v;
+    }
+    __syncthreads();
+    if (abort_flag || ctl[13] != (unsigned)GI_MODE_RUN) break;
+    float T[12];
+#pragma unroll
+    for (int k = 0; k < 12; k++) T[k] = __uint_as_float(ctl[k]);
+    const int want_grad = (int)ctl[12];
+    double acc[14];
+#pragma unroll
+    for (int k = 0; k < 14; k++) acc[k] = 0.0;
+    for (int i = i0 + tid; i < i1; i += GI_THREADS) cost_point(L.P, T, want_grad, i, acc);
+#pragma unroll
+    for (int k = 0; k < 14; k++) {
+      double v = acc[k];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+      if (lane == 0) sm[warp][k] = v;
+    }
+    __syncthreads();
+    if (tid < K7_SLOTS) {
+      double t = 0;
+      if (tid < 14)
+#pragma unroll
+        for (int w = 0; w < GI_THREADS / 32; w++) t += sm[w][tid];
+      gi_st(reinterpret_cast<unsigned long long*>(&W->rows[round & 1][rank][tid]), (unsigned long long)__double_as_longlong(t));
+    }
+    __syncthreads();  // sm and ctl are reused by the next round
+  }
+}
+
+__global__ void gi_arm_kernel(unsigned long long* p, size_t n) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = GI_EMPTY;
+}
+
 }  // namespace
 
 void gicp_covariances(const NnGrid& grid, const float4* pts, size_t n, int k, double gicp_epsilon, double* d_cov6,
@@ -378,6 +656,49 @@ void GicpSolver::init(int device, cudaStream_t s) {
   B200_CUDA(cudaMemset(counter_.ptr, 0, 4 * sizeof(unsigned)));
   result_.ensure(K7_SLOTS);
   partials_.ensure((size_t)148 * 4 * K7_SLOTS);
+  cudaDeviceProp prop;
+  B200_CUDA(cudaGetDeviceProperties(&prop, device));
+  sm_count_ = prop.multiProcessorCount;
+  B200_CUDA(cudaMalloc(&d_inner_work_, sizeof(GicpInnerWork)));
+  B200_CUDA(cudaMemset(d_inner_work_, 0, sizeof(GicpInnerWork)));
+  gi_arm_kernel<<<64, 256>>>(reinterpret_cast<unsigned long long*>(&d_inner_work_->rows[0][0][0]), (size_t)2 * GI_MAX_CTAS * K7_SLOTS);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaDeviceSynchronize());
+  B200_CUDA(cudaMallocHost(&h_inner_result_, sizeof(GicpInnerResult)));
+}
+
+int GicpSolver::inner_loop_device(double* x, const GicpConfig& cfg, int* inner_iterations) {
+  GicpInnerLaunch L{};
+  L.P.moved = moved_.ptr;
+  L.P.target = target_;
+  L.P.corr = corr_.ptr;
+  L.P.maha = maha_.ptr;
+  L.P.n = (int)n_source_;
+  L.work = d_inner_work_;
+  L.result_host = h_inner_result_;
+  for (int k = 0; k < 6; k++) L.x0[k] = x[k];
+  L.m = (double)last_m_;
+  L.gradient_tol = cfg.gradient_tol;
+  L.max_inner = cfg.max_inner_iterations;
+  L.epoch = inner_epoch_++;
+  h_inner_result_->error = 3;  // "the kernel never wrote a result"
+  const int max_ctas = std::min(sm_count_, GI_MAX_CTAS);
+  const int n_eval = std::max(1, std::min((int)((n_source_ + GI_THREADS - 1) / GI_THREADS), max_ctas - 1));
+  void* args[] = {&L};
+  B200_CUDA(cudaLaunchCooperativeKernel((const void*)gicp_inner_kernel, dim3(n_eval + 1), dim3(GI_THREADS), args, 0, stream_));
+  B200_CUDA(cudaStreamSynchronize(stream_));
+  launches += 1;
+  const GicpInnerResult& r = *h_inner_result_;
+  if (r.error != 0) {  // watchdog (or the kernel never ran): re-arm the rows and report
+    gi_arm_kernel<<<64, 256, 0, stream_>>>(reinterpret_cast<unsigned long long*>(&d_inner_work_->rows[0][0][0]), (size_t)2 * GI_MAX_CTAS * K7_SLOTS);
+    B200_CUDA(cudaMemsetAsync(&d_inner_work_->error, 0, sizeof(unsigned), stream_));
+    B200_CUDA(cudaStreamSynchronize(stream_));
+    throw CudaError("GICP inner-loop kernel watchdog fired");
+  }
+  for (int k = 0; k < 6; k++) x[k] = r.x[k];
+  evaluations_ += r.evaluations;
+  *inner_iterations = r.inner;
+  return r.status;
 }
 
 size_t GicpSolver::covariances(int which, std::vector<double>& out, cudaStream_t s) {
@@ -534,16 +855,21 @@ GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, s
       double f;
       fn.fdf(xx, f, gg);
     };
-    Bfgs6 bfgs(fn);
     int inner = 0;
-    int result = bfgs.minimizeInit(x);
-    result = BFGS_Running;
-    do {
-      inner++;
-      result = bfgs.minimizeOneStep(x);
-      if (result) break;
-      result = bfgs.testGradient(cfg.gradient_tol);
-    } while (result == BFGS_Running && inner < cfg.max_inner_iterations);
+    int result;
+    if (device_bfgs) {
+      result = inner_loop_device(x, cfg, &inner);
+    } else {
+      Bfgs6 bfgs(fn);
+      result = bfgs.minimizeInit(x);
+      result = BFGS_Running;
+      do {
+        inner++;
+        result = bfgs.minimizeOneStep(x);
+        if (result) break;
+        result = bfgs.testGradient(cfg.gradient_tol);
+      } while (result == BFGS_Running && inner < cfg.max_inner_iterations);
+    }
     if (!(result == BFGS_NoProgress || result == BFGS_Success || inner == cfg.max_inner_iterations)) break;  // throws in the reference
     set_identity16(transformation);
     apply_state(transformation, x);

@@ -23,6 +23,13 @@ struct GicpOutcome {
   int converged, iterations, evaluations;
 };
 
+struct GicpInnerWork;     // device work area of the persistent inner-loop kernel (gicp.cu)
+struct GicpInnerResult {  // written by the kernel into pinned host memory
+  double x[6];
+  double f;
+  int status, inner, evaluations, error;
+};
+
 class GicpSolver {
  public:
   void init(int device, cudaStream_t s);
@@ -37,9 +44,18 @@ class GicpSolver {
   size_t covariances(int which, std::vector<double>& out, cudaStream_t s);
   int last_correspondences() const { return last_m_; }
   int launches = 0;
+  // true: estimateRigidTransformationBFGS runs as ONE persistent cooperative kernel per outer iteration (BFGS on the
+  // device); false: host-side BFGS, one K7 launch + synchronisation per functor evaluation
+  bool device_bfgs = false;
 
  private:
   void fdf(const float* T_rowmajor16, bool want_grad, double* f, double* g_t3, double* R9);
+  // returns the BFGS status; x is updated in place
+  int inner_loop_device(double* x, const GicpConfig& cfg, int* inner_iterations);
+  GicpInnerWork* d_inner_work_ = nullptr;
+  GicpInnerResult* h_inner_result_ = nullptr;  // pinned
+  unsigned inner_epoch_ = 0;
+  int sm_count_ = 0;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;
   bool target_cov_valid_ = false, source_cov_valid_ = false, source_grid_valid_ = false;
