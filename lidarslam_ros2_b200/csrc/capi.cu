@@ -258,7 +258,7 @@ int b200reg_create(int kind, int device, b200reg_t* out) {
     h->solver.timing_enabled = getenv("B200REG_TIMING") != nullptr;
     h->solver.scalar_controller = getenv("B200REG_SCALAR_CTL") != nullptr;
     h->solver.plain_launch = getenv("B200REG_PLAIN_LAUNCH") != nullptr;
-    h->gicp_solver.device_bfgs = getenv("B200REG_GICP_DEVICE_BFGS") != nullptr;
+    h->gicp_solver.device_bfgs = getenv("B200REG_GICP_HOST_BFGS") == nullptr;  // developer switch: host-driven BFGS
     h->gicp_solver.init(device, h->stream);
     if (kind == B200REG_GICP) {
       h->corr_dist = 5.0;  // gicp_omp.h:119

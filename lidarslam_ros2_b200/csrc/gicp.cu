@@ -375,7 +375,7 @@ void r_derivative(const double* x, const double* R, double* g) {
 // control words, self-validating partial rows double-buffered by round parity.
 // =====================================================================================================================
 constexpr int GI_THREADS = 256;
-constexpr int GI_MAX_CTAS = 256;
+constexpr int GI_MAX_CTAS = 160;  // one CTA per SM at most (148 on B200); rows per controller thread = GI_MAX_CTAS / 16
 constexpr int GI_CTL_WORDS = 14;  // T[12] (float bits), want_grad, mode
 constexpr int GI_CTL_COPIES = 4;
 constexpr unsigned long long GI_EMPTY = 0xFFF8DEADFFF8DEADull;
@@ -488,21 +488,40 @@ struct GicpDeviceFunctor {
     // fixed-order reduction of the evaluators' rows; the loads are the arrival poll; consumed words are re-armed
     const int slot = tid & 15, part = tid >> 4;
     double* buf = &W->rows[round & 1][0][0];
-    double s = 0;
-    const long long t0 = clock64();
-    for (int b = part; b < n_eval; b += 16) {
-      unsigned long long* w = reinterpret_cast<unsigned long long*>(buf + (size_t)b * K7_SLOTS + slot);
-      unsigned long long v = gi_ld(w);
-      while (v == GI_EMPTY && !failed) {
-        if (clock64() - t0 > GI_TIMEOUT_CYCLES) {
-          failed = 1;
-          W->error = 1;
-          break;
-        }
-        v = gi_ld(w);
+    // thread (part, slot) owns words slot of rows part, part + 16, ...: all of them are loaded at once (one L2 round trip),
+    // the ones that are still empty are re-loaded
+    constexpr int OWN = GI_MAX_CTAS / 16;
+    unsigned long long v[OWN];
+    unsigned pend = 0;
+#pragma unroll
+    for (int k = 0; k < OWN; k++) {
+      const int b = part + 16 * k;
+      v[k] = 0ull;  // bits of +0.0
+      if (b < n_eval) {
+        v[k] = gi_ld(reinterpret_cast<const unsigned long long*>(buf + (size_t)b * K7_SLOTS + slot));
+        if (v[k] == GI_EMPTY) pend |= 1u << k;
       }
-      s += __longlong_as_double((long long)v);
-      gi_st(w, GI_EMPTY);
+    }
+    const long long t0 = clock64();
+    while (pend && !failed) {
+#pragma unroll
+      for (int k = 0; k < OWN; k++) {
+        if ((pend >> k) & 1u) {
+          v[k] = gi_ld(reinterpret_cast<const unsigned long long*>(buf + (size_t)(part + 16 * k) * K7_SLOTS + slot));
+          if (v[k] != GI_EMPTY) pend &= ~(1u << k);
+        }
+      }
+      if (clock64() - t0 > GI_TIMEOUT_CYCLES) {
+        failed = 1;
+        W->error = 1;
+      }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < OWN; k++) {
+      s += __longlong_as_double((long long)v[k]);  // fixed order; rows beyond n_eval contribute +0.0
+      const int b = part + 16 * k;
+      if (b < n_eval) gi_st(reinterpret_cast<unsigned long long*>(buf + (size_t)b * K7_SLOTS + slot), GI_EMPTY);
     }
     __syncthreads();  // previous evaluation's readers of red/tot are done
     red[part][slot] = s;

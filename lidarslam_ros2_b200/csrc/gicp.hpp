@@ -46,7 +46,7 @@ class GicpSolver {
   int launches = 0;
   // true: estimateRigidTransformationBFGS runs as ONE persistent cooperative kernel per outer iteration (BFGS on the
   // device); false: host-side BFGS, one K7 launch + synchronisation per functor evaluation
-  bool device_bfgs = false;
+  bool device_bfgs = true;
 
  private:
   void fdf(const float* T_rowmajor16, bool want_grad, double* f, double* g_t3, double* R9);
