@@ -3,6 +3,7 @@ all-gather of the loop-closure sweep on a world_size-2 gloo group."""
 import os
 import re
 import socket
+import sys
 
 import numpy as np
 import pytest
@@ -158,3 +159,23 @@ def test_cpp_adapter_compiles_and_fails_loudly_without_gpu():
         assert rc.returncode == 0, rc.stdout
     else:
         assert rc.returncode == 3 and "no CUDA device" in rc.stdout, rc.stdout
+
+
+def test_bench_reference_arm_contract():
+    """bench.py --impl reference: rank 0 prints ONE JSON line with "impl": "reference" (the CPU restatement timed on the host
+    cores), every other rank exits 0 without work or output."""
+    import json
+    import subprocess
+
+    env = dict(os.environ, RANK="1", LOCAL_RANK="1", WORLD_SIZE="2")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                        "--warmup", "1", "--workload", "c1"], capture_output=True, text=True, env=env, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""
+    env = dict(os.environ, RANK="0", LOCAL_RANK="0", WORLD_SIZE="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1",
+                        "--workload", "c1"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "registrations/s"
+    assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["value"] == line["value"]
+    assert line["steps"] == 2 and line["higher_is_better"] is True
