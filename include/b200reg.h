@@ -183,6 +183,22 @@ int b200sm_get_targeted(b200sm_t s, float* out_xyzi, size_t capacity, size_t* n)
 int b200sm_get_submap(b200sm_t s, size_t index, float* out_xyzi, size_t capacity, size_t* n, double* pose_colmajor16,
                       double* distance);
 int b200sm_get_filtered_scan(b200sm_t s, float* out_xyzi, size_t capacity, size_t* n);
+/* GraphBasedSlamComponent::searchLoop (gbs.cpp:144-258) on the session's submaps, device-resident: the newest submap is the
+ * source; among the older submaps with (travelled-distance gap > distance_loop_closure) and (position distance <
+ * range_of_searching_loop_closure) the closest one, id_min, is the candidate; target = VoxelGrid(voxel_leaf_size) of the
+ * submaps id_min +- search_submap_num, each moved by its pose cast to float; align() without guess, getFitnessScore();
+ * accepted iff fitness < threshold_loop_closure_score, then relative_pose = from^-1 * (final * init) as in the LoopEdge.
+ * `reg` is the backend's registration object (gbs.cpp:47-64 sets its parameters). 4x4 matrices are column-major.       */
+typedef struct b200sm_loop_result {
+  int is_candidate, id_min, accepted, pad;
+  double min_dist, fitness;
+  float final_T[16];
+  double relative_pose[16];
+  size_t n_source, n_target;
+} b200sm_loop_result;
+int b200sm_search_loop(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double threshold_loop_closure_score,
+                       double distance_loop_closure, double range_of_searching_loop_closure, int search_submap_num,
+                       b200sm_loop_result* out);
 typedef struct b200sm_stats {
   size_t n_scan, n_filtered, n_targeted, n_submaps;
   int kernel_launches;

@@ -35,8 +35,14 @@ SYMBOLS = [
     "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
     "b200sm_create", "b200sm_destroy", "b200sm_last_error", "b200sm_set_params", "b200sm_set_initial_pose",
     "b200sm_set_scan", "b200sm_update_map", "b200sm_receive_cloud", "b200sm_num_submaps", "b200sm_get_targeted",
-    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats",
+    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats", "b200sm_search_loop",
 ]
+
+
+class SmLoopResult(C.Structure):
+    _fields_ = [("is_candidate", C.c_int), ("id_min", C.c_int), ("accepted", C.c_int), ("pad", C.c_int),
+                ("min_dist", C.c_double), ("fitness", C.c_double), ("final_T", C.c_float * 16),
+                ("relative_pose", C.c_double * 16), ("n_source", C.c_size_t), ("n_target", C.c_size_t)]
 
 
 class SmStats(C.Structure):
@@ -130,6 +136,7 @@ def lib() -> C.CDLL:
     L.b200sm_get_submap.argtypes = [vp, sz, vp, sz, C.POINTER(sz), vp, C.POINTER(d)]
     L.b200sm_get_filtered_scan.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.b200sm_get_stats.argtypes = [vp, C.POINTER(SmStats)]
+    L.b200sm_search_loop.argtypes = [vp, vp, f, d, d, d, i, C.POINTER(SmLoopResult)]
     for name in SYMBOLS:
         fn = getattr(L, name)
         if name not in ("b200reg_last_error", "b200sm_last_error", "b200sm_destroy"):

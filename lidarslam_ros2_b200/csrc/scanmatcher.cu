@@ -134,6 +134,7 @@ struct b200sm_session {
   std::vector<std::unique_ptr<Submap>> submaps;
   DeviceBuffer<float4> targeted;
   size_t n_targeted = 0;
+  DeviceBuffer<float4> loop_src, loop_tgt;  // search_loop scratch
   int launches = 0;
   // frontend bookkeeping (ScanMatcherComponent members)
   bool initial_cloud_received = false;
@@ -395,6 +396,13 @@ int b200sm_update_map(b200sm_t s, b200reg_t reg, const float* final_T_colmajor16
     float T[16];
     for (int r = 0; r < 4; r++)
       for (int c = 0; c < 4; c++) T[r * 4 + c] = final_T_colmajor16[c * 4 + r];
+    if (!s->submaps.empty()) {  // updateMap :471: latest_distance_ += trans_ (distance travelled since the last submap)
+      const double dx = position3[0] - s->previous_position[0], dy = position3[1] - s->previous_position[1],
+                   dz = position3[2] - s->previous_position[2];
+      s->trans = std::sqrt(dx * dx + dy * dy + dz * dz);
+      s->latest_distance += s->trans;
+    }
+    for (int k = 0; k < 3; k++) s->previous_position[k] = position3[k];
     int rc = update_map(s, T, position3, quat_xyzw);
     if (rc == B200REG_OK && adopt_now && reg) {
       int kind = B200REG_NDT;
@@ -499,6 +507,111 @@ int b200sm_get_submap(b200sm_t s, size_t index, float* out_xyzi, size_t capacity
 int b200sm_get_filtered_scan(b200sm_t s, float* out_xyzi, size_t capacity, size_t* n) {
   if (!s) return B200REG_ERR_ARG;
   return sm_guarded(s, [&]() { return read_back(s, s->vg_input.out.ptr, s->n_filtered, out_xyzi, capacity, n); });
+}
+
+// GraphBasedSlamComponent::searchLoop (graph_based_slam_component.cpp:144-258) over the session's own submaps — the map
+// array the frontend publishes is the backend's input, here it never left the device.
+int b200sm_search_loop(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double threshold_loop_closure_score,
+                       double distance_loop_closure, double range_of_searching_loop_closure, int search_submap_num,
+                       b200sm_loop_result* out) {
+  if (!s || !reg || !out || !(voxel_leaf_size > 0) || search_submap_num < 0) return B200REG_ERR_ARG;
+  return sm_guarded(s, [&]() {
+    std::memset(out, 0, sizeof(*out));
+    out->id_min = -1;
+    const int n_sub = (int)s->submaps.size();
+    if (n_sub == 0) return (int)B200REG_OK;
+    const Submap& latest = *s->submaps[n_sub - 1];
+    // candidate = older submap reached again: travelled distance apart, position close; the closest one wins (:187-204)
+    double min_dist = 1.7976931348623157e308;
+    int id_min = 0;
+    bool is_candidate = false;
+    for (int i = 0; i < n_sub; i++) {
+      const Submap& sub = *s->submaps[i];
+      const double dx = latest.pose[3] - sub.pose[3], dy = latest.pose[7] - sub.pose[7], dz = latest.pose[11] - sub.pose[11];
+      const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+      if (latest.distance - sub.distance > distance_loop_closure && dist < range_of_searching_loop_closure) {
+        is_candidate = true;
+        if (dist < min_dist) {
+          id_min = i;
+          min_dist = dist;
+        }
+      }
+    }
+    out->is_candidate = is_candidate ? 1 : 0;
+    if (!is_candidate) return (int)B200REG_OK;
+    out->id_min = id_min;
+    out->min_dist = min_dist;
+    auto pose_f32 = [](const Submap& sub) {  // affine.matrix().cast<float>()
+      Mat34f T;
+      for (int k = 0; k < 12; k++) T.m[k] = (float)sub.pose[k];
+      return T;
+    };
+    // source = latest submap in the map frame (:165-176)
+    s->loop_src.ensure(std::max<size_t>(latest.n, 1));
+    if (latest.n) transform_f32_kernel<<<(int)((latest.n + 255) / 256), 256, 0, s->stream>>>(latest.cloud, latest.n, pose_f32(latest), s->loop_src.ptr);
+    // target = VoxelGrid(voxel_leaf_size) of the submaps id_min - search_submap_num .. id_min + search_submap_num (:206-225).
+    // The reference does not test the upper index (undefined behaviour when the window runs past the newest submap);
+    // here indices beyond the array are skipped like the negative ones.
+    size_t total = 0;
+    for (int j = 0; j <= 2 * search_submap_num; j++) {
+      const int idx = id_min + j - search_submap_num;
+      if (idx < 0 || idx >= n_sub) continue;
+      total += s->submaps[idx]->n;
+    }
+    s->loop_tgt.ensure(std::max<size_t>(total, 1));
+    size_t off = 0;
+    for (int j = 0; j <= 2 * search_submap_num; j++) {
+      const int idx = id_min + j - search_submap_num;
+      if (idx < 0 || idx >= n_sub) continue;
+      const Submap& sub = *s->submaps[idx];
+      if (sub.n) transform_f32_kernel<<<(int)((sub.n + 255) / 256), 256, 0, s->stream>>>(sub.cloud, sub.n, pose_f32(sub), s->loop_tgt.ptr + off);
+      off += sub.n;
+      s->launches += 1;
+    }
+    B200_CUDA(cudaGetLastError());
+    size_t m = 0;
+    const float4* tgt = filter_on_device(s, s->vg_target, s->loop_tgt.ptr, total, voxel_leaf_size, &m);
+    if (latest.n == 0 || m == 0) return sm_fail(s, B200REG_ERR_NO_TARGET, "search_loop: empty source or target");
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    int rc = b200reg_set_input_source_device(reg, s->loop_src.ptr, latest.n);
+    if (rc == B200REG_OK) rc = b200reg_set_input_target_device(reg, tgt, m);
+    float fin[16];
+    if (rc == B200REG_OK) rc = b200reg_align(reg, nullptr, fin);  // :229, no guess
+    double fitness = 0;
+    if (rc == B200REG_OK) rc = b200reg_get_fitness_score(reg, 1.7976931348623157e308, &fitness);  // :230
+    if (rc != B200REG_OK) {
+      s->err = std::string("search_loop: ") + b200reg_last_error(reg);
+      return rc;
+    }
+    out->n_source = latest.n;
+    out->n_target = m;
+    out->fitness = fitness;
+    std::memcpy(out->final_T, fin, sizeof(fin));
+    if (fitness < threshold_loop_closure_score) {  // :232-246: loop edge (id_min, newest), relative pose from^-1 * (final * init)
+      out->accepted = 1;
+      double F[16], to[16], rel[16];
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) F[r * 4 + c] = (double)fin[c * 4 + r];
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+          double a = 0;
+          for (int k = 0; k < 4; k++) a += F[r * 4 + k] * latest.pose[k * 4 + c];
+          to[r * 4 + c] = a;
+        }
+      const double* fr = s->submaps[id_min]->pose;  // Isometry3d::inverse(): R^T, -R^T t
+      double inv[16] = {fr[0], fr[4], fr[8], 0, fr[1], fr[5], fr[9], 0, fr[2], fr[6], fr[10], 0, 0, 0, 0, 1};
+      for (int r = 0; r < 3; r++) inv[r * 4 + 3] = -(inv[r * 4 + 0] * fr[3] + inv[r * 4 + 1] * fr[7] + inv[r * 4 + 2] * fr[11]);
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) {
+          double a = 0;
+          for (int k = 0; k < 4; k++) a += inv[r * 4 + k] * to[k * 4 + c];
+          rel[r * 4 + c] = a;
+        }
+      for (int r = 0; r < 4; r++)
+        for (int c = 0; c < 4; c++) out->relative_pose[c * 4 + r] = rel[r * 4 + c];
+    }
+    return (int)B200REG_OK;
+  });
 }
 
 int b200sm_get_stats(b200sm_t s, b200sm_stats* out) {

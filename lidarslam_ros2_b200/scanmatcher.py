@@ -84,6 +84,24 @@ class ScanMatcher:
         q = np.ascontiguousarray(quat_xyzw, dtype=np.float64)
         self._check(self._lib.b200sm_update_map(self._h, self.registration._h, _ptr(T), _ptr(p), _ptr(q), int(adopt_now)))
 
+    def searchLoop(self, registration, voxel_leaf_size: float = 0.2, threshold_loop_closure_score: float = 1.0,
+                   distance_loop_closure: float = 20.0, range_of_searching_loop_closure: float = 20.0,
+                   search_submap_num: int = 3) -> dict:
+        """GraphBasedSlamComponent::searchLoop (graph_based_slam_component.cpp:144-258) over the session's device-resident
+        submaps; `registration` is the backend's engine (see backend_registration()). Parameter names and defaults are the
+        node's (gbs.cpp:23-39)."""
+        r = _capi.SmLoopResult()
+        self._check(self._lib.b200sm_search_loop(self._h, registration._h, float(voxel_leaf_size), float(threshold_loop_closure_score),
+                                                 float(distance_loop_closure), float(range_of_searching_loop_closure),
+                                                 int(search_submap_num), C.byref(r)))
+        out = {"is_candidate": bool(r.is_candidate), "id_min": int(r.id_min), "accepted": bool(r.accepted)}
+        if r.is_candidate:
+            out.update(min_dist=float(r.min_dist), fitness=float(r.fitness), n_source=int(r.n_source), n_target=int(r.n_target),
+                       final=np.array(r.final_T, dtype=np.float32).reshape(4, 4).T.copy())
+            if r.accepted:
+                out["relative_pose"] = np.array(r.relative_pose, dtype=np.float64).reshape(4, 4).T.copy()
+        return out
+
     # ---- read-back ----
     def stats(self) -> dict:
         st = _capi.SmStats()
@@ -117,3 +135,25 @@ class ScanMatcher:
         out = np.empty((n.value, 4), dtype=np.float32)
         self._check(self._lib.b200sm_get_submap(self._h, index, _ptr(out), n.value, C.byref(n), _ptr(pose), C.byref(dist)))
         return out, pose.reshape(4, 4).T.copy(), float(dist.value)
+
+
+def backend_registration(registration_method: str = "NDT", ndt_resolution: float = 5.0, ndt_num_threads: int = 0, device: int = 0):
+    """The backend node's registration object (graph_based_slam_component.cpp:44-70)."""
+    if registration_method == "NDT":
+        reg = NormalDistributionsTransform(device=device)
+        reg.setMaximumIterations(100)
+        reg.setResolution(ndt_resolution)
+        reg.setTransformationEpsilon(0.01)
+        reg.setNeighborhoodSearchMethod(2)  # pclomp::DIRECT7
+        if ndt_num_threads > 0:
+            reg.setNumThreads(ndt_num_threads)
+        return reg
+    if registration_method == "GICP":
+        reg = GeneralizedIterativeClosestPoint(device=device)
+        reg.setMaxCorrespondenceDistance(30)
+        reg.setMaximumIterations(100)
+        reg.setTransformationEpsilon(1e-8)
+        reg.setEuclideanFitnessEpsilon(1e-6)
+        reg.setRANSACIterations(0)
+        return reg
+    raise ValueError("registration_method must be NDT or GICP")

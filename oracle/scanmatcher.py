@@ -128,6 +128,62 @@ class ScanMatcher:
         self.submaps.append((filtered, pose_matrix(position, quat), self.latest_distance))
         self.pending = True
 
+    def update_map_external(self, cloud, final_T, position, quat):
+        """The caller-driven form (b200sm_update_map): advances latest_distance_ by the distance to the previous submap
+        position (updateMap :471) and updates the map."""
+        position = np.asarray(position, dtype=np.float64)
+        if self.submaps:
+            self.trans = float(np.sqrt(np.sum((position - self.previous_position) ** 2)))
+            self.latest_distance += self.trans
+        self.previous_position = position.copy()
+        c = np.ascontiguousarray(cloud, dtype=np.float32)
+        if c.shape[1] < 4:
+            c = np.concatenate([c[:, :3], np.zeros((len(c), 1), dtype=np.float32)], axis=1)
+        self.update_map(c, final_T, position, quat)
+
+    def search_loop(self, reg, voxel_leaf_size=0.2, threshold_loop_closure_score=1.0, distance_loop_closure=20.0,
+                    range_of_searching_loop_closure=20.0, search_submap_num=3):
+        """GraphBasedSlamComponent::searchLoop (graph_based_slam_component.cpp:144-258) over this frontend's submaps.
+        `reg` is the backend's registration oracle (gbs.cpp:47-64). Returns a dict like b200sm_loop_result."""
+        out = {"is_candidate": False, "id_min": -1, "accepted": False}
+        n_sub = len(self.submaps)
+        if n_sub == 0:
+            return out
+        lc, lM, ldist = self.submaps[-1]
+        min_dist, id_min = np.finfo(np.float64).max, 0
+        for i, (c, M, dist_i) in enumerate(self.submaps):  # :187-204
+            dist = float(np.sqrt(np.sum((lM[:3, 3] - M[:3, 3]) ** 2)))
+            if ldist - dist_i > distance_loop_closure and dist < range_of_searching_loop_closure:
+                out["is_candidate"] = True
+                if dist < min_dist:
+                    id_min, min_dist = i, dist
+        if not out["is_candidate"]:
+            return out
+        out["id_min"], out["min_dist"] = id_min, min_dist
+        src = transform_f32(lc, lM.astype(np.float32))  # :165-176
+        parts = []
+        for j in range(2 * search_submap_num + 1):  # :207-221 (indices past the newest submap: skipped, see b200reg.h)
+            idx = id_min + j - search_submap_num
+            if idx < 0 or idx >= n_sub:
+                continue
+            c, M, _ = self.submaps[idx]
+            parts.append(transform_f32(c, M.astype(np.float32)))
+        tgt = oracle.voxelgrid(np.concatenate(parts, axis=0), voxel_leaf_size)  # :223-225
+        reg.set_source(src[:, :3])
+        reg.set_target(tgt[:, :3])
+        final = np.asarray(reg.align(), dtype=np.float32)  # :229
+        fitness = reg.fitness()  # :230
+        out.update(fitness=fitness, final=final, n_source=len(src), n_target=len(tgt))
+        if fitness < threshold_loop_closure_score:  # :232-246
+            out["accepted"] = True
+            to = final.astype(np.float64) @ lM
+            fr = self.submaps[id_min][1]
+            inv = np.eye(4)
+            inv[:3, :3] = fr[:3, :3].T
+            inv[:3, 3] = -fr[:3, :3].T @ fr[:3, 3]
+            out["relative_pose"] = inv @ to
+        return out
+
     def _adopt(self, gicp_filter: bool):
         if not self.pending:
             return

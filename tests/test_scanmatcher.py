@@ -114,3 +114,65 @@ def test_update_map_bitwise_given_the_same_inputs():
         assert np.array_equal(np.isfinite(tg), np.isfinite(to))
         c, M, _ = g.submap(k)
         assert len(c) == m and np.array_equal(M, o.submaps[k][1])
+
+
+# ---------------------------------------------------------------- loop search (backend node, gbs.cpp:144-258)
+def _out_and_back(n_out=5, step=2.0, rings=16, azimuths=300):
+    """Scans at ground-truth poses: n_out submaps down the canyon, then back over the same ground (0.3 m to the side)."""
+    scene = synth.make_scene()
+    xs = [step * k for k in range(n_out)] + [step * k for k in range(n_out - 2, -1, -1)]
+    ys = [0.0] * n_out + [0.3] * (n_out - 1)
+    S0 = synth.sensor_pose(synth.pose_matrix((0, 0, 0), (0, 0, 0)), -40.0)
+    for k, (x, y) in enumerate(zip(xs, ys)):
+        Sk = synth.sensor_pose(synth.pose_matrix((x, y, 0.0), (0.0, 0.0, 0.01 * k)), -40.0)
+        yield synth.make_scan(scene, rings, azimuths, Sk, stream=8800 + k), np.linalg.inv(S0) @ Sk
+
+
+def test_oracle_search_loop_finds_the_revisit():
+    o = osm.ScanMatcher(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.3, num_targeted_cloud=3, num_threads=8)
+    for scan, T in _out_and_back():
+        o.update_map_external(scan, T.astype(np.float32), T[:3, 3], osm.quat_from_matrix(T[:3, :3]))
+    assert len(o.submaps) == 9 and abs(o.submaps[-1][2] - 16.0) < 0.5
+    reg = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7, num_threads=8)
+    far = o.search_loop(reg, voxel_leaf_size=0.3, distance_loop_closure=50.0, range_of_searching_loop_closure=1.0, search_submap_num=1)
+    assert not far["is_candidate"] and far["id_min"] == -1  # never 50 m apart along the path
+    r = o.search_loop(reg, voxel_leaf_size=0.3, distance_loop_closure=5.0, range_of_searching_loop_closure=1.0, search_submap_num=1)
+    assert r["is_candidate"] and r["id_min"] == 0 and r["accepted"], r
+    assert r["fitness"] < 1.0 and abs(r["min_dist"] - 0.3) < 1e-6
+    # poses are ground truth, so the registration correction is small and the edge is the true relative pose
+    M0, ML = o.submaps[0][1], o.submaps[-1][1]
+    dt, dr = synth.pose_error(r["relative_pose"], np.linalg.inv(M0) @ ML)
+    assert dt < 0.3 and dr < 0.02, (dt, dr)
+
+
+@pytest.mark.gpu
+def test_search_loop_parity():
+    from lidarslam_ros2_b200.scanmatcher import ScanMatcher, backend_registration
+
+    kw = dict(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.3, num_targeted_cloud=3)
+    g = ScanMatcher(**kw)
+    o = osm.ScanMatcher(num_threads=oracle.max_threads(), **kw)
+    for scan, T in _out_and_back():
+        q = osm.quat_from_matrix(T[:3, :3])
+        g.setScan(scan)
+        g.updateMap(T.astype(np.float32), T[:3, 3], q, adopt_now=False)
+        o.update_map_external(scan, T.astype(np.float32), T[:3, 3], q)
+    greg = backend_registration("NDT", ndt_resolution=2.0)
+    oreg = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7,
+                      num_threads=oracle.max_threads())
+    args = dict(voxel_leaf_size=0.3, distance_loop_closure=5.0, range_of_searching_loop_closure=1.0, search_submap_num=1)
+    rg, ro = g.searchLoop(greg, **args), o.search_loop(oreg, **args)
+    assert rg["is_candidate"] == ro["is_candidate"] and rg["id_min"] == ro["id_min"] == 0
+    assert rg["accepted"] == ro["accepted"] is True
+    assert rg["n_source"] == ro["n_source"]
+    # the target is a VoxelGrid of transformed VoxelGrid centroids: a centroid that differs in its last float bit between the
+    # two sides may fall into the neighbouring leaf
+    assert abs(rg["n_target"] - ro["n_target"]) <= 4
+    assert abs(rg["min_dist"] - ro["min_dist"]) < 1e-9
+    dt, dr = synth.pose_error(rg["final"], ro["final"])
+    assert dt < 1e-3 and dr < 1e-3, (dt, dr)
+    assert abs(rg["fitness"] - ro["fitness"]) < 1e-3 * max(1.0, ro["fitness"])
+    dt, dr = synth.pose_error(rg["relative_pose"], ro["relative_pose"])
+    assert dt < 2e-3 and dr < 1e-3
+    none = g.searchLoop(greg, voxel_leaf_size=0.3, distance_loop_closure=50.0, range_of_searching_loop_closure=1.0, search_submap_num=1)
+    assert not none["is_candidate"] and none["id_min"] == -1
