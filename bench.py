@@ -429,6 +429,28 @@ def run_c4(args, rank, local_rank, world, m):
             "mean_fitness": float(res["fitness"].mean()),
             "pose_error_vs_truth_first4": [[float(a), float(b)] for a, b in errs],
         }
+        try:  # the reference's CPU path on a bounded sample of the same pairs (rank 0's first two)
+            import oracle
+
+            oracle.build()
+            o = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7,
+                           num_threads=oracle.max_threads())
+            t_cpu, n_cpu, dmax = 0.0, 0, 0.0
+            for i in mine[:2]:
+                c0 = time.perf_counter()
+                o.set_target(data[i][1])
+                o.set_source(data[i][0])
+                To = o.align()
+                o.fitness()
+                t_cpu += time.perf_counter() - c0
+                n_cpu += 1
+                k = int(np.where(res["index"] == i)[0][0])
+                dmax = max(dmax, synth.pose_error(res["pose"][k], To)[0])
+            line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "registrations/s", "cores": oracle.max_threads(), "kind": "port",
+                                    "sample": f"{n_cpu} pairs (setInputTarget + setInputSource + align + getFitnessScore)",
+                                    "pose_parity_max_m": dmax}
+        except Exception as e:  # the GPU line must not depend on the CPU leg
+            line["cpu_baseline"] = {"value": None, "error": str(e)}
         print(json.dumps(line), flush=True)
 
 
