@@ -179,3 +179,16 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["value"] > 0 and line["unit"] == "registrations/s"
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["value"] == line["value"]
     assert line["steps"] == 2 and line["higher_is_better"] is True
+
+
+def test_abi_header_is_plain_c():
+    """include/b200reg.h must be consumable by a C compiler (cgo / JNI / ctypes-style bindings): C99, no C++ constructs."""
+    import subprocess
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "hdr.c")
+        with open(src, "w") as f:
+            f.write('#include "b200reg.h"\nint main(void){b200reg_stats s; b200sm_stats t; b200sm_loop_result r; (void)s; (void)t; (void)r; return 0;}\n')
+        subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+                               "-fsyntax-only", src])
