@@ -14,6 +14,7 @@
 #pragma once
 #include <array>
 #include <cfloat>
+#include <limits>
 #include <cstddef>
 #include <memory>
 #include <stdexcept>

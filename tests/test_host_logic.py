@@ -192,3 +192,23 @@ def test_abi_header_is_plain_c():
             f.write('#include "b200reg.h"\nint main(void){b200reg_stats s; b200sm_stats t; b200sm_loop_result r; (void)s; (void)t; (void)r; return 0;}\n')
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
                                "-fsyntax-only", src])
+
+
+def test_cpp_adapter_pcl_mode_type_checks():
+    """include/b200reg_pcl.hpp compiled with -DB200REG_WITH_PCL against a PCL-1.12-shaped stub (tests/cpp/fake_pcl): the
+    classes must derive from pcl::Registration, override its virtuals and be assignable to the nodes' `registration_` pointer
+    (INTEGRATION.md section 2). Without a GPU the engine refuses to construct (exit code 3)."""
+    import subprocess
+
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = os.path.join(ROOT, "tests", "cpp", "adapter_pcl_mode")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-DB200REG_WITH_PCL",
+                           "-I" + os.path.join(ROOT, "tests", "cpp", "fake_pcl"), "-I" + os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "cpp", "adapter_pcl_mode.cpp"), "-o", exe,
+                           "-L" + os.path.join(ROOT, "lidarslam_ros2_b200", "csrc"), "-lb200reg",
+                           "-Wl,-rpath," + os.path.join(ROOT, "lidarslam_ros2_b200", "csrc")])
+    rc = subprocess.run([exe], capture_output=True, text=True)
+    assert rc.returncode == 3 and "no CUDA device" in rc.stdout, rc.stdout
