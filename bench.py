@@ -37,7 +37,7 @@ WORKLOADS = {
     "c2": ("c2", 2.0, "NDT align, 32-ring scan (~60k pts) vs 500k-pt map, res 2.0, DIRECT7, eps 0.01, max_iter 35"),
     "c1": ("c1", 5.0, "NDT align, 16-ring scan (~10k pts) vs 50k-pt map, res 5.0, DIRECT7, eps 0.01, max_iter 35"),
 }
-N_SCANS = 4  # distinct scans rotated through the steps
+N_SCANS = 4  # ray-cast base scans; every step gets its own copy with an independent sensor-noise draw (step_scans)
 
 
 def make_workload(name: str, rank: int):
@@ -56,103 +56,137 @@ def make_workload(name: str, rank: int):
     return scans, tgt, res, desc
 
 
+def step_scans(base, n_steps: int, rank: int):
+    """One scan per step: base scan k mod N_SCANS plus an independent 3 mm isotropic sensor-noise draw (seeded by rank and
+    step), so that no two steps of a run read the same input buffer. Deterministic; the CPU legs get the same arrays."""
+    out = []
+    for k in range(n_steps):
+        rng = np.random.default_rng(77_000 + 1000 * rank + k)
+        b = base[k % len(base)]
+        out.append((b + rng.normal(0.0, 0.003, size=b.shape)).astype(np.float32))
+    return out
+
+
 class ClockSampler:
-    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe). The timed region of
-    this bench lasts milliseconds, so the sampler polls NVML in-process (nvidia_ml_py) every millisecond; an
-    `nvidia-smi -lms` child, the recipe's literal form, would not deliver a single sample in that time and is only the
-    fallback."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe) by a NATIVE thread
+    (tools/clock_sampler.c: NVML through dlopen, one sample every 250 us plus one before and one after the region).
+    Round 1 polled NVML from a Python thread: eight such pollers fighting eight launch loops for their GILs cost one
+    rank 6.5 ms inside a 3.8 ms timed region on the 8-GPU box. If the native sampler is unavailable the clocks are
+    read once before and once after the region through nvidia_ml_py (never from a polling Python thread)."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
+    LIB = os.path.join(ROOT, "tools", "libclocksampler.so")
 
-    def __init__(self, gpu_index: int):
-        self.gpu = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index: int, period_us: int = 250):
+        self.gpu, self.period_us = gpu_index, period_us
+        self.native = None
         self.nvml = None
-        self.sm, self.mask = [], 0
-        self.mx = None
-        self._stop = threading.Event()
+        self.sm, self.mask, self.mx = [], 0, None
 
-    def _nvml_handle(self):
+    def _uuid(self):
+        try:
+            import torch
+            u = str(torch.cuda.get_device_properties(self.gpu).uuid)
+            return u if u.startswith("GPU-") else "GPU-" + u
+        except Exception:
+            return None
+
+    def _one_shot(self):
+        try:
+            import pynvml
+            if self.nvml is None:
+                pynvml.nvmlInit()
+                u = self._uuid()
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(u) if u else pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
+                self.nvml = pynvml
+                self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
+            try:
+                self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+            except Exception:
+                self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+        except Exception:
+            pass
+
+    def start(self):
+        import ctypes as C
+        try:
+            if os.environ.get("BENCH_NO_NVML"):
+                raise RuntimeError("disabled")
+            L = C.CDLL(self.LIB)
+            L.b200clk_start.argtypes = [C.c_char_p, C.c_int, C.c_int]
+            L.b200clk_stop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            u = self._uuid()
+            if L.b200clk_start(u.encode() if u else None, self.gpu, self.period_us) == 0:
+                self.native = L
+                return
+        except Exception:
+            self.native = None
+        self._one_shot()
+
+    def stop(self) -> dict:
+        import ctypes as C
+        if self.native is not None:
+            cap = 65536
+            sm = (C.c_uint * cap)()
+            rs = (C.c_ulonglong * cap)()
+            mx = C.c_uint(0)
+            n = self.native.b200clk_stop(sm, rs, cap, C.byref(mx))
+            vals = [float(sm[i]) for i in range(n)]
+            mask = 0
+            for i in range(n):
+                mask |= int(rs[i])
+            return {"sm_mhz": float(np.median(vals)) if vals else None, "sm_max_mhz": float(mx.value) or None, "samples": n,
+                    "reasons": sorted(name for bit, name in self.REASONS if mask & bit),
+                    "source": f"nvml from a native thread, every {self.period_us} us inside the timed region (+1 before, +1 after)"}
+        self._one_shot()
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
+                "reasons": sorted(name for bit, name in self.REASONS if self.mask & bit),
+                "source": "nvml, one sample before and one after the timed region (native sampler unavailable)"}
+
+
+def pin_host_thread(local_rank: int):
+    """Keep the launching thread on a few cores of its GPU's NUMA node for the timed regions (the 8-GPU box has two
+    sockets; a migrating launch thread is one of the host-jitter sources the round-1 record showed). Returns the
+    previous affinity so that the CPU baseline can have all cores back."""
+    try:
+        prev = os.sched_getaffinity(0)
+    except Exception:
+        return None
+    try:
         import pynvml
         import torch
         pynvml.nvmlInit()
-        try:
-            uuid = str(torch.cuda.get_device_properties(self.gpu).uuid)
-            if not uuid.startswith("GPU-"):
-                uuid = "GPU-" + uuid
-            h = pynvml.nvmlDeviceGetHandleByUUID(uuid)
-        except Exception:
-            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu)
-        return pynvml, h
+        u = str(torch.cuda.get_device_properties(local_rank).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(u if u.startswith("GPU-") else "GPU-" + u)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = sorted(c for c in (w * 64 + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1) if c in prev)
+        if len(cpus) >= 8:
+            base = (local_rank * 8 + 4) % (len(cpus) - 4)
+            os.sched_setaffinity(0, set(cpus[base:base + 4]))
+    except Exception:
+        pass
+    return prev
 
-    def start(self):
-        try:
-            if os.environ.get("BENCH_NO_NVML"):
-                raise RuntimeError("nvml disabled")
-            self.nvml, self.h = self._nvml_handle()
-            self.mx = float(self.nvml.nvmlDeviceGetMaxClockInfo(self.h, self.nvml.NVML_CLOCK_SM))
-            self._sample()
-            self.t = threading.Thread(target=self._poll, daemon=True)
-            self.t.start()
-            return
-        except Exception:
-            self.nvml = None
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
 
-    def _sample(self):
-        self.sm.append(float(self.nvml.nvmlDeviceGetClockInfo(self.h, self.nvml.NVML_CLOCK_SM)))
-        try:
-            self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksEventReasons(self.h))
-        except Exception:
-            self.mask |= int(self.nvml.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
-
-    def _poll(self):
-        while not self._stop.is_set():
-            try:
-                self._sample()
-            except Exception:
-                break
-            time.sleep(0.001)
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self) -> dict:
-        if self.nvml is not None:
-            self._stop.set()
-            self.t.join(timeout=1)
-            reasons = sorted(name for bit, name in self.REASONS if self.mask & bit)
-            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx,
-                    "samples": len(self.sm), "reasons": reasons, "source": "nvml, 1 ms polling inside the timed region"}
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
-            try:
-                sm.append(float(r[1]))
-                mx.append(float(r[2]))
-            except Exception:
-                continue
-            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
-                if len(r) > col and r[col].lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi -lms 200"}
+def cpu_info() -> dict:
+    info = {"cpus": os.cpu_count()}
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("model name"):
+                    info["model"] = line.split(":", 1)[1].strip()
+                    break
+        out = subprocess.run(["lscpu"], capture_output=True, text=True, timeout=5).stdout
+        for line in out.splitlines():
+            k = line.split(":", 1)[0].strip()
+            if k in ("Socket(s)", "NUMA node(s)", "Thread(s) per core", "Core(s) per socket", "CPU max MHz"):
+                info[k] = line.split(":", 1)[1].strip()
+        with open("/sys/devices/system/cpu/cpu0/cpufreq/scaling_governor") as f:
+            info["governor"] = f.read().strip()
+    except Exception:
+        pass
+    return info
 
 
 def ncu_traffic():
@@ -176,13 +210,52 @@ def hbm_peak():
     return 6650.0, "fallback"
 
 
-def time_cpu(scans, tgt, res, max_seconds: float, max_aligns: int, threads: int | None = None):
-    """CPU oracle on the same workload. Returns (registrations/s, n_aligns, threads, poses)."""
+def host_threads() -> int:
+    """Hardware threads the CPU legs may use (torchrun exports OMP_NUM_THREADS=1, which is not a property of the box)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def workload_config(name: str, scans, tgt) -> dict:
+    """The `config` object — identical in the GPU arm and in the reference arm (same workload, same inputs)."""
+    desc = WORKLOADS[name][2]
+    return {"workload": desc, "n_source": int(len(scans[0])), "n_target": int(len(tgt)), "guess": "identity",
+            "distinct_scans": len(scans),
+            "l2": "GPU arm: 256 MiB memset evicts L2 before every timed region (and between the steps of the single_align leg); "
+                  "inside the batched region every step reads its own scan buffer, the 0.5 MB voxel map of the fixed target "
+                  "stays cache-resident by design (steady-state registration against one map); CPU arm: not applicable"}
+
+
+def make_cpu_ndt(res, threads):
     import oracle
 
-    oracle.build()
-    nt = threads or oracle.max_threads()
-    n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=nt)
+    return oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=threads)
+
+
+def best_cpu_threads(scans, tgt, res):
+    """Thread count the CPU path runs fastest with on this box: all hardware threads, or one per physical core (SMT
+    siblings often hurt this cache-bound loop). One probe align each after a common warm-up."""
+    hw = host_threads()
+    cand = sorted({hw, max(1, hw // 2)}, reverse=True)
+    best = None
+    for c in cand:
+        n = make_cpu_ndt(res, c)
+        n.set_target(tgt)
+        n.set_source(scans[0])
+        n.align()  # builds the lazy target kd-tree like PCL's first align
+        t0 = time.perf_counter()
+        n.align()
+        dt = time.perf_counter() - t0
+        if best is None or dt < best[0]:
+            best = (dt, c)
+    return best[1], cand
+
+
+def time_cpu(scans, tgt, res, max_seconds: float, max_aligns: int, threads: int):
+    """CPU oracle on the same workload. Returns (registrations/s, n_aligns, poses)."""
+    n = make_cpu_ndt(res, threads)
     n.set_target(tgt)
     n.set_source(scans[0])
     n.align()  # warm-up (also builds the lazy target kd-tree like PCL's first align)
@@ -193,35 +266,39 @@ def time_cpu(scans, tgt, res, max_seconds: float, max_aligns: int, threads: int 
         poses.append(n.align())
         t_total += time.perf_counter() - t0
         k += 1
-    return k / t_total, k, nt, poses
+    return k / t_total, k, poses
+
+
+def cpu_thread_sweep(scans, tgt, res, counts):
+    """registrations/s of the CPU path at a few thread counts (two aligns each; BASELINE.md quotes the reference's README at
+    1 and 8 threads)."""
+    out = {}
+    for c in counts:
+        n = make_cpu_ndt(res, c)
+        n.set_target(tgt)
+        n.set_source(scans[0])
+        n.align()
+        t0 = time.perf_counter()
+        for k in range(2):
+            n.set_source(scans[k % len(scans)])
+            n.align()
+        out[str(c)] = 2.0 / (time.perf_counter() - t0)
+    return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the reference's CPU (OpenMP) path for this hot path, timed on the box's host cores."""
+    """--impl reference: the reference's CPU (OpenMP) path for this hot path, timed on the box's host cores with every
+    hardware thread it can use (the reference itself needs PCL/Eigen/FLANN and cannot be built here: kind = port)."""
     if rank != 0:
         return
     scans, tgt, res, desc = make_workload(args.workload, 0)
     import oracle
 
     oracle.build()
-    # thread count: whatever is fastest here — all hardware threads, or one per physical core (SMT siblings often hurt
-    # this memory-bound loop); one probe align each after a common warm-up
-    cand = sorted({oracle.max_threads(), max(1, (os.cpu_count() or 2) // 2), max(1, os.cpu_count() or 1)}, reverse=True)
-    best = None
-    for c in cand:
-        n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=c)
-        n.set_target(tgt)
-        n.set_source(scans[0])
-        n.align()  # builds the lazy target kd-tree like PCL's first align
-        t0 = time.perf_counter()
-        n.align()
-        dt = time.perf_counter() - t0
-        if best is None or dt < best[0]:
-            best = (dt, c)
-    nt = best[1]
-    n = oracle.NDT(resolution=res, transformation_epsilon=0.01, max_iterations=35, search_method=oracle.DIRECT7, num_threads=nt)
+    nt, cand = best_cpu_threads(scans, tgt, res)
+    n = make_cpu_ndt(res, nt)
     n.set_target(tgt)
-    for w in range(max(1, min(args.warmup, 3))):
+    for w in range(args.warmup):
         n.set_source(scans[w % len(scans)])
         n.align()
     t_total = 0.0
@@ -231,15 +308,19 @@ def run_reference(args, rank, world):
         n.align()
         t_total += time.perf_counter() - t0
     v = args.steps / t_total
+    sweep = cpu_thread_sweep(scans, tgt, res, sorted({1, min(8, host_threads())}))
+    sweep[str(nt)] = v
     line = {
         "impl": "reference", "metric": "scan-to-map registrations/sec", "value": v, "unit": "registrations/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": min(args.warmup, 3), "ms_per_step": 1e3 * t_total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math / f64 accumulation",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math / f64 reduction",
         "data": "synthetic",
-        "config": {"workload": desc, "n_source": int(len(scans[0])), "n_target": int(len(tgt)),
-                   "note": "reference cannot be compiled here (PCL/Eigen/FLANN absent): CPU restatement oracle/ (kind=port)"},
+        "config": workload_config(args.workload, scans, tgt),
         "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": nt, "kind": "port",
-                         "sample": f"{args.steps} full align() calls, {nt} OpenMP threads (fastest of {cand}), host has {os.cpu_count()} cpus"},
+                         "sample": f"{args.steps} full align() calls, {nt} OpenMP threads (fastest of {cand}), "
+                                   f"host has {os.cpu_count()} cpus",
+                         "threads_sweep": sweep, "host": cpu_info(),
+                         "note": "reference cannot be compiled here (PCL/Eigen/FLANN absent): CPU restatement oracle/"},
         "e2e": {"value": v, "unit": "registrations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -293,7 +374,7 @@ def run_c5(args, rank, local_rank, world, m):
     import oracle.scanmatcher as osm
 
     oracle.build()
-    o = osm.ScanMatcher(num_threads=oracle.max_threads(), **kw)
+    o = osm.ScanMatcher(num_threads=host_threads(), **kw)
     n_cpu, t_cpu, dpose = 0, 0.0, 0.0
     g2 = ScanMatcher(device=local_rank, **kw)
     for scan, _ in frames[:min(len(frames), args.cpu_frames)]:
@@ -319,7 +400,7 @@ def run_c5(args, rank, local_rank, world, m):
         "gpu_launches": mid["launches"],
         "clocks": clocks,
         "roofline": None,
-        "cpu_baseline": {"value": n_cpu / t_cpu if t_cpu > 0 else None, "unit": "frames/s", "cores": oracle.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": n_cpu / t_cpu if t_cpu > 0 else None, "unit": "frames/s", "cores": host_threads(), "kind": "port",
                          "sample": f"first {n_cpu} frames of the same stream through oracle/scanmatcher.py", "pose_parity_max_m": dpose},
     }
     print(json.dumps(line), flush=True)
@@ -361,81 +442,84 @@ def run_c3(args, rank, local_rank, world, m):
     print(json.dumps(line), flush=True)
 
 
-def run_c4(args, rank, local_rank, world, m):
-    """BASELINE config 4: batched loop-closure NDT — `--pairs` independent scan<->submap pairs (32-ring scan ~60k pts vs
-    200k-pt local map, res 2.0, max_iter 100 as graph_based_slam_component.cpp:66), sharded pair i -> rank i mod N,
-    one NCCL all-gather of the result rows. Strong scaling: value = pairs / max-over-ranks time. Every step goes
-    through the public API with HOST buffers (setInputTarget + setInputSource + align + getFitnessScore)."""
+def c4_generate(pairs: int, mine: list[int]):
+    """The (scan, submap) pairs of the loop-closure sweep owned by this rank, generated in worker processes (before CUDA
+    is touched: fork). Pair i is reproducible on its own (synth.loop_closure_pairs), so every N sees the same 64 pairs."""
+    from concurrent.futures import ProcessPoolExecutor
+
+    world = max(1, int(os.environ.get("WORLD_SIZE", "1")))
+    workers = max(1, min(len(mine), host_threads() // world, 32))
+    if workers <= 1 or len(mine) <= 1:
+        return {i: _c4_pair((pairs, i)) for i in mine}
+    with ProcessPoolExecutor(max_workers=workers) as ex:
+        return dict(zip(mine, ex.map(_c4_pair, [(pairs, i) for i in mine])))
+
+
+def _c4_pair(arg):
+    from lidarslam_ros2_b200 import synth
+
+    pairs, i = arg
+    _, src, tgt, T_rel = next(iter(synth.loop_closure_pairs(pairs, first=i, count=1)))
+    return src, tgt, T_rel
+
+
+def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
+    """BASELINE config 4 inside the default line: the loop-closure candidate sweep — args.pairs independent scan<->submap
+    registrations (32-ring scan ~56k pts vs 200k-pt local map, NDT res 2.0, max_iter 100 as graph_based_slam_component.
+    cpp:66), the SAME pairs at every N, pair i -> rank i mod N, per pair the node's sequence setInputTarget +
+    setInputSource + align + getFitnessScore (gbs.cpp:181, 227-231) from HOST buffers, and ONE all-gather of the result
+    rows INSIDE the timed region. Strong scaling: value = pairs / max-over-ranks time."""
     import torch
     import torch.distributed as dist
 
     from lidarslam_ros2_b200 import batch, synth
 
     mine = batch.shard_pairs(args.pairs, rank, world)
-    data = {}
-    for i in mine:
-        _, src, tgt, T_rel = next(iter(synth.loop_closure_pairs(args.pairs, first=i, count=1)))
-        data[i] = (src, tgt, T_rel)
-    ndt = m.NormalDistributionsTransform(device=local_rank)
-    ndt.setResolution(2.0)
-    ndt.setTransformationEpsilon(0.01)
-    ndt.setMaximumIterations(100)
-    ndt.setNeighborhoodSearchMethod(m.DIRECT7)
-    if mine:  # warm-up on the first pair
+    sweep = batch.LoopSweep(m, device=local_rank, resolution=2.0, max_iterations=100)
+    dev = torch.device("cuda", local_rank)
+    if mine:  # warm-up: allocations and first-launch costs (two pairs, twice)
         for _ in range(2):
-            batch.register_pair(ndt, data[mine[0]][0], data[mine[0]][1])
-    if world > 1:  # warm-up of the collective (NCCL communicator setup happens on first use)
-        batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world,
-                          device=torch.device("cuda", local_rank))
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    launches0 = ndt.stats()["kernel_launches"]
+            sweep.run([data[i][0] for i in mine[:2]], [data[i][1] for i in mine[:2]], mine[:2])
+    batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev)  # NCCL warm-up
+    launches0 = sweep.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     e0.record()
-    rows = []
-    for i in mine:
-        T, fit, conv, it = batch.register_pair(ndt, data[i][0], data[i][1])
-        rows.append(batch.pack_row(i, T, fit, conv, it))
-    res = batch.gather_rows(np.array(rows), args.pairs, rank, world, device=torch.device("cuda", local_rank))
+    rows = sweep.run([data[i][0] for i in mine], [data[i][1] for i in mine], mine)
+    res = batch.gather_rows(rows, args.pairs, rank, world, device=dev)  # the one collective: all-gather of the result rows
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
     t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    allms = [t.clone() for _ in range(world)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    clocks = sampler.stop()
-    if rank == 0:
-        errs = [synth.pose_error(res["pose"][k], next(iter(synth.loop_closure_pairs(args.pairs, n_tgt=10, rings=1, azimuths=4, first=int(i), count=1)))[3])
-                for k, i in enumerate(res["index"][:4])]
-        line = {
-            "metric": "loop-closure candidate registrations/sec (64 scan<->submap pairs)", "value": args.pairs / (ms_max * 1e-3),
-            "unit": "registrations/s", "n_gpus": world, "steps": args.pairs, "warmup": 2, "ms_per_step": ms_max / args.pairs,
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32 pair math / f64 reduction",
-            "data": "synthetic",
-            "config": {"workload": f"c4: {args.pairs} independent NDT pairs, 32-ring scan (~60k) vs 200k-pt submap, res 2.0, "
-                                   "max_iter 100, DIRECT7, setInputTarget+setInputSource+align+getFitnessScore per pair",
-                       "parallelism": f"pair i -> rank i mod {world}; one NCCL all-gather of {batch.ROW}-float rows",
-                       "l2": "every pair has new inputs (host buffers uploaded per step)"},
-            "e2e": {"value": args.pairs / (ms_max * 1e-3), "unit": "registrations/s",
-                    "h2d_bytes_per_step": int(16 * (len(data[mine[0]][0]) + len(data[mine[0]][1]))) if mine else 0,
-                    "d2h_bytes_per_step": 64 + 8},
-            "gpu_launches": int(ndt.stats()["kernel_launches"] - launches0),
-            "clocks": clocks,
-            "converged": int(res["converged"].sum()), "mean_iterations": float(res["iterations"].mean()),
-            "mean_fitness": float(res["fitness"].mean()),
-            "pose_error_vs_truth_first4": [[float(a), float(b)] for a, b in errs],
-        }
+        dist.all_gather(allms, t)
+    per_rank_ms = [float(x.item()) for x in allms] if world > 1 else [ms]
+    ms_max = max(per_rank_ms)
+    if rank != 0:
+        return None
+    errs = [synth.pose_error(res["pose"][k], data[int(i)][2]) for k, i in enumerate(res["index"]) if int(i) in data]
+    out = {
+        "metric": "loop-closure candidate registrations/sec (64 scan<->submap pairs, sharded)", "value": args.pairs / (ms_max * 1e-3),
+        "unit": "registrations/s", "n_gpus": world, "pairs": args.pairs, "ms_per_pair": ms_max / args.pairs, "ms_total": ms_max,
+        "per_rank_ms": per_rank_ms, "scaling": "strong", "collective": "one all-gather of 20-float result rows, inside the timed region",
+        "workload": f"c4: {args.pairs} independent NDT pairs, 32-ring scan (~56k) vs 200k-pt submap, res 2.0, max_iter 100, DIRECT7, "
+                    "setInputTarget+setInputSource+align+getFitnessScore per pair from host buffers; pair i -> rank i mod N",
+        "h2d_bytes_per_pair": int(np.mean([16 * (len(data[i][0]) + len(data[i][1])) for i in mine])) if mine else 0,
+        "gpu_launches": int(sweep.kernel_launches() - launches0),
+        "converged": int(res["converged"].sum()), "mean_iterations": float(res["iterations"].mean()),
+        "mean_fitness": float(res["fitness"].mean()),
+        "pose_error_vs_truth_max": [float(max(e[0] for e in errs)), float(max(e[1] for e in errs))] if errs else None,
+    }
+    if with_cpu:
         try:  # the reference's CPU path on a bounded sample of the same pairs (rank 0's first two)
             import oracle
 
-            oracle.build()
-            o = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7,
-                           num_threads=oracle.max_threads())
-            t_cpu, n_cpu, dmax = 0.0, 0, 0.0
+            nt = host_threads()
+            o = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7, num_threads=nt)
+            t_cpu, n_cpu, dmax, rmax = 0.0, 0, 0.0, 0.0
             for i in mine[:2]:
                 c0 = time.perf_counter()
                 o.set_target(data[i][1])
@@ -445,13 +529,14 @@ def run_c4(args, rank, local_rank, world, m):
                 t_cpu += time.perf_counter() - c0
                 n_cpu += 1
                 k = int(np.where(res["index"] == i)[0][0])
-                dmax = max(dmax, synth.pose_error(res["pose"][k], To)[0])
-            line["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "registrations/s", "cores": oracle.max_threads(), "kind": "port",
-                                    "sample": f"{n_cpu} pairs (setInputTarget + setInputSource + align + getFitnessScore)",
-                                    "pose_parity_max_m": dmax}
-        except Exception as e:  # the GPU line must not depend on the CPU leg
-            line["cpu_baseline"] = {"value": None, "error": str(e)}
-        print(json.dumps(line), flush=True)
+                e = synth.pose_error(res["pose"][k], To)
+                dmax, rmax = max(dmax, e[0]), max(rmax, e[1])
+            out["cpu_baseline"] = {"value": n_cpu / t_cpu, "unit": "registrations/s", "cores": nt, "kind": "port",
+                                   "sample": f"{n_cpu} of the pairs (setInputTarget + setInputSource + align + getFitnessScore)",
+                                   "pose_parity_max": {"dt_m": dmax, "dr_rad": rmax}}
+        except Exception as e:  # the GPU numbers must not depend on the CPU leg
+            out["cpu_baseline"] = {"value": None, "error": str(e)}
+    return out
 
 
 def main():
@@ -461,11 +546,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="headline", choices=sorted(WORKLOADS) + ["c3", "c4", "c5"])
-    ap.add_argument("--pairs", type=int, default=64, help="c4: number of loop-closure candidate pairs (strong scaling)")
+    ap.add_argument("--pairs", type=int, default=64, help="loop-closure sweep: number of candidate pairs (strong scaling)")
     ap.add_argument("--frames", type=int, default=200, help="c5: frames of the synthetic drive (BASELINE config: 1000)")
     ap.add_argument("--cpu-frames", type=int, default=6, help="c5: frames of the stream the CPU restatement is timed on")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the loop-closure sweep object of the headline line")
+    ap.add_argument("--slots", type=int, default=2, help="registrations in flight per batched launch (1 or 2)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -475,6 +562,15 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank, world)
         return
+
+    args.warmup = max(args.warmup, 3)
+    K, W = args.steps, args.warmup
+    # ---- inputs first (worker processes fork before CUDA exists) --------------------------------------------------
+    c4_data = None
+    if args.workload in ("headline", "c4") and not (args.workload == "headline" and args.no_c4):
+        from lidarslam_ros2_b200 import batch as _batch
+
+        c4_data = c4_generate(args.pairs, _batch.shard_pairs(args.pairs, rank, world))
 
     import torch
     import torch.distributed as dist
@@ -486,149 +582,188 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import lidarslam_ros2_b200 as m
 
-    args.warmup = max(args.warmup, 3)
-    if args.workload in ("c3", "c4", "c5"):
-        {"c3": run_c3, "c4": run_c4, "c5": run_c5}[args.workload](args, rank, local_rank, world, m)
+    if args.workload in ("c3", "c5"):
+        {"c3": run_c3, "c5": run_c5}[args.workload](args, rank, local_rank, world, m)
         if world > 1:
             dist.destroy_process_group()
         return
-    scans, tgt, res, desc = make_workload(args.workload, rank)
-    K, W = args.steps, args.warmup
+    if args.workload == "c4":
+        prev = pin_host_thread(local_rank)
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+        c4 = c4_sweep(args, rank, local_rank, world, m, c4_data, with_cpu=False)
+        clocks = sampler.stop()
+        if prev:
+            os.sched_setaffinity(0, prev)
+        if rank == 0:
+            c4["clocks"] = clocks
+            print(json.dumps(c4), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    base, tgt, res, desc = make_workload(args.workload, rank)
+    scans = step_scans(base, max(K, W), rank)
 
     ndt = m.NormalDistributionsTransform(device=local_rank)
     ndt.setResolution(res)
     ndt.setTransformationEpsilon(0.01)
     ndt.setMaximumIterations(35)
     ndt.setNeighborhoodSearchMethod(m.DIRECT7)
+    ndt.setBatchSlots(args.slots)
+    ndt.setInputTarget(tgt)  # first call: allocations
     t0 = time.perf_counter()
     ndt.setInputTarget(tgt)  # H2D + voxel map build (reported separately)
     set_target_ms = 1e3 * (time.perf_counter() - t0)
     target_build_ms = ndt.stats()["target_build_ms"]
 
-    # scans resident in HBM as float4 (plumbing: torch owns the device memory)
-    dev_scans = []
-    for s in scans:
-        a = np.concatenate([s, np.ones((len(s), 1), dtype=np.float32)], axis=1)
-        dev_scans.append(torch.from_numpy(a).cuda())
-    pinned_scans = [torch.from_numpy(np.ascontiguousarray(s)).pin_memory() for s in scans]
+    # scans resident in HBM as float4 (plumbing: torch owns the device memory), and in pinned / pageable host memory
+    dev_scans = [torch.from_numpy(np.concatenate([x, np.ones((len(x), 1), dtype=np.float32)], axis=1)).cuda() for x in scans]
+    pinned_scans = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in scans]
+    pageable_scans = [np.ascontiguousarray(x).copy() for x in scans]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     poses_dev = torch.zeros((K, 16), dtype=torch.float32, device="cuda")
+    gathered = [torch.empty_like(poses_dev) for _ in range(world)]
+    ptrs = [d.data_ptr() for d in dev_scans]
+    counts = [int(d.shape[0]) for d in dev_scans]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_resident(k):
-        d = dev_scans[k % N_SCANS]
-        ndt.setInputSourceDevice(d.data_ptr(), d.shape[0])
-        return ndt.align()
+    def flush():
+        if not args.no_flush:
+            flush_buf.zero_()  # evict L2 (126 MB); excluded from the timing
+            torch.cuda.synchronize()
 
-    def step_e2e(k):
-        ndt.setInputSource(pinned_scans[k % N_SCANS].numpy())
-        return ndt.align()
+    def timed(fn):
+        """barrier + sync, CUDA events around fn() (synchronous engine call) + the pose all-gather, sync; max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        flush()
+        barrier()
+        e0.record()
+        r = fn()
+        poses_dev.copy_(torch.from_numpy(np.ascontiguousarray(r["pose"].reshape(-1, 16)[:K])), non_blocking=False)
+        if world > 1:  # the one collective of the replicated sweep: all-gather of the 4x4 poses (NCCL over NVLink)
+            dist.all_gather(gathered, poses_dev)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        allt = [t.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(allt, t)
+        per = [float(x.item()) for x in allt] if world > 1 else [ms]
+        return r, max(per), per
 
+    # ---- warm-up: W single aligns, one batch of W from HBM, one from host --------------------------------------
     for k in range(W):
-        step_resident(k)
-        step_e2e(k)
+        ndt.setInputSourceDevice(ptrs[k], counts[k])
+        ndt.align()
+    ndt.alignBatchDevice(ptrs[:W], counts[:W])
+    ndt.alignBatch([p.numpy() for p in pinned_scans[:W]])
+    ndt.alignBatch(pageable_scans[:W])
+    if world > 1:
+        dist.all_gather(gathered, poses_dev)
 
-    # ---- timed: HBM-resident -------------------------------------------------------------------------------
+    prev_aff = pin_host_thread(local_rank)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    # ---- timed (value): K registrations of HBM-resident scans, ONE batched launch ---------------------------------
     launches0 = ndt.stats()["kernel_launches"]
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    solve_ms, evals, hits_tot, alg_bytes = [], [], [], []
-    poses = []
-    barrier()
     wall0 = time.perf_counter()
-    for k in range(K):
-        if not args.no_flush:
-            flush_buf.zero_()  # evict L2 (126 MB) between steps; excluded from the per-step timing
-            torch.cuda.synchronize()
-        ev[k][0].record()
-        T = step_resident(k)
-        ev[k][1].record()
-        poses.append(T)
-        st = ndt.stats()
-        solve_ms.append(st["solve_ms"])
-        evals.append(st["evaluations"])
-        hits_tot.append(st["hits_total"])
-        n_src = st["n_source"]
-        alg_bytes.append(st["evaluations"] * (n_src * 16 + n_src * 7 * 8 + 224) + st["hits_total"] * 48)
-    poses_dev.copy_(torch.from_numpy(np.stack(poses).reshape(K, 16)))
-    if world > 1:  # the one collective of the batched sweep: all-gather of the 4x4 poses (NCCL over NVLink)
-        gathered = [torch.empty_like(poses_dev) for _ in range(world)]
-        dist.all_gather(gathered, poses_dev)
-    barrier()
+    rb, total_ms_max, per_rank_ms = timed(lambda: ndt.alignBatchDevice(ptrs[:K], counts[:K]))
     wall = time.perf_counter() - wall0
-    launches = ndt.stats()["kernel_launches"] - launches0
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    total_ms = float(np.sum(step_ms))
+    st = ndt.stats()
+    launches = st["kernel_launches"] - launches0
+    kernel_ms = float(st["solve_ms"])
+    evals, hits = rb["evaluations"].astype(np.int64), rb["hits_total"].astype(np.int64)
+    n_pts = np.array(counts[:K], dtype=np.int64)
+    alg_bytes = float(np.sum(evals * (n_pts * 16 + n_pts * 7 * 8 + 224)) + np.sum(hits) * 48)
+    # ---- timed (e2e): the same K registrations from HOST buffers through the public call ---------------------------
+    re, e2e_ms_max, _ = timed(lambda: ndt.alignBatch([p.numpy() for p in pinned_scans[:K]]))
+    rp, e2e_pg_ms_max, _ = timed(lambda: ndt.alignBatch(pageable_scans[:K]))
     clocks = sampler.stop()
-    t_total = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    per_rank = torch.tensor([total_ms, float(np.sum(solve_ms)), float(np.sum(evals))], dtype=torch.float64, device="cuda")
-    per_rank_all = [per_rank.clone() for _ in range(world)]
-    if world > 1:
-        dist.all_reduce(t_total, op=dist.ReduceOp.MAX)
-        dist.all_gather(per_rank_all, per_rank)
-    total_ms_max = float(t_total.item())
-    per_rank_rows = [{"step_ms_sum": float(r[0]), "kernel_ms_sum": float(r[1]), "evaluations": int(r[2])} for r in per_rank_all]
 
-    # ---- timed: end to end with host buffers -------------------------------------------------------------
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    # ---- single_align leg: one b200reg_align per step (latency-bound: round 1's headline), L2 flushed between steps ----
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    single_solve_ms, single_poses = [], []
     barrier()
     for k in range(K):
-        if not args.no_flush:
-            flush_buf.zero_()
-            torch.cuda.synchronize()
-        ev2[k][0].record()
-        T = step_e2e(k)
-        ev2[k][1].record()
+        flush()
+        ev[k][0].record()
+        ndt.setInputSourceDevice(ptrs[k], counts[k])
+        single_poses.append(ndt.align())
+        ev[k][1].record()
+        single_solve_ms.append(ndt.stats()["solve_ms"])
     barrier()
-    e2e_ms = float(np.sum([a.elapsed_time(b) for a, b in ev2]))
-    t2 = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_ms_max = float(t2.item())
+    single_ms = float(np.sum([a.elapsed_time(b) for a, b in ev]))
+    if prev_aff:
+        os.sched_setaffinity(0, prev_aff)
+    bitwise = all(np.array_equal(rb["pose"][k], single_poses[k]) for k in range(K)) and \
+        all(np.array_equal(rb["pose"][k], re["pose"][k]) and np.array_equal(rb["pose"][k], rp["pose"][k]) for k in range(K))
+
+    # ---- the loop-closure sweep (BASELINE config 4) rides in the same line ---------------------------------------
+    c4 = None
+    if c4_data is not None:
+        c4 = c4_sweep(args, rank, local_rank, world, m, c4_data, with_cpu=not args.no_cpu_baseline)
 
     if rank == 0:
         peak, which = hbm_peak()
-        kern_s = float(np.sum(solve_ms)) * 1e-3
-        achieved = float(np.sum(alg_bytes)) / kern_s / 1e9 if kern_s > 0 else 0.0
+        achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        n_evals = int(np.sum(evals))
         line = {
             "metric": "scan-to-map registrations/sec", "value": world * K / (total_ms_max * 1e-3), "unit": "registrations/s",
             "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": total_ms_max / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math / f64 reduction", "data": "synthetic",
-            "config": {"workload": desc, "n_source": int(len(scans[0])), "n_target": int(len(tgt)),
-                       "n_voxels": int(ndt.stats()["n_voxels"]), "guess": "identity",
-                       "l2": "working set < L2: L2 flushed (256 MiB memset) between steps, flush excluded from timing"
-                       if not args.no_flush else "L2 warm (no flush)",
-                       "parallelism": f"replicas x{world} + 1 NCCL all-gather of poses" if world > 1 else "1 GPU",
-                       "grid_ctas": ndt.stats()["grid_ctas"], "block_threads": ndt.stats()["block_threads"],
-                       "index_in_smem": ndt.stats()["index_in_smem"]},
+            "config": workload_config(args.workload, base, tgt),
+            "details": {"n_voxels": int(st["n_voxels"]), "grid_ctas": st["grid_ctas"], "block_threads": st["block_threads"],
+                        "index_in_smem": st["index_in_smem"], "slots_in_flight": args.slots,
+                        "step": "the K steps are K independent registrations (own scan buffer each) issued as ONE "
+                                "b200reg_ndt_align_batch_device call = one persistent launch, 2 registrations in flight",
+                        "parallelism": f"replicas x{world} + 1 NCCL all-gather of the poses inside the timed region" if world > 1 else "1 GPU",
+                        "batch_bitwise_equals_single_align": bool(bitwise),
+                        "mean_iterations": float(rb["iterations"].mean()), "converged": int(rb["converged"].sum())},
             "e2e": {"value": world * K / (e2e_ms_max * 1e-3), "unit": "registrations/s",
-                    "h2d_bytes_per_step": int(pinned_scans[0].numel() * 4), "d2h_bytes_per_step": 64 + 456,
-                    "ms_per_step": e2e_ms_max / K},
+                    "h2d_bytes_per_step": int(np.mean([p.numel() * 4 for p in pinned_scans[:K]])), "d2h_bytes_per_step": 448,
+                    "ms_per_step": e2e_ms_max / K, "host_memory": "pinned",
+                    "pageable": {"value": world * K / (e2e_pg_ms_max * 1e-3), "ms_per_step": e2e_pg_ms_max / K,
+                                 "note": "pcl::PointCloud storage is pageable: staged through a pinned buffer with memcpy"}},
+            "single_align": {"value": world * K / (single_ms * 1e-3), "unit": "registrations/s", "ms_per_step": single_ms / K,
+                             "kernel_ms_per_step": float(np.mean(single_solve_ms)),
+                             "note": "one b200reg_align per step (setInputSourceDevice + align, L2 flushed between steps): the "
+                                     "latency of ONE registration; rank 0's own time"},
             "gpu_launches": int(launches),
-            "per_rank": per_rank_rows,
+            "per_rank": [{"step_ms_sum": x} for x in per_rank_ms],
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "ndt_solver_kernel<DIRECT7> (persistent: all evaluations of one align)",
+            "roofline": {"bound": "hbm", "kernel": f"ndt_solver_kernel<DIRECT7> (persistent: all evaluations of {K} registrations, "
+                                                   f"{args.slots} in flight)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                         "traffic": ncu_traffic(), "alg_bytes_per_launch": float(np.mean(alg_bytes)),
-                         "launch_ms": float(np.mean(solve_ms)), "evaluations_per_launch": float(np.mean(evals)),
-                         "us_per_evaluation": 1e3 * float(np.sum(solve_ms)) / max(1, int(np.sum(evals))),
-                         "hits_per_point": float(np.sum(hits_tot)) / max(1, int(np.sum(evals))) / max(1, len(scans[0]))},
+                         "traffic": ncu_traffic(), "alg_bytes_per_launch": alg_bytes,
+                         "launch_ms": kernel_ms, "evaluations_per_launch": n_evals,
+                         "us_per_evaluation": 1e3 * kernel_ms / max(1, n_evals),
+                         "hits_per_point": float(np.sum(hits)) / max(1.0, float(np.sum(evals * n_pts)))},
             "target_build": {"set_input_target_ms": set_target_ms, "voxel_build_device_ms": target_build_ms},
             "wall_s_timed_region": wall,
         }
-        if not args.no_cpu_baseline and world >= 1:
-            v, k_done, nt, cpu_poses = time_cpu(scans, tgt, res, max_seconds=20.0, max_aligns=min(K, 40))
+        if c4 is not None:
+            line["c4"] = c4
+        if not args.no_cpu_baseline:
+            import oracle
+
+            oracle.build()
+            nt, cand = best_cpu_threads(scans, tgt, res)
+            v, k_done, cpu_poses = time_cpu(scans, tgt, res, max_seconds=15.0, max_aligns=min(K, 40), threads=nt)
             from lidarslam_ros2_b200 import synth
 
-            errs = [synth.pose_error(poses[i], cpu_poses[i]) for i in range(min(len(cpu_poses), K))]
+            errs = [synth.pose_error(rb["pose"][i], cpu_poses[i]) for i in range(min(len(cpu_poses), K))]
+            sweep = cpu_thread_sweep(scans, tgt, res, sorted({1, min(8, host_threads())}))
+            sweep[str(nt)] = v
             line["cpu_baseline"] = {"value": v, "unit": "registrations/s", "cores": nt, "kind": "port",
-                                    "sample": f"{k_done} full align() calls of the same workload, {nt} OpenMP threads "
-                                              f"(host reports {os.cpu_count()} cpus)",
+                                    "sample": f"{k_done} full align() calls of the same steps, {nt} OpenMP threads "
+                                              f"(fastest of {cand}; host reports {os.cpu_count()} cpus)",
+                                    "threads_sweep": sweep, "host": cpu_info(),
                                     "pose_parity_max": {"dt_m": max(e[0] for e in errs), "dr_rad": max(e[1] for e in errs)}}
         print(json.dumps(line), flush=True)
     if world > 1:

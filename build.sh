@@ -14,3 +14,8 @@ for f in voxel_map ndt_solver ndt_aux nn_grid voxelgrid gicp cloud_codec capi sc
 done
 $NVCC -gencode arch=compute_100a,code=sm_100a -shared -o libb200reg.so $OBJS -ccbin $(command -v g++)
 echo built lidarslam_ros2_b200/csrc/libb200reg.so
+# measurement plumbing of bench.py (NVML clock sampling in a native thread), not part of the engine
+cd ../../tools
+if [ ! -f libclocksampler.so ] || [ clock_sampler.c -nt libclocksampler.so ]; then
+  gcc -O2 -shared -fPIC -o libclocksampler.so clock_sampler.c -ldl -lpthread
+fi

@@ -14,7 +14,8 @@
  *  - 4x4 matrices are 16 floats COLUMN-MAJOR — exactly Eigen::Matrix4f::data().
  *  - clouds are (const float* base, size_t n, size_t stride_bytes) with x,y,z at byte offsets 0,4,8 of every
  *    point: pass pcl::PointCloud<PointXYZI>::points.data() with stride 32 (PointXYZ: 16).
- *  - the library copies what it needs to the GPU inside set_input_*; caller memory may be freed on return.
+ *  - the library copies what it needs to the GPU inside set_input_*; caller memory (host or device) may be freed or
+ *    overwritten on return. A device buffer must be complete (its producer stream synchronised) at the call.
  *  - one handle = one CUDA stream + its device buffers; a handle is used from one host thread at a time,
  *    different handles may be used concurrently from different threads (lidarslam/src/lidarslam.cpp:12-17).
  *  - there is NO CPU fallback: without a CUDA device b200reg_create fails with B200REG_ERR_CUDA.
@@ -101,10 +102,38 @@ int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out);
 /* the `output` cloud of align(): source transformed by the final transformation; out has n_source points */
 int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes);
 
-/* Batched loop-closure sweep (generalises gbs.cpp:187-233 from the arg-min candidate to all candidates):
- * runs align() on `count` independent handles of ONE device concurrently (one stream each) and returns when
- * all are done. guesses may be NULL (identity); finals = 16*count floats. */
+/* Batched loop-closure sweep over independent handles (different targets; generalises gbs.cpp:187-233 from the
+ * arg-min candidate to all candidates): every NDT solve is ENQUEUED on its handle's stream before the first one is
+ * waited for, so the host-side launch / synchronise round trips overlap the device work of the other handles. The
+ * solver kernels themselves occupy the whole GPU and run one after the other. guesses may be NULL (identity);
+ * finals = 16*count floats. Results are those of b200reg_align on each handle. */
 int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, float* finals);
+
+/* K independent NDT registrations against the handle's CURRENT target in ONE persistent launch — repeated
+ * align() calls of apps/align.cpp:32-36 ("10times"), multi-hypothesis initial guesses, or the candidate scans of a
+ * loop-closure sweep sharing one map. Two registrations are in flight inside the kernel: while one registration's
+ * Newton step (fixed-order reduction, 6x6 solve, next pose) runs on its controller SM, the evaluator SMs compute the
+ * other registration's derivatives, so the sequential part of ndt_omp_impl.hpp:121-166 no longer idles the GPU.
+ * Every result is BITWISE the result b200reg_align gives for the same (source, guess).
+ * guesses: 16*count floats column-major, or NULL (identity). results[k].status is B200REG_OK or an error code.
+ * After the call the handle's getters (final transformation, converged, ...) describe the LAST registration;
+ * b200reg_get_stats reports evaluations / hits_total / solve_ms summed over the batch. */
+typedef struct b200reg_batch_result {
+  float final_T[16];         /* getFinalTransformation(), column-major                                     */
+  double trans_probability;  /* getTransformationProbability()                                              */
+  int converged, iterations, evaluations, status;
+  long long hits_total;
+} b200reg_batch_result;
+/* sources in HOST memory: (base, n, stride) clouds as in b200reg_set_input_source, one bulk copy + unpack each, no
+ * synchronisation in between */
+int b200reg_ndt_align_batch(b200reg_t h, int count, const float* const* sources, const size_t* n_points,
+                            size_t stride_bytes, const float* guesses, b200reg_batch_result* results);
+/* sources already in HBM as float4 (x, y, z, ignored) on the handle's device; read in place (no copy) — they must
+ * be complete when the call is made and stay untouched until it returns */
+int b200reg_ndt_align_batch_device(b200reg_t h, int count, const void* const* dev_sources, const size_t* n_points,
+                                   const float* guesses, b200reg_batch_result* results);
+/* registrations in flight per batch launch (1 or 2; default 2). Developer / measurement switch. */
+int b200reg_ndt_set_batch_slots(b200reg_t h, int slots);
 
 /* ---- pcl::VoxelGrid<PointXYZI>::filter (sm.cpp:266-269,311-314,325-328,444-447; gbs.cpp:225-226) ------ */
 /* Centroid downsample of all fields (x,y,z,intensity). intensity_offset_bytes < 0: no intensity field.

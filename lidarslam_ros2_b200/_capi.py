@@ -30,6 +30,7 @@ SYMBOLS = [
     "b200reg_set_input_target_device", "b200reg_set_input_source_device",
     "b200reg_align", "b200reg_get_final_transformation", "b200reg_has_converged",
     "b200reg_get_fitness_score", "b200reg_get_aligned", "b200reg_align_batch",
+    "b200reg_ndt_align_batch", "b200reg_ndt_align_batch_device", "b200reg_ndt_set_batch_slots",
     "b200reg_voxelgrid", "b200reg_get_stats", "b200reg_ndt_derivatives", "b200reg_ndt_hessian_radius",
     "b200reg_ndt_num_voxels", "b200reg_ndt_get_voxels", "b200reg_nn1",
     "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
@@ -48,6 +49,11 @@ class SmLoopResult(C.Structure):
 class SmStats(C.Structure):
     _fields_ = [("n_scan", C.c_size_t), ("n_filtered", C.c_size_t), ("n_targeted", C.c_size_t), ("n_submaps", C.c_size_t),
                 ("kernel_launches", C.c_int), ("trans", C.c_double), ("latest_distance", C.c_double)]
+
+
+class BatchResult(C.Structure):
+    _fields_ = [("final_T", C.c_float * 16), ("trans_probability", C.c_double), ("converged", C.c_int), ("iterations", C.c_int),
+                ("evaluations", C.c_int), ("status", C.c_int), ("hits_total", C.c_longlong)]
 
 
 class Stats(C.Structure):
@@ -111,6 +117,9 @@ def lib() -> C.CDLL:
     L.b200reg_get_fitness_score.argtypes = [vp, d, C.POINTER(d)]
     L.b200reg_get_aligned.argtypes = [vp, vp, sz]
     L.b200reg_align_batch.argtypes = [vp, i, vp, vp]
+    L.b200reg_ndt_align_batch.argtypes = [vp, i, vp, vp, sz, vp, vp]
+    L.b200reg_ndt_align_batch_device.argtypes = [vp, i, vp, vp, vp, vp]
+    L.b200reg_ndt_set_batch_slots.argtypes = [vp, i]
     L.b200reg_voxelgrid.argtypes = [i, vp, sz, sz, C.c_long, f, vp, sz, C.POINTER(sz)]
     L.b200reg_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200reg_ndt_derivatives.argtypes = [vp, vp, vp, i, C.POINTER(d), vp, vp]

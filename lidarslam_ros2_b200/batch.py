@@ -72,3 +72,22 @@ def register_pair(engine, source, target, guess=None, fitness_max_range=None):
     T = engine.align(guess)
     fit = engine.getFitnessScore() if fitness_max_range is None else engine.getFitnessScore(fitness_max_range)
     return T, fit, engine.hasConverged(), engine.getFinalNumIteration()
+
+
+class LoopSweep:
+    """The loop-closure candidate sweep of one rank: its share of the (scan, submap) pairs, one after the other through the
+    node's own call sequence (graph_based_slam_component.cpp:181, 227-231). Returns the packed result rows."""
+
+    def __init__(self, m, device: int = 0, resolution: float = 2.0, max_iterations: int = 100, transformation_epsilon: float = 0.01):
+        self.ndt = m.NormalDistributionsTransform(device=device)
+        self.ndt.setResolution(resolution)
+        self.ndt.setTransformationEpsilon(transformation_epsilon)
+        self.ndt.setMaximumIterations(max_iterations)  # graph_based_slam_component.cpp:66
+        self.ndt.setNeighborhoodSearchMethod(m.DIRECT7)
+
+    def kernel_launches(self) -> int:
+        return int(self.ndt.stats()["kernel_launches"])
+
+    def run(self, sources, targets, indices) -> np.ndarray:
+        rows = [pack_row(i, *register_pair(self.ndt, s, t)) for s, t, i in zip(sources, targets, indices)]
+        return np.array(rows, dtype=np.float32).reshape(-1, ROW)

@@ -14,6 +14,8 @@
 
 using namespace b200;
 
+static constexpr int NDT_BATCH_SLOTS_DEFAULT = 2;  // registrations in flight per batch launch (engine.hpp / ndt_solver.cuh)
+
 struct b200reg_engine {
   int kind = B200REG_NDT;
   int device = 0;
@@ -56,7 +58,14 @@ struct b200reg_engine {
   long long hits_last = 0, hits_total = 0;
   float solve_ms = 0, target_build_ms = 0;
   bool align_pending = false;
+  bool grid_overflow = false;  // the last voxel-map build hit the int32 guard (voxel_grid_covariance_omp_impl.hpp:79)
   int other_launches = 0;
+
+  // batched registrations (b200reg_ndt_align_batch*)
+  DeviceBuffer<float4> d_batch;          // host-buffer form: all sources of the batch, back to back
+  CloudUploader batch_uploader;
+  std::vector<NdtSolver::BatchItem> batch_items;
+  int batch_slots = NDT_BATCH_SLOTS_DEFAULT;
 };
 
 namespace {
@@ -108,6 +117,7 @@ void ensure_map(b200reg_t h) {
   B200_CUDA(cudaEventElapsedTime(&h->target_build_ms, h->ev0, h->ev1));
   h->map_valid = true;
   h->map_resolution = h->ndt.resolution;
+  h->grid_overflow = !ok;
   if (!ok) h->err = "voxel grid would overflow int32: leaf size too small for the target cloud (map left empty)";
 }
 
@@ -211,9 +221,13 @@ int set_cloud(b200reg_t h, bool target, const float* base, size_t n, size_t stri
   if (n == 0 || (!base && !dev)) return fail(h, B200REG_ERR_ARG, "empty input cloud ignored");
   if (!dev && stride < 12) return fail(h, B200REG_ERR_ARG, "stride_bytes must be >= 12");
   DeviceBuffer<float4>& dst = target ? h->d_target : h->d_source;
+  if (!dev && (stride % 4) != 0) return fail(h, B200REG_ERR_ARG, "stride_bytes must be a multiple of 4 (float fields)");
   if (dev) {
     dst.ensure(n);
     B200_CUDA(cudaMemcpyAsync(dst.ptr, dev, n * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+    // "caller memory may be reused on return" (b200reg.h): the copy runs on the handle's own stream, so wait for it —
+    // the producer (a torch allocator, the frontend session's stream) is free to overwrite the buffer afterwards
+    B200_CUDA(cudaStreamSynchronize(h->stream));
   } else {
     upload_cloud(base, n, stride, dst, h->uploader, h->stream);
     // the caller may reuse its buffer (and the staging copy is reused by the next upload): wait for the copy engine
@@ -225,7 +239,10 @@ int set_cloud(b200reg_t h, bool target, const float* base, size_t n, size_t stri
     h->map_valid = false;
     h->nn_valid = false;
     h->gicp_solver.invalidate_target();
-    if (h->kind == B200REG_NDT) ensure_map(h);  // setInputTarget → init() builds the voxel structure eagerly
+    if (h->kind == B200REG_NDT) {
+      ensure_map(h);  // setInputTarget → init() builds the voxel structure eagerly
+      if (h->grid_overflow) return B200REG_ERR_GRID;
+    }
   } else {
     h->n_source = n;
     h->have_source = true;
@@ -322,7 +339,10 @@ int b200reg_ndt_set_resolution(b200reg_t h, float resolution) {
   return guarded(h, [&]() {
     if (h->ndt.resolution != resolution) {  // ndt_omp.h:127-137: re-voxelise only when it changes
       h->ndt.resolution = resolution;
-      if (h->have_target && h->have_source) ensure_map(h);  // reference re-inits `if (input_)`
+      if (h->have_target && h->have_source) {  // reference re-inits `if (input_)`
+        ensure_map(h);
+        if (h->grid_overflow) return (int)B200REG_ERR_GRID;
+      }
     }
     return (int)B200REG_OK;
   });
@@ -745,6 +765,162 @@ int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, i
     B200_CUDA(cudaStreamSynchronize(h->stream));
     return (int)B200REG_OK;
   });
+}
+
+}  // extern "C"
+
+// ---- batched NDT registration: K independent scans against the current target in ONE persistent launch --------------
+namespace {
+// items: device-resident sources + row-major guesses, already in h->batch_items
+int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results) {
+  if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "align_batch: no input target");
+  ensure_map(h);
+  std::vector<NdtSolver::BatchItem>& items = h->batch_items;
+  auto store = [&](int k, const float* T_row, int converged, int iterations, int evaluations, double tp, long long hits,
+                   int status) {
+    b200reg_batch_result& r = results[k];
+    row_to_col(T_row, r.final_T);
+    r.trans_probability = tp;
+    r.converged = converged;
+    r.iterations = iterations;
+    r.evaluations = evaluations;
+    r.status = status;
+    r.hits_total = hits;
+  };
+  long long evals = 0, hits = 0;
+  // One launch cannot serve: an empty map (the reference returns the guess), or a configuration whose line search runs
+  // the More-Thuente inner loop (step_max <= step_min: it leaves the kernel for the f64 radius Hessian) — those take
+  // the single-registration path one by one.
+  const bool sequential = h->map.n_voxels == 0 || !((h->ndt.step_size - h->ndt.trans_eps / 2) > 0) || h->solver.timing_enabled;
+  if (sequential) {
+    int worst = B200REG_OK;
+    float ms = 0;
+    for (int k = 0; k < count; k++) {
+      h->d_source.ensure(items[k].n_src);
+      B200_CUDA(cudaMemcpyAsync(h->d_source.ptr, items[k].src, items[k].n_src * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+      h->n_source = items[k].n_src;
+      h->have_source = true;
+      float Tc[16];
+      row_to_col(items[k].T_rowmajor16, Tc);
+      int rc = ndt_align_begin(h, Tc);
+      if (rc == B200REG_OK) rc = ndt_align_end(h);
+      store(k, h->final_T, h->converged, h->iterations, h->evaluations, h->trans_probability, h->hits_total, rc);
+      evals += h->evaluations;
+      hits += h->hits_total;
+      ms += h->solve_ms;
+      if (rc != B200REG_OK) worst = rc;
+    }
+    h->evaluations = (int)evals;
+    h->hits_total = hits;
+    h->solve_ms = ms;
+    return worst;
+  }
+  // sequence numbers bound the rounds one slot may run inside a launch: chunk the batch accordingly
+  const int per_launch = std::max(1, NdtSolver::kMaxRoundsPerLaunch / (h->ndt.max_iterations + 4));
+  int worst = B200REG_OK;
+  float ms_total = 0;
+  for (int first = 0; first < count; first += per_launch) {
+    const int n = std::min(per_launch, count - first);
+    B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+    h->solver.launch_batch(h->map, items.data() + first, n, h->ndt, h->batch_slots);
+    B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+    B200_CUDA(cudaStreamSynchronize(h->stream));
+    float ms = 0;
+    B200_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    ms_total += ms;
+    const NdtResult* R = h->solver.batch_results();
+    bool failed = false;
+    for (int k = 0; k < n; k++) {
+      const NdtResult& r = R[k];
+      if (r.error != 0) {
+        failed = true;
+        float I[16];
+        set_identity(I);
+        store(first + k, I, 0, 0, 0, 0.0, 0, B200REG_ERR_TIMEOUT);
+        continue;
+      }
+      store(first + k, r.final_T, r.converged, r.iterations, r.evaluations, r.trans_probability, r.hits_total, B200REG_OK);
+      evals += r.evaluations;
+      hits += r.hits_total;
+    }
+    if (failed) {
+      h->solver.reset_barrier();
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+      worst = fail(h, B200REG_ERR_TIMEOUT, "NDT batch solver: a registration did not finish (device watchdog)");
+    }
+  }
+  // the handle's "last align" state = the last registration of the batch
+  if (count > 0 && results[count - 1].status == B200REG_OK) {
+    col_to_row(results[count - 1].final_T, h->final_T);
+    h->converged = results[count - 1].converged;
+    h->iterations = results[count - 1].iterations;
+    h->trans_probability = results[count - 1].trans_probability;
+  }
+  h->evaluations = (int)evals;
+  h->hits_total = hits;
+  h->solve_ms = ms_total;
+  return worst;
+}
+}  // namespace
+
+extern "C" {
+
+int b200reg_ndt_align_batch_device(b200reg_t h, int count, const void* const* dev_sources, const size_t* n_points,
+                                   const float* guesses, b200reg_batch_result* results) {
+  if (!h || h->kind != B200REG_NDT || count < 0 || (count > 0 && (!dev_sources || !n_points || !results))) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    h->batch_items.resize((size_t)count);
+    for (int k = 0; k < count; k++) {
+      if (!dev_sources[k] || n_points[k] == 0) return fail(h, B200REG_ERR_ARG, "align_batch: empty source cloud");
+      NdtSolver::BatchItem& it = h->batch_items[k];
+      it.src = static_cast<const float4*>(dev_sources[k]);
+      it.n_src = n_points[k];
+      if (guesses) col_to_row(guesses + 16 * k, it.T_rowmajor16);
+      else set_identity(it.T_rowmajor16);
+    }
+    return ndt_batch_run(h, count, results);
+  });
+}
+
+int b200reg_ndt_align_batch(b200reg_t h, int count, const float* const* sources, const size_t* n_points, size_t stride_bytes,
+                            const float* guesses, b200reg_batch_result* results) {
+  if (!h || h->kind != B200REG_NDT || count < 0 || (count > 0 && (!sources || !n_points || !results))) return B200REG_ERR_ARG;
+  if (stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
+  return guarded(h, [&]() {
+    size_t total = 0, raw_total = 0;
+    bool pageable = false;
+    std::vector<char> pinned((size_t)count);
+    for (int k = 0; k < count; k++) {
+      if (!sources[k] || n_points[k] == 0) return fail(h, B200REG_ERR_ARG, "align_batch: empty source cloud");
+      total += n_points[k];
+      raw_total += (n_points[k] * stride_bytes + 255) & ~(size_t)255;
+      pinned[k] = CloudUploader::is_pinned(sources[k]) ? 1 : 0;
+      pageable = pageable || !pinned[k];
+    }
+    h->d_batch.ensure(total);
+    h->batch_uploader.reserve(raw_total, pageable);
+    h->batch_items.resize((size_t)count);
+    size_t off = 0, raw_off = 0;
+    for (int k = 0; k < count; k++) {  // copies and unpack kernels stream back to back; nothing waits in between
+      h->batch_uploader.upload_at(sources[k], pinned[k] != 0, n_points[k], stride_bytes, -1, 1.0f, h->d_batch.ptr + off, raw_off,
+                                  h->stream);
+      NdtSolver::BatchItem& it = h->batch_items[k];
+      it.src = h->d_batch.ptr + off;
+      it.n_src = n_points[k];
+      if (guesses) col_to_row(guesses + 16 * k, it.T_rowmajor16);
+      else set_identity(it.T_rowmajor16);
+      off += n_points[k];
+      raw_off += (n_points[k] * stride_bytes + 255) & ~(size_t)255;
+    }
+    h->other_launches += count;
+    return ndt_batch_run(h, count, results);
+  });
+}
+
+int b200reg_ndt_set_batch_slots(b200reg_t h, int slots) {
+  if (!h || slots < 1) return B200REG_ERR_ARG;
+  h->batch_slots = slots;
+  return B200REG_OK;
 }
 
 }  // extern "C"

@@ -45,6 +45,34 @@ void CloudUploader::upload(const void* host, size_t n, size_t stride, long w_off
   launches += 1;
 }
 
+// Batched form: `reserve` sizes the raw device buffer (and the pinned staging copy when some input is pageable) for
+// the whole batch once, `upload_at` then enqueues copy + unpack of one cloud at its byte offset — no synchronisation
+// between the clouds of a batch, the copy engine streams them back to back.
+void CloudUploader::reserve(size_t raw_bytes, bool need_staging) {
+  raw.ensure(raw_bytes);
+  if (need_staging) staging.ensure(raw_bytes);
+}
+bool CloudUploader::is_pinned(const void* host) {
+  cudaPointerAttributes attr{};
+  const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  if (!pinned) cudaGetLastError();
+  return pinned;
+}
+void CloudUploader::upload_at(const void* host, bool pinned, size_t n, size_t stride, long w_off, float w_default, float4* dst,
+                              size_t byte_offset, cudaStream_t s) {
+  if (n == 0) return;
+  const size_t bytes = n * stride;
+  const void* src = host;
+  if (!pinned) {
+    std::memcpy(staging.ptr + byte_offset, host, bytes);
+    src = staging.ptr + byte_offset;
+  }
+  B200_CUDA(cudaMemcpyAsync(raw.ptr + byte_offset, src, bytes, cudaMemcpyHostToDevice, s));
+  unpack_points_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(raw.ptr + byte_offset, n, stride, w_off, w_default, dst);
+  B200_CUDA(cudaGetLastError());
+  launches += 1;
+}
+
 void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst, CloudUploader& up, cudaStream_t s) {
   dst.ensure(n);
   up.upload(base, n, stride_bytes, -1, 1.0f, dst.ptr, s);

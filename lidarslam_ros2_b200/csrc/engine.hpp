@@ -84,6 +84,11 @@ struct CloudUploader {
   int launches = 0;
   // w_off >= 0: byte offset of the float that goes to .w (intensity); otherwise .w = w_default
   void upload(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst, cudaStream_t s);
+  // batched form (no synchronisation between clouds): reserve once, then upload_at per cloud at its byte offset
+  void reserve(size_t raw_bytes, bool need_staging);
+  static bool is_pinned(const void* host);
+  void upload_at(const void* host, bool pinned, size_t n, size_t stride, long w_off, float w_default, float4* dst,
+                 size_t byte_offset, cudaStream_t s);
 };
 void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst, CloudUploader& up, cudaStream_t s);
 
@@ -150,6 +155,8 @@ void fitness_reduce(const float* d_d2, const int* d_idx, size_t n, double max_ra
 
 // ---- NDT solver (K1 fused derivative kernel inside a persistent cooperative Newton loop) ----------------
 struct NdtSolverWork;  // device-side work area, defined in ndt_solver.cu
+struct NdtJob;
+struct NdtLaunch;
 
 struct NdtResult {
   float final_T[16];  // row-major 4x4
@@ -179,6 +186,18 @@ class NdtSolver {
   // resume = 1 continues a solve that left the kernel for a K2 (radius Hessian) pass
   void launch(const VoxelMap& map, const float4* src, size_t n_src, const NdtConfig& cfg, int mode,
               const float* T_rowmajor16, const double* p6, int compute_hessian, int resume = 0);
+  // one registration of a batch: device-resident source (float4) and the row-major 4x4 guess
+  struct BatchItem {
+    const float4* src;
+    size_t n_src;
+    float T_rowmajor16[16];
+  };
+  // enqueue ONE launch that performs n independent registrations against `map`, `slots` (<= NDT_MAX_SLOTS) in flight;
+  // after the stream has drained batch_results()[k] holds registration k (error != 0: the kernel never finished it)
+  void launch_batch(const VoxelMap& map, const BatchItem* items, int n, const NdtConfig& cfg, int slots);
+  const NdtResult* batch_results() const { return h_batch_results_; }
+  // rounds one slot can run inside a launch (sequence numbers are 16 bits per launch)
+  static constexpr int kMaxRoundsPerLaunch = 60000;
   NdtSolverWork* work() const { return d_work_; }
   // device addresses of the controller's f64 angle tables / current transform (inputs of the K2 pass)
   const double* state_jd() const;
@@ -207,6 +226,12 @@ class NdtSolver {
   bool fits_checked_ = false;
   NdtSolverWork* d_work_ = nullptr;
   NdtResult* h_result_ = nullptr;  // pinned
+  NdtJob* d_jobs_ = nullptr;       // batch launches: job table on the device ...
+  NdtJob* h_jobs_ = nullptr;       // ... and its pinned host image
+  NdtResult* h_batch_results_ = nullptr;  // pinned + device-visible: the controllers write the results there
+  size_t jobs_cap_ = 0;
+  void fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& cfg, int mode, size_t& dyn_smem);
+  int eval_ctas_for(size_t n_src) const;
 };
 
 // off-hot-path f64 kernels (ndt_aux.cu)

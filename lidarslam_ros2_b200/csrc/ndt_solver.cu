@@ -370,7 +370,20 @@ struct CtlShared {
   unsigned code[72];  // shared-memory copy of kAngleTableCode
   int ready;          // per-round: bit w set once reducing warp w has summed all its partial rows
   unsigned long long t_warp[32];  // timing mode: when each reducing warp finished
+  // the registration this controller is working on (batch launches take new ones from NdtSolverWork::next_job)
+  int cur_job;     // index into NdtLaunch::jobs (0 for a single launch)
+  int cur_n_src;   // its source size (trans_probability = score / n_src)
+  int n_rows;      // evaluator CTAs that own points of it = partial rows to reduce
+  int job_done;    // batch: finish() ran this round — hand the result over and start the next registration
+  NdtResult result;  // batch: result under construction (copied to the mapped host array by the warp)
 };
+
+// evaluator CTAs that get points of a scan of n_src points: as soon as each gets at least four warps of points, all of
+// them (the evaluation is issue-bound per SM, so spreading thin beats filling CTAs)
+__host__ __device__ __forceinline__ int rows_for(int n_src, int n_eval_grid) {
+  const int want = (n_src + 127) / 128;
+  return max(1, min(want, n_eval_grid));
+}
 
 // ---- compact f64 helpers ------------------------------------------------------------------------------------
 // The controller runs ONCE per evaluation in ONE warp: its cost is the length of its dependent instruction chain
@@ -555,11 +568,12 @@ __device__ __forceinline__ void load_totals(NdtState& st, const double* tot, boo
 
 __device__ void finish(const NdtLaunch& L, CtlShared& cs, NdtSolverWork* W, int lane) {
   NdtState& st = cs.st;
+  const bool batch = L.jobs != nullptr;
   if (lane == 0) {
-    NdtResult& r = W->result;
+    NdtResult& r = batch ? cs.result : W->result;
     for (int k = 0; k < 16; k++) r.final_T[k] = st.final_T[k];
     r.score = st.score;
-    r.trans_probability = st.score / (double)L.n_src;  // ndt_omp_impl.hpp:136,170
+    r.trans_probability = st.score / (double)cs.cur_n_src;  // ndt_omp_impl.hpp:136,170
     for (int k = 0; k < 6; k++) r.g[k] = st.g[k];
     for (int k = 0; k < 36; k++) r.H[k] = st.H[k];
     r.hits_last = st.hits_last;
@@ -569,8 +583,55 @@ __device__ void finish(const NdtLaunch& L, CtlShared& cs, NdtSolverWork* W, int 
     r.evaluations = st.evaluations;
     r.error = 0;
   }
+  if (batch) {  // the warp hands the result over and takes the next registration (controller_cta)
+    cs.job_done = 1;
+    return;
+  }
   cs.next.mode = EVAL_DONE;
   cs.done = 1;
+}
+
+// batch launches, warp 0 of a controller CTA: take the next unassigned registration. Fills the solver state and
+// cs.next (the control block of its first evaluation); when the batch is exhausted the slot is retired (EVAL_DONE).
+__device__ __noinline__ void start_next_job(const NdtLaunch& L, CtlShared& cs, int lane, int n_eval_grid) {
+  unsigned job = 0;
+  if (lane == 0) job = atomicAdd(&L.work->next_job, 1u);
+  job = __shfl_sync(0xffffffffu, job, 0);
+  if ((int)job >= L.n_jobs) {
+    if (lane == 0) {
+      cs.next.mode = EVAL_DONE;
+      cs.done = 1;
+    }
+    __syncwarp();
+    return;
+  }
+  const NdtJob* J = L.jobs + job;
+  {
+    const unsigned* src = reinterpret_cast<const unsigned*>(&J->init);
+    unsigned* dst = reinterpret_cast<unsigned*>(&cs.next);
+    for (int k = lane; k < NDT_CONTROL_WORDS; k += 32) dst[k] = __ldg(src + k);
+  }
+  if (lane < 6) cs.st.p[lane] = J->p0[lane];
+  if (lane < 16) cs.st.final_T[lane] = J->init_final[lane];
+  __syncwarp();
+  if (lane == 0) {
+    NdtState& st = cs.st;
+    st.phase = PH_INITIAL;
+    st.nr_iterations = 0;
+    st.evaluations = 0;
+    st.converged = 0;
+    st.hits_total = 0;
+    st.hits_last = 0;
+    st.step_iterations = 0;
+    st.a_t = 0;
+    cs.next.mode = EVAL_DERIV;
+    cs.next.compute_hessian = 1;
+    cs.next.job = (int)job;
+    cs.cur_job = (int)job;
+    cs.cur_n_src = J->n_src;
+    cs.n_rows = rows_for(J->n_src, n_eval_grid);
+  }
+  __syncwarp();
 }
 
 // One controller step, executed by ONE thread (lane 0 of warp 0 of the controller CTA): consumes the totals of the
@@ -745,16 +806,20 @@ __device__ __noinline__ void controller(const NdtLaunch& L, CtlShared& cs, NdtSo
 // =====================================================================================================
 // controller CTA
 // =====================================================================================================
-__device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, double (*warp_part)[SLOT_COUNT], int n_eval_i) {
+__device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, double (*warp_part)[SLOT_COUNT], int n_eval_i,
+                                            int slot) {
   NdtSolverWork* W = L.work;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const unsigned n_eval = (unsigned)n_eval_i;
+  const bool batch = L.jobs != nullptr;
+  // sequence number of the control block published at the end of round r: single launches hand round 0's block over
+  // in the launch parameters, batch launches publish it (index 0) before the first reduction
+  const int pub_shift = batch ? 1 : 0;
   // state: fresh, or restored from global after a K2 pass
   if (L.resume) {
     const int* src = reinterpret_cast<const int*>(&W->state);
     int* dst = reinterpret_cast<int*>(&cs.st);
     for (int k = tid; k < (int)(sizeof(NdtState) / 4); k += SOLVER_THREADS) dst[k] = __ldcg(src + k);
-  } else if (tid == 0) {
+  } else if (tid == 0 && !batch) {
     NdtState& st = cs.st;
     for (int k = 0; k < 6; k++) st.p[k] = L.p0[k];
     for (int k = 0; k < 16; k++) st.final_T[k] = L.init_final[k];
@@ -771,9 +836,31 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
   if (tid == 0) {
     cs.done = 0;
     cs.ready = 0;
+    cs.job_done = 0;
+    cs.cur_job = 0;
+    cs.cur_n_src = L.n_src;
+    cs.n_rows = n_eval_i;
   }
   if (tid < 69) cs.code[tid] = kAngleTableCode[tid];
   __syncthreads();
+  unsigned long long* ctl_ll = &W->ctl_ll[slot][0][0];
+  auto publish = [&](int index) {  // warp 0: {payload, sequence} words, every replica
+    const unsigned* src = reinterpret_cast<const unsigned*>(&cs.next);
+    const unsigned long long seq = (unsigned long long)ctl_sequence(L.epoch, index) << 32;
+    for (int k = lane; k < NDT_CONTROL_WORDS; k += 32) {
+      const unsigned long long v = seq | src[k];
+#pragma unroll
+      for (int c = 0; c < NDT_CTL_COPIES; c++) st_relaxed_gpu_u64(ctl_ll + c * NDT_CTL_LL_WORDS + k, v);
+    }
+  };
+  if (batch) {  // first registration of this slot
+    if (warp == 0) {
+      start_next_job(L, cs, lane, n_eval_i);
+      publish(0);
+    }
+    __syncthreads();
+    if (cs.done) return;  // more slots than registrations
+  }
 
   const int all_ready = (1 << SOLVER_WARPS) - 2;
   for (int round = 0;; round++) {
@@ -782,13 +869,14 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
       // Warp w owns rows w-1, w-1+23, ... in batches of 16: one 16-byte load instruction covers TWO rows (lanes 0..15
       // the first, lanes 16..31 the second, two slots per lane), 8 in flight; the loads double as the arrival poll — a
       // slot still holding NDT_PARTIAL_EMPTY is simply re-loaded. Consumed rows are re-armed for round + 2.
-      double* buf = &W->partials[round & 1][0][0];
+      double* buf = &W->partials[slot][round & 1][0][0];
       const int half = lane >> 4, c2 = (lane & 15) * 2;
       const int stride = SOLVER_WARPS - 1;
+      const int n_rows = cs.n_rows;  // rows of the registration evaluated this round (stable until the end-of-round barrier)
       double s0 = 0, s1 = 0;
       bool failed = false;
       const long long t0 = clock64();
-      for (int base = 0; (warp - 1) + stride * base < (int)n_eval && !failed; base += 16) {
+      for (int base = 0; (warp - 1) + stride * base < n_rows && !failed; base += 16) {
         unsigned long long va[8], vb[8];
         unsigned pend = 0;
 #pragma unroll
@@ -796,7 +884,7 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
           const int row = (warp - 1) + stride * (base + 2 * u + half);
           va[u] = 0ull;  // bits of +0.0
           vb[u] = 0ull;
-          if (row < (int)n_eval) {
+          if (row < n_rows) {
             ld_relaxed_gpu_v2(buf + (size_t)row * SLOT_COUNT + c2, va[u], vb[u]);
             if (va[u] == NDT_PARTIAL_EMPTY || vb[u] == NDT_PARTIAL_EMPTY) pend |= 1u << u;
           }
@@ -838,7 +926,7 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
       if (lane == 0) atomicOr(&cs.ready, 1 << warp);
       // re-arm the consumed rows for round + 2 — after the flag, so that no fence of the signalling path has to wait
       // for these stores; they are performed before this warp meets the end-of-round barrier
-      for (int i = half; (warp - 1) + stride * i < (int)n_eval; i += 2) {
+      for (int i = half; (warp - 1) + stride * i < n_rows; i += 2) {
         const int row = (warp - 1) + stride * i;
         st_relaxed_gpu_v2(buf + (size_t)row * SLOT_COUNT + c2, NDT_PARTIAL_EMPTY, NDT_PARTIAL_EMPTY);
       }
@@ -888,22 +976,34 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
         B200_STAMP(lane == 0, round, 8);
         if (cs.build) build_control(cs, lane);
         B200_STAMP(lane == 0, round, 9);
-      }
-      __syncwarp();
-      {  // publish the next control block: {payload, sequence} words, every replica
-        const unsigned* src = reinterpret_cast<const unsigned*>(&cs.next);
-        const unsigned long long seq = (unsigned long long)ctl_sequence(L.epoch, round) << 32;
-        for (int k = lane; k < NDT_CONTROL_WORDS; k += 32) {
-          const unsigned long long v = seq | src[k];
-#pragma unroll
-          for (int c = 0; c < NDT_CTL_COPIES; c++) st_relaxed_gpu_u64(&W->ctl_ll[c][k], v);
+        __syncwarp();
+        if (batch && cs.job_done) {
+          // this registration is finished: its result goes straight to the mapped host array, the slot takes the next one
+          const int* src = reinterpret_cast<const int*>(&cs.result);
+          int* dst = reinterpret_cast<int*>(L.result_host + cs.cur_job);
+          for (int k = lane; k < (int)(sizeof(NdtResult) / 4); k += 32) dst[k] = src[k];
+          __syncwarp();
+          if (lane == 0) cs.job_done = 0;
+          start_next_job(L, cs, lane, n_eval_i);
+        } else if (batch && lane == 0) {
+          cs.next.job = cs.cur_job;
+          if (cs.done == 2) {  // a K2 pass cannot be served inside a batch launch (the host never batches such configurations)
+            cs.next.mode = EVAL_DONE;
+            cs.done = 3;
+          }
         }
       }
+      __syncwarp();
+      publish(round + pub_shift);
       B200_STAMP(lane == 0, round, 6);
       if (lane == 0) cs.ready = 0;
     }
     __syncthreads();
     if (cs.done) break;
+  }
+  if (batch) {
+    __threadfence_system();
+    return;
   }
   if (cs.done == 2) {  // leaving for a K2 pass: the next launch reads the control block from the work area
     const int* src = reinterpret_cast<const int*>(&cs.next);
@@ -938,20 +1038,27 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
   NdtSolverWork* W = L.work;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-  const int n_eval_ctas = (int)gridDim.x - 1;
-  if ((int)blockIdx.x == n_eval_ctas) {  // ---- the controller CTA (the last one) ----
+  const bool batch = L.jobs != nullptr;
+  const int n_slots = batch ? L.n_slots : 1;  // registrations in flight = controller CTAs (the last n_slots of the grid)
+  const int n_eval_ctas = (int)gridDim.x - n_slots;
+  if ((int)blockIdx.x >= n_eval_ctas) {  // ---- a controller CTA ----
     CtlShared& cs = *reinterpret_cast<CtlShared*>(dyn_smem);
-    controller_cta(L, cs, warp_part, n_eval_ctas);
+    controller_cta(L, cs, warp_part, n_eval_ctas, (int)blockIdx.x - n_eval_ctas);
     return;
   }
   const int my_rank = (int)blockIdx.x;
   if (L.timing && my_rank == 0 && tid == 0) W->timing[NDT_TIMING_ROUNDS - 1][0] = globaltimer_ns();  // kernel entry
 
   // ---- evaluator CTAs --------------------------------------------------------------------------------------
-  __shared__ __align__(16) NdtControl ctl;
+  // Every evaluator serves all slots in turn: while the controller of one registration reduces, solves and publishes,
+  // the evaluators are busy with the other registration's evaluation — the SM's issue slots no longer idle through
+  // the sequential part of a Newton round.
+  __shared__ __align__(16) NdtControl ctl_s[NDT_MAX_SLOTS];
   __shared__ int abort_flag;
   __shared__ __align__(8) unsigned long long tma_bar;
-  __shared__ float4 pts_s[SMEM_POINTS];
+  __shared__ float4 pts_s[NDT_MAX_SLOTS][SMEM_POINTS];
+  __shared__ const float4* slot_src[NDT_MAX_SLOTS];
+  __shared__ int slot_nsrc[NDT_MAX_SLOTS], slot_job[NDT_MAX_SLOTS];
   // dynamic shared memory: [rank index, L.acc_offset bytes][per-thread f32 accumulators]
   float (*acc_s)[ACC_STRIDE] = reinterpret_cast<float (*)[ACC_STRIDE]>(dyn_smem + L.acc_offset);
   const RankWord* idx = L.index_in_smem ? reinterpret_cast<const RankWord*>(dyn_smem) : L.index;
@@ -973,147 +1080,211 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
     }
   }
 
-  // This CTA's share of the source points, staged once into shared memory for the whole solve. The scan is dealt out
+  // This CTA's share of a scan, staged once into shared memory for the whole registration. The scan is dealt out
   // in units of 32 consecutive points (one warp's worth: consecutive points of a LiDAR ring are spatial neighbours and
-  // hit the same voxels, so a warp's record loads coalesce), unit u going to evaluator u mod n_eval: every CTA gets a
+  // hit the same voxels, so a warp's record loads coalesce), unit u going to evaluator u mod n_rows: every CTA gets a
   // mix of near and far rings, which evens out the per-CTA evaluation time (measured 2.3 .. 5.1 us with contiguous
   // chunks — the evaluation is issue-bound and the barrier waits for the slowest CTA).
   const int n_eval = n_eval_ctas;
-  const int n_units = (L.n_src + 31) >> 5;
-  const int my_units = (n_units > my_rank) ? (n_units - my_rank + n_eval - 1) / n_eval : 0;
-  const int n_local = my_units * 32;  // local slots (the last unit of the scan may be ragged)
-  auto global_index = [&](int j) { return (((j >> 5) * n_eval + my_rank) << 5) + (j & 31); };
-  const int n_staged = min(n_local, SMEM_POINTS);
-  for (int j = tid; j < n_staged; j += SOLVER_THREADS) {
-    const int gi = global_index(j);
-    pts_s[j] = (gi < L.n_src) ? L.src[gi] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding slot of the ragged last unit
-  }
-
+  auto stage_points = [&](int s, const float4* src, int n_src) {
+    const int n_rows = rows_for(n_src, n_eval);
+    if (my_rank >= n_rows) return;
+    const int n_units = (n_src + 31) >> 5;
+    const int my_units = (n_units > my_rank) ? (n_units - my_rank + n_rows - 1) / n_rows : 0;
+    const int n_staged = min(my_units * 32, SMEM_POINTS);
+    for (int j = tid; j < n_staged; j += SOLVER_THREADS) {  // thread tid later reads exactly the slots it writes here
+      const int gi = (((j >> 5) * n_rows + my_rank) << 5) + (j & 31);
+      pts_s[s][j] = (gi < n_src) ? src[gi] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding slot of the ragged last unit
+    }
+  };
+  if (tid < NDT_MAX_SLOTS) slot_job[tid] = -1;
   if (tid == 0) abort_flag = 0;
-  {  // round-0 control: from the launch parameters (fresh solve) or from the work area (resume after K2)
-    const int* src = L.resume ? reinterpret_cast<const int*>(&W->control) : reinterpret_cast<const int*>(&L.init);
-    int* dst = reinterpret_cast<int*>(&ctl);
-    for (int k = tid; k < NDT_CONTROL_WORDS; k += SOLVER_THREADS) dst[k] = L.resume ? __ldcg(src + k) : src[k];
-  }
+  if (!batch) stage_points(0, L.src, L.n_src);
+
   if (L.index_in_smem) {
     long long t0 = clock64();
     while (!mbar_try_wait(&tma_bar, 0)) {
-      if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) break;
+      if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {  // a partially staged index must never be evaluated
+        W->result.error = 1;
+        abort_flag = 1;
+        break;
+      }
     }
   }
   if (L.timing && my_rank == 0 && tid == 0) W->timing[NDT_TIMING_ROUNDS - 1][1] = globaltimer_ns();  // prologue done
   bool skip_eval = L.resume != 0;
   const bool stamp0 = (my_rank == 0 && tid == 0);
   const float gd2 = (float)L.d2;
+  const int pub_shift = batch ? 1 : 0;  // see controller_cta
 
-  for (int round = 0;; round++) {
+  int rounds[NDT_MAX_SLOTS];
+  bool alive[NDT_MAX_SLOTS];
+#pragma unroll
+  for (int k = 0; k < NDT_MAX_SLOTS; k++) {
+    rounds[k] = 0;
+    alive[k] = k < n_slots;
+  }
+  int n_alive = n_slots;
+  for (int s = 0; n_alive > 0; s = (s + 1 >= n_slots) ? 0 : s + 1) {
+    int round = 0;
+    bool live = false;
+#pragma unroll
+    for (int k = 0; k < NDT_MAX_SLOTS; k++)
+      if (k == s) {
+        round = rounds[k];
+        live = alive[k];
+      }
+    if (!live) continue;
+
+    // ---- (0) the control block of (slot s, round): from the launch parameters (single launch, round 0) or from the
+    // slot's controller CTA — thread k polls word k until it carries the expected sequence number (one 64-bit load
+    // brings payload and validity together) -----------------------------------------------------------------------
+    if (tid < NDT_CONTROL_WORDS) {
+      unsigned payload;
+      if (!batch && round == 0) {
+        const int* src = L.resume ? reinterpret_cast<const int*>(&W->control) : reinterpret_cast<const int*>(&L.init);
+        payload = (unsigned)(L.resume ? __ldcg(src + tid) : src[tid]);
+      } else {
+        const unsigned long long* wsrc = &W->ctl_ll[s][my_rank % NDT_CTL_COPIES][tid];
+        const unsigned want = ctl_sequence(L.epoch, round - 1 + pub_shift);
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+          v = ld_relaxed_gpu_u64(wsrc);
+          if ((unsigned)(v >> 32) == want) break;
+          if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
+            W->result.error = 1;
+            abort_flag = 1;
+            break;
+          }
+        }
+        payload = (unsigned)v;
+      }
+      reinterpret_cast<unsigned*>(&ctl_s[s])[tid] = payload;
+      if (round > 0) B200_STAMP(stamp0, round - 1, 7);
+    }
     __syncthreads();
-    if (ctl.mode != EVAL_DERIV || abort_flag) break;
+    const NdtControl& ctl = ctl_s[s];
+    if (ctl.mode != EVAL_DERIV || abort_flag) {  // this slot is finished (or the watchdog fired)
+#pragma unroll
+      for (int k = 0; k < NDT_MAX_SLOTS; k++)
+        if (k == s) alive[k] = false;
+      n_alive--;
+      continue;
+    }
     B200_STAMP(stamp0, round, 0);
     const unsigned long long t_round = (L.timing && tid == 0) ? globaltimer_ns() : 0ull;
 
-    // ---- (1) evaluate this CTA's points ---------------------------------------------------------------
-    Accum acc;
-    acc.s = acc_s;
-    acc.tid = tid;
-    acc.first = true;
-    acc.score = 0.0;
-    acc.hits = 0;
-    if (!skip_eval) {
-      if (ctl.compute_hessian) {
-        for (int j = tid; j < n_staged; j += SOLVER_THREADS) {
-          if (global_index(j) < L.n_src) process_point<METHOD, true>(L, ctl, idx, pts_s[j], gd2, acc);
-        }
-        for (int j = SMEM_POINTS + tid; j < n_local; j += SOLVER_THREADS) {
-          const int gi = global_index(j);
-          if (gi < L.n_src) process_point<METHOD, true>(L, ctl, idx, L.src[gi], gd2, acc);
-        }
-      } else {
-        for (int j = tid; j < n_staged; j += SOLVER_THREADS) {
-          if (global_index(j) < L.n_src) process_point<METHOD, false>(L, ctl, idx, pts_s[j], gd2, acc);
-        }
-        for (int j = SMEM_POINTS + tid; j < n_local; j += SOLVER_THREADS) {
-          const int gi = global_index(j);
-          if (gi < L.n_src) process_point<METHOD, false>(L, ctl, idx, L.src[gi], gd2, acc);
+    // ---- (0b) batch: a new registration on this slot — restage its points ----------------------------------------
+    if (batch && ctl.job != slot_job[s]) {
+      __syncthreads();  // everybody has compared before the entry changes
+      if (tid == 0) {
+        const NdtJob* J = L.jobs + ctl.job;
+        slot_job[s] = ctl.job;
+        slot_src[s] = J->src;
+        slot_nsrc[s] = J->n_src;
+      }
+      __syncthreads();
+      stage_points(s, slot_src[s], slot_nsrc[s]);
+    }
+    const float4* __restrict__ src = batch ? slot_src[s] : L.src;
+    const int n_src = batch ? slot_nsrc[s] : L.n_src;
+    const int n_rows = rows_for(n_src, n_eval);
+    const bool active = my_rank < n_rows;  // small scans are spread over fewer evaluators (rows_for)
+    const int n_units = (n_src + 31) >> 5;
+    const int my_units = (active && n_units > my_rank) ? (n_units - my_rank + n_rows - 1) / n_rows : 0;
+    const int n_local = my_units * 32;  // local slots (the last unit of the scan may be ragged)
+    auto global_index = [&](int j) { return (((j >> 5) * n_rows + my_rank) << 5) + (j & 31); };
+    const int n_staged = min(n_local, SMEM_POINTS);
+    const float4* pts = pts_s[s];
+
+    if (active) {
+      // ---- (1) evaluate this CTA's points ---------------------------------------------------------------
+      Accum acc;
+      acc.s = acc_s;
+      acc.tid = tid;
+      acc.first = true;
+      acc.score = 0.0;
+      acc.hits = 0;
+      if (!skip_eval) {
+        if (ctl.compute_hessian) {
+          for (int j = tid; j < n_staged; j += SOLVER_THREADS) {
+            if (global_index(j) < n_src) process_point<METHOD, true>(L, ctl, idx, pts[j], gd2, acc);
+          }
+          for (int j = SMEM_POINTS + tid; j < n_local; j += SOLVER_THREADS) {
+            const int gi = global_index(j);
+            if (gi < n_src) process_point<METHOD, true>(L, ctl, idx, src[gi], gd2, acc);
+          }
+        } else {
+          for (int j = tid; j < n_staged; j += SOLVER_THREADS) {
+            if (global_index(j) < n_src) process_point<METHOD, false>(L, ctl, idx, pts[j], gd2, acc);
+          }
+          for (int j = SMEM_POINTS + tid; j < n_local; j += SOLVER_THREADS) {
+            const int gi = global_index(j);
+            if (gi < n_src) process_point<METHOD, false>(L, ctl, idx, src[gi], gd2, acc);
+          }
         }
       }
+      B200_STAMP(stamp0, round, 1);
+      if (L.timing && tid == 0 && round == 2) {
+        W->cta_eval_ns[my_rank][0] = (unsigned)t_round;
+        W->cta_eval_ns[my_rank][1] = (unsigned)globaltimer_ns();
+      }
+
+      // ---- (2) per-warp reduction: lane L sums slot L over the warp's 32 columns in fixed order (f64), CTA partial --
+      if (acc.first) {
+#pragma unroll
+        for (int k = 0; k < ACC_SLOTS; k++) acc_s[k][tid] = 0.f;
+      }
+      double sc = acc.score, hc = (double)acc.hits;
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) {
+        sc += __shfl_xor_sync(0xffffffffu, sc, d);
+        hc += __shfl_xor_sync(0xffffffffu, hc, d);
+      }
+      __syncwarp();
+      {
+        double v = 0.0;
+        if (lane >= SLOT_G && lane < SLOT_G + ACC_SLOTS) {
+          const float* row = &acc_s[lane - SLOT_G][warp * 32];
+          double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // four independent chains, fixed order
+#pragma unroll
+          for (int t = 0; t < 32; t += 4) {
+            v0 += (double)row[t];
+            v1 += (double)row[t + 1];
+            v2 += (double)row[t + 2];
+            v3 += (double)row[t + 3];
+          }
+          v = (v0 + v1) + (v2 + v3);
+        } else if (lane == SLOT_SCORE) {
+          v = sc;
+        } else if (lane == SLOT_HITS) {
+          v = hc;
+        }
+        warp_part[warp][lane] = v;
+      }
+      __syncthreads();
+      if (tid < SLOT_COUNT) {  // warp 0: one plain 8-byte store per slot; a written slot can never equal NDT_PARTIAL_EMPTY
+        double sa = 0, sb = 0, sc2 = 0, sd = 0;  // four independent chains, fixed order
+#pragma unroll
+        for (int w = 0; w < SOLVER_WARPS; w += 4) {
+          sa += warp_part[w][tid];
+          sb += warp_part[w + 1][tid];
+          sc2 += warp_part[w + 2][tid];
+          sd += warp_part[w + 3][tid];
+        }
+        const double sum = (sa + sb) + (sc2 + sd);
+        st_relaxed_gpu_u64(reinterpret_cast<unsigned long long*>(&W->partials[s][round & 1][my_rank][tid]),
+                           (unsigned long long)__double_as_longlong(sum));
+        if (L.timing && round == 2 && tid == 0) W->cta_eval_ns[my_rank][2] = (unsigned)globaltimer_ns();
+      }
+      B200_STAMP(stamp0, round, 2);
+      B200_STAMP(stamp0, round, 3);
     }
     skip_eval = false;
-    B200_STAMP(stamp0, round, 1);
-    if (L.timing && tid == 0 && round == 2) {
-      W->cta_eval_ns[my_rank][0] = (unsigned)t_round;
-      W->cta_eval_ns[my_rank][1] = (unsigned)globaltimer_ns();
-    }
-
-    // ---- (2) per-warp reduction: lane L sums slot L over the warp's 32 columns in fixed order (f64), CTA partial --
-    if (acc.first) {
 #pragma unroll
-      for (int k = 0; k < ACC_SLOTS; k++) acc_s[k][tid] = 0.f;
-    }
-    double sc = acc.score, hc = (double)acc.hits;
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      sc += __shfl_xor_sync(0xffffffffu, sc, d);
-      hc += __shfl_xor_sync(0xffffffffu, hc, d);
-    }
-    __syncwarp();
-    {
-      double v = 0.0;
-      if (lane >= SLOT_G && lane < SLOT_G + ACC_SLOTS) {
-        const float* row = &acc_s[lane - SLOT_G][warp * 32];
-        double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // four independent chains, fixed order
-#pragma unroll
-        for (int t = 0; t < 32; t += 4) {
-          v0 += (double)row[t];
-          v1 += (double)row[t + 1];
-          v2 += (double)row[t + 2];
-          v3 += (double)row[t + 3];
-        }
-        v = (v0 + v1) + (v2 + v3);
-      } else if (lane == SLOT_SCORE) {
-        v = sc;
-      } else if (lane == SLOT_HITS) {
-        v = hc;
-      }
-      warp_part[warp][lane] = v;
-    }
-    __syncthreads();
-    if (tid < SLOT_COUNT) {  // warp 0: one plain 8-byte store per slot; a written slot can never equal NDT_PARTIAL_EMPTY
-      double sa = 0, sb = 0, sc2 = 0, sd = 0;  // four independent chains, fixed order
-#pragma unroll
-      for (int w = 0; w < SOLVER_WARPS; w += 4) {
-        sa += warp_part[w][tid];
-        sb += warp_part[w + 1][tid];
-        sc2 += warp_part[w + 2][tid];
-        sd += warp_part[w + 3][tid];
-      }
-      const double s = (sa + sb) + (sc2 + sd);
-      st_relaxed_gpu_u64(reinterpret_cast<unsigned long long*>(&W->partials[round & 1][my_rank][tid]),
-                         (unsigned long long)__double_as_longlong(s));
-      if (L.timing && round == 2 && tid == 0) W->cta_eval_ns[my_rank][2] = (unsigned)globaltimer_ns();
-    }
-    B200_STAMP(stamp0, round, 2);
-    B200_STAMP(stamp0, round, 3);
-
-    // ---- (3) wait for the controller CTA's next control block: thread k polls word k until it carries this round's
-    // sequence number (one 64-bit load brings payload and validity together) ---------------------------------------
-    if (tid < NDT_CONTROL_WORDS) {
-      const unsigned long long* wsrc = &W->ctl_ll[my_rank % NDT_CTL_COPIES][tid];
-      const unsigned want = ctl_sequence(L.epoch, round);
-      const long long t0 = clock64();
-      unsigned long long v;
-      for (;;) {
-        v = ld_relaxed_gpu_u64(wsrc);
-        if ((unsigned)(v >> 32) == want) break;
-        if (clock64() - t0 > SPIN_TIMEOUT_CYCLES) {
-          W->result.error = 1;
-          abort_flag = 1;
-          break;
-        }
-      }
-      reinterpret_cast<unsigned*>(&ctl)[tid] = (unsigned)v;
-      B200_STAMP(stamp0, round, 7);
-    }
+    for (int k = 0; k < NDT_MAX_SLOTS; k++)
+      if (k == s) rounds[k] = round + 1;
   }
 }
 
@@ -1139,6 +1310,9 @@ KernelFn kernel_for(int method) {
 NdtSolver::~NdtSolver() {
   if (d_work_) cudaFree(d_work_);
   if (h_result_) cudaFreeHost(h_result_);
+  if (d_jobs_) cudaFree(d_jobs_);
+  if (h_jobs_) cudaFreeHost(h_jobs_);
+  if (h_batch_results_) cudaFreeHost(h_batch_results_);
 }
 
 void NdtSolver::init(int device, cudaStream_t s) {
@@ -1150,8 +1324,8 @@ void NdtSolver::init(int device, cudaStream_t s) {
   max_smem_optin_ = (int)prop.sharedMemPerBlockOptin;
   B200_CUDA(cudaMalloc(&d_work_, sizeof(NdtSolverWork)));
   B200_CUDA(cudaMemset(d_work_, 0, sizeof(NdtSolverWork)));
-  arm_partials_kernel<<<296, 256>>>(reinterpret_cast<unsigned long long*>(&d_work_->partials[0][0][0]),
-                                    (size_t)2 * NDT_MAX_CTAS * SLOT_COUNT);
+  arm_partials_kernel<<<296, 256>>>(reinterpret_cast<unsigned long long*>(&d_work_->partials[0][0][0][0]),
+                                    (size_t)NDT_MAX_SLOTS * 2 * NDT_MAX_CTAS * SLOT_COUNT);
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaDeviceSynchronize());
   B200_CUDA(cudaMallocHost(&h_result_, sizeof(NdtResult)));
@@ -1179,49 +1353,19 @@ void NdtSolver::fetch_result() {  // slow path: the kernel did not get to write 
 void NdtSolver::reset_barrier() {
   // after a watchdog abort: clear the error word, re-arm every partial slot and the role-election counters
   B200_CUDA(cudaMemsetAsync(d_work_, 0, 16, stream_));
-  arm_partials_kernel<<<296, 256, 0, stream_>>>(reinterpret_cast<unsigned long long*>(&d_work_->partials[0][0][0]),
-                                                (size_t)2 * NDT_MAX_CTAS * SLOT_COUNT);
+  arm_partials_kernel<<<296, 256, 0, stream_>>>(reinterpret_cast<unsigned long long*>(&d_work_->partials[0][0][0][0]),
+                                                (size_t)NDT_MAX_SLOTS * 2 * NDT_MAX_CTAS * SLOT_COUNT);
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaStreamSynchronize(stream_));
 }
 
-void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, const NdtConfig& cfg, int mode,
-                       const float* T_rowmajor16, const double* p6, int compute_hessian, int resume) {
-  NdtLaunch L{};
-  L.src = src;
-  L.index = map.index.ptr;
-  L.records = map.records.ptr;
-  L.icov_d = map.icov_d.ptr;
-  L.centroids = map.centroids.ptr;
-  L.work = d_work_;
-  L.result_host = h_result_;
-  h_result_->error = 3;  // "the kernel never wrote a result"
-  L.geom = map.geom;
-  L.n_src = (int)n_src;
-  L.n_voxels = (int)map.n_voxels;
-  L.search_method = cfg.search_method;
-  L.mode = mode;
-  L.resume = resume;
-  L.timing = timing_enabled ? 1 : 0;
-  L.scalar_controller = scalar_controller ? 1 : 0;
-  L.epoch = epoch_++;
-  L.max_iterations = cfg.max_iterations;
-  L.resolution = cfg.resolution;
-  L.radius2 = static_cast<float>((double)cfg.resolution * (double)cfg.resolution);
-  GaussConsts gc = gauss_constants(cfg.outlier_ratio, cfg.resolution);
-  L.d1 = gc.d1;
-  L.d2 = gc.d2;
-  L.d3 = gc.d3;
-  L.step_size = cfg.step_size;
-  L.trans_eps = cfg.trans_eps;
-
-  // initial pose: final_transformation_ = guess (or identity), p = (t, eulerAngles(0,1,2)) in float → double
-  // (ndt_omp_impl.hpp:95-111); the first evaluation transforms the source by the guess matrix itself.
-  float T[16];
-  std::memcpy(T, T_rowmajor16, sizeof(T));
-  std::memcpy(L.init_final, T, sizeof(T));
-  for (int k = 0; k < 12; k++) L.init.T[k] = T[k];
-  double p0[6];
+namespace {
+// pose parameters and first control block of a registration that starts at the (row-major) guess T:
+// final_transformation_ = guess (or identity), p = (t, eulerAngles(0,1,2)) in float -> double
+// (ndt_omp_impl.hpp:95-111); the first evaluation transforms the source by the guess matrix itself.
+void initial_pose(const float* T, const double* p6, double* p0, float* init_final, NdtControl& init, int compute_hessian) {
+  std::memcpy(init_final, T, 16 * sizeof(float));
+  for (int k = 0; k < 12; k++) init.T[k] = T[k];
   if (p6) {
     for (int k = 0; k < 6; k++) p0[k] = p6[k];
   } else {
@@ -1235,41 +1379,133 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
     p0[4] = ang[1];
     p0[5] = ang[2];
   }
-  for (int k = 0; k < 6; k++) L.p0[k] = p0[k];
-  angle_tables(p0, L.init.jang, L.init.hang, nullptr, nullptr);
-  L.init.mode = EVAL_DERIV;
-  L.init.compute_hessian = compute_hessian;
+  angle_tables(p0, init.jang, init.hang, nullptr, nullptr);
+  init.mode = EVAL_DERIV;
+  init.compute_hessian = compute_hessian;
+  init.job = 0;
+  init.pad = 0;
+}
+}  // namespace
 
+void NdtSolver::fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& cfg, int mode, size_t& dyn_smem) {
+  L.index = map.index.ptr;
+  L.records = map.records.ptr;
+  L.icov_d = map.icov_d.ptr;
+  L.centroids = map.centroids.ptr;
+  L.work = d_work_;
+  L.geom = map.geom;
+  L.n_voxels = (int)map.n_voxels;
+  L.search_method = cfg.search_method;
+  L.mode = mode;
+  L.timing = timing_enabled ? 1 : 0;
+  L.scalar_controller = scalar_controller ? 1 : 0;
+  L.epoch = epoch_++;
+  L.max_iterations = cfg.max_iterations;
+  L.resolution = cfg.resolution;
+  L.radius2 = static_cast<float>((double)cfg.resolution * (double)cfg.resolution);
+  GaussConsts gc = gauss_constants(cfg.outlier_ratio, cfg.resolution);
+  L.d1 = gc.d1;
+  L.d2 = gc.d2;
+  L.d3 = gc.d3;
+  L.step_size = cfg.step_size;
+  L.trans_eps = cfg.trans_eps;
   // dynamic shared memory: the rank index when it fits (<= 64 KB), then the per-thread accumulators; the controller
-  // CTA overlays its own state on the same bytes
+  // CTAs overlay their own state on the same bytes
   const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 127) & ~(size_t)127;
   L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= (size_t)SOLVER_MAX_INDEX_SMEM) ? 1 : 0;
   L.acc_offset = L.index_in_smem ? (int)index_bytes : 0;
-  size_t dyn_smem = std::max((size_t)L.acc_offset + ACC_BYTES, sizeof(CtlShared));
+  dyn_smem = std::max((size_t)L.acc_offset + ACC_BYTES, sizeof(CtlShared));
   dyn_smem = (dyn_smem + 127) & ~(size_t)127;
-
-  KernelFn fn = kernel_for(cfg.search_method);
+  index_in_smem_ = L.index_in_smem;
   if (!fits_checked_) {  // the largest configuration (64 KB index + accumulators) fits or nothing does
     int per_sm = 0;
-    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, SOLVER_THREADS, SOLVER_MAX_DYN_SMEM));
+    B200_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel_for(cfg.search_method), SOLVER_THREADS,
+                                                            SOLVER_MAX_DYN_SMEM));
     if (per_sm < 1) throw CudaError("ndt_solver_kernel does not fit on an SM");
     fits_checked_ = true;
   }
-  const int max_ctas = std::min(sm_count_, NDT_MAX_CTAS);  // one CTA per SM, all co-resident (cooperative launch)
-  // evaluator CTAs: every SM but the controller's as soon as each gets at least four warps of points (the evaluation
-  // is issue-bound per SM, so spreading thin beats filling CTAs)
-  const int want = (int)((n_src + 127) / 128);
-  const int n_eval = std::max(1, std::min(want, max_ctas - 1));
-  grid_ = n_eval + 1;  // + the controller CTA
-  block_ = SOLVER_THREADS;
-  index_in_smem_ = L.index_in_smem;
+}
 
+int NdtSolver::eval_ctas_for(size_t n_src) const {
+  // one CTA per SM, all co-resident (cooperative launch); NDT_MAX_SLOTS SMs are left to controller CTAs in EVERY launch
+  // so that single and batched registrations partition a scan identically (bitwise-equal results)
+  const int max_ctas = std::min(sm_count_, NDT_MAX_CTAS);
+  return rows_for((int)n_src, std::max(1, max_ctas - NDT_MAX_SLOTS));
+}
+
+void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, const NdtConfig& cfg, int mode,
+                       const float* T_rowmajor16, const double* p6, int compute_hessian, int resume) {
+  NdtLaunch L{};
+  size_t dyn_smem = 0;
+  fill_common(L, map, cfg, mode, dyn_smem);
+  L.src = src;
+  L.result_host = h_result_;
+  h_result_->error = 3;  // "the kernel never wrote a result"
+  L.jobs = nullptr;
+  L.n_jobs = 1;
+  L.n_slots = 1;
+  L.n_src = (int)n_src;
+  L.resume = resume;
+  initial_pose(T_rowmajor16, p6, L.p0, L.init_final, L.init, compute_hessian);
+
+  grid_ = eval_ctas_for(n_src) + 1;  // + the controller CTA
+  block_ = SOLVER_THREADS;
+  KernelFn fn = kernel_for(cfg.search_method);
   void* args[] = {&L};
   if (plain_launch) {  // developer switch: measure what the cooperative launch costs
     B200_CUDA(cudaLaunchKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
   } else {
     B200_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
   }
+  launches += 1;
+}
+
+// K independent registrations against the same voxel map in ONE cooperative launch, NDT_MAX_SLOTS of them in flight:
+// while one registration's controller CTA reduces / solves / publishes, the evaluator CTAs work on the other one.
+// Results land in the mapped host array batch_results()[0..n) once the stream has drained.
+void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n, const NdtConfig& cfg, int slots) {
+  if (n <= 0) return;
+  if ((size_t)n > jobs_cap_) {
+    if (d_jobs_) cudaFree(d_jobs_);
+    if (h_jobs_) cudaFreeHost(h_jobs_);
+    if (h_batch_results_) cudaFreeHost(h_batch_results_);
+    d_jobs_ = nullptr;
+    h_jobs_ = nullptr;
+    h_batch_results_ = nullptr;
+    jobs_cap_ = 0;
+    const size_t cap = (size_t)n + 16;
+    B200_CUDA(cudaMalloc(&d_jobs_, cap * sizeof(NdtJob)));
+    B200_CUDA(cudaMallocHost(&h_jobs_, cap * sizeof(NdtJob)));
+    B200_CUDA(cudaMallocHost(&h_batch_results_, cap * sizeof(NdtResult)));
+    jobs_cap_ = cap;
+  }
+  size_t n_max = 0;
+  for (int k = 0; k < n; k++) {
+    NdtJob& J = h_jobs_[k];
+    std::memset(&J, 0, sizeof(J));
+    J.src = items[k].src;
+    J.n_src = (int)items[k].n_src;
+    initial_pose(items[k].T_rowmajor16, nullptr, J.p0, J.init_final, J.init, 1);
+    J.init.job = k;
+    n_max = std::max(n_max, items[k].n_src);
+    h_batch_results_[k].error = 3;  // "the kernel never wrote a result"
+  }
+  B200_CUDA(cudaMemcpyAsync(d_jobs_, h_jobs_, (size_t)n * sizeof(NdtJob), cudaMemcpyHostToDevice, stream_));
+  B200_CUDA(cudaMemsetAsync(&d_work_->next_job, 0, sizeof(unsigned), stream_));
+  NdtLaunch L{};
+  size_t dyn_smem = 0;
+  fill_common(L, map, cfg, NDT_MODE_ALIGN, dyn_smem);
+  L.timing = 0;
+  L.result_host = h_batch_results_;
+  L.jobs = d_jobs_;
+  L.n_jobs = n;
+  L.n_slots = std::max(1, std::min(std::min(slots, NDT_MAX_SLOTS), n));
+  L.n_src = (int)n_max;
+  grid_ = eval_ctas_for(n_max) + L.n_slots;
+  block_ = SOLVER_THREADS;
+  KernelFn fn = kernel_for(cfg.search_method);
+  void* args[] = {&L};
+  B200_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
   launches += 1;
 }
 

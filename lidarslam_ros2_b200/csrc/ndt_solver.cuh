@@ -6,6 +6,10 @@
 namespace b200 {
 
 constexpr int NDT_MAX_CTAS = 256;  // one CTA per SM
+// Registrations in flight inside one batch launch = controller CTAs. Every launch (single or batched) leaves this many
+// SMs to controllers, so that the evaluator count — and with it the point partition and the fixed summation order —
+// is the same for b200reg_align and for b200reg_ndt_align_batch: a batched result is bitwise the single-align result.
+constexpr int NDT_MAX_SLOTS = 2;
 
 enum EvalMode : int {
   EVAL_DERIV = 0,        // fused derivative pass (K1)
@@ -22,7 +26,8 @@ struct NdtControl {
   float hang[45];  // 15 x 3 f32 angle-Hessian table    (ndt_omp_impl.hpp:371-391)
   int mode;        // EvalMode
   int compute_hessian;
-  int pad[2];
+  int job;         // batch launches: index of the registration this block belongs to (evaluators restage on a change)
+  int pad;
 };
 constexpr int NDT_CONTROL_WORDS = sizeof(NdtControl) / 4;
 
@@ -55,14 +60,25 @@ constexpr int NDT_CTL_LL_WORDS = 96;  // >= NDT_CONTROL_WORDS, whole 128-byte li
 constexpr unsigned long long NDT_PARTIAL_EMPTY = 0xFFF8DEADFFF8DEADull;
 constexpr int NDT_MAX_ROUNDS = 60000;  // sequence numbers are epoch * 65536 + round + 1
 
+// one registration of a batch launch (device array, filled by the host before the launch)
+struct NdtJob {
+  const float4* src;
+  int n_src;
+  int pad;
+  double p0[6];         // initial pose parameters (ndt_omp_impl.hpp:103-111)
+  float init_final[16]; // final_transformation_ = guess
+  NdtControl init;      // control block of the first evaluation (transform = guess, angle tables at p0)
+};
+
 struct NdtSolverWork {
   unsigned error;
-  unsigned pad[3];
+  unsigned next_job;     // batch launches: next unassigned registration (atomicAdd by the controllers)
+  unsigned pad[2];
   NdtControl control;    // plain copy of the control block, written only when the kernel leaves for a K2 pass
   NdtState state;
   NdtResult result;
-  alignas(128) unsigned long long ctl_ll[NDT_CTL_COPIES][NDT_CTL_LL_WORDS];
-  alignas(128) double partials[2][NDT_MAX_CTAS][SLOT_COUNT];
+  alignas(128) unsigned long long ctl_ll[NDT_MAX_SLOTS][NDT_CTL_COPIES][NDT_CTL_LL_WORDS];
+  alignas(128) double partials[NDT_MAX_SLOTS][2][NDT_MAX_CTAS][SLOT_COUNT];
   unsigned long long timing[NDT_TIMING_ROUNDS][NDT_TIMING_SLOTS];
   unsigned cta_eval_ns[NDT_MAX_CTAS][4];  // timing mode, round 2, low 32 bits of globaltimer: start, evaluate end, published
 };
@@ -75,6 +91,11 @@ struct NdtLaunch {
   const float4* centroids;
   NdtSolverWork* work;
   NdtResult* result_host;  // pinned, device-visible host memory: the controller CTA writes the result there on exit
+  // batch launches (n_slots >= 1 and jobs != nullptr): n_jobs registrations against the same map, n_slots in flight;
+  // result_host is then an array of n_jobs results. jobs == nullptr: the single registration described inline below.
+  const NdtJob* jobs;
+  int n_jobs;
+  int n_slots;
   GridGeom geom;
   int n_src;
   int n_voxels;

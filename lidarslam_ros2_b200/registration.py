@@ -192,6 +192,48 @@ class NormalDistributionsTransform(_Registration):
         self._check(self._lib.b200reg_ndt_calculate_score(self._h, _ptr(c), len(c), c.strides[0], C.byref(v)))
         return v.value
 
+    # ---- batched registrations against the current target (one persistent launch, two in flight) ----
+    def _batch_out(self, res, K):
+        T = np.stack([_from_colmajor(np.frombuffer(res[k].final_T, dtype=np.float32).copy()) for k in range(K)]) if K else \
+            np.zeros((0, 4, 4), dtype=np.float32)
+        return {"pose": T,
+                "converged": np.array([res[k].converged for k in range(K)], dtype=np.int32),
+                "iterations": np.array([res[k].iterations for k in range(K)], dtype=np.int32),
+                "evaluations": np.array([res[k].evaluations for k in range(K)], dtype=np.int32),
+                "trans_probability": np.array([res[k].trans_probability for k in range(K)]),
+                "hits_total": np.array([res[k].hits_total for k in range(K)], dtype=np.int64),
+                "status": np.array([res[k].status for k in range(K)], dtype=np.int32)}
+
+    def alignBatch(self, clouds, guesses=None) -> dict:
+        """K independent align() calls against the current target, sources in HOST memory (b200reg_ndt_align_batch).
+        clouds: list of (N_k, >=3) float32 arrays with equal row stride; guesses: list of 4x4 or None (identity)."""
+        K = len(clouds)
+        cs = [_as_cloud(c) for c in clouds]
+        stride = cs[0].strides[0] if K else 16
+        if any(c.strides[0] != stride for c in cs):
+            raise ValueError("alignBatch: all clouds must share one row stride")
+        ptrs = (C.c_void_p * K)(*[c.ctypes.data for c in cs])
+        ns = (C.c_size_t * K)(*[len(c) for c in cs])
+        g = np.ascontiguousarray(np.stack([_colmajor(x) for x in guesses])) if guesses is not None else None
+        res = (_capi.BatchResult * max(K, 1))()
+        rc = self._lib.b200reg_ndt_align_batch(self._h, K, ptrs, ns, stride, _ptr(g) if g is not None else None, res)
+        self._check(rc, soft=(_capi.ERR_NO_TARGET,))
+        return self._batch_out(res, K)
+
+    def alignBatchDevice(self, dev_ptrs, counts, guesses=None) -> dict:
+        """Same with the sources already in HBM as float4 buffers (b200reg_ndt_align_batch_device), read in place."""
+        K = len(dev_ptrs)
+        ptrs = (C.c_void_p * K)(*[int(p) for p in dev_ptrs])
+        ns = (C.c_size_t * K)(*[int(n) for n in counts])
+        g = np.ascontiguousarray(np.stack([_colmajor(x) for x in guesses])) if guesses is not None else None
+        res = (_capi.BatchResult * max(K, 1))()
+        rc = self._lib.b200reg_ndt_align_batch_device(self._h, K, ptrs, ns, _ptr(g) if g is not None else None, res)
+        self._check(rc, soft=(_capi.ERR_NO_TARGET,))
+        return self._batch_out(res, K)
+
+    def setBatchSlots(self, slots: int):
+        self._check(self._lib.b200reg_ndt_set_batch_slots(self._h, int(slots)))
+
     # ---- parity hooks ----
     def derivatives(self, T, p6, compute_hessian: bool = True):
         """One fused derivative pass (computeDerivatives, ndt_omp_impl.hpp:179-284) → (score, g[6], H[6,6])."""

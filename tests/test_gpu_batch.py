@@ -1,0 +1,155 @@
+"""GPU tests of the batched NDT entry points (b200reg_ndt_align_batch / _device, b200reg_align_batch) and of
+b200reg_get_aligned. A batched registration must be BITWISE the registration b200reg_align performs for the same
+(source, guess): the batch kernel keeps the point partition and every summation order of the single launch."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def b200():
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.fail("no CUDA device: the gpu tests must run on the B200 box (there is no CPU fallback)")
+    import lidarslam_ros2_b200 as m
+
+    return m
+
+
+def _engine(m, tgt, res=2.0, max_it=35):
+    g = m.NormalDistributionsTransform()
+    g.setResolution(res)
+    g.setTransformationEpsilon(0.01)
+    g.setMaximumIterations(max_it)
+    g.setNeighborhoodSearchMethod(m.DIRECT7)
+    g.setInputTarget(tgt)
+    return g
+
+
+def _scans_and_guesses(src, n):
+    """n different (scan, guess) problems from one scan: sub-sampled / perturbed copies and perturbed guesses."""
+    from lidarslam_ros2_b200 import synth
+
+    rng = np.random.default_rng(7)
+    scans, guesses = [], []
+    d = np.pi / 180
+    for k in range(n):
+        keep = rng.random(len(src)) < (1.0 - 0.07 * (k % 4))  # ragged sizes
+        s = src[keep].copy()
+        s[:, :3] += rng.normal(0, 0.004, size=(len(s), 3)).astype(np.float32)
+        scans.append(np.ascontiguousarray(s[:, :3]))
+        guesses.append(synth.pose_matrix((0.05 * (k % 3), -0.04 * (k % 2), 0.0), (0, 0, 0.3 * d * (k % 5))).astype(np.float32))
+    return scans, guesses
+
+
+def _single(g, scans, guesses):
+    out = []
+    for s, T in zip(scans, guesses):
+        g.setInputSource(s)
+        P = g.align(T)
+        out.append((P, g.getFinalNumIteration(), g.hasConverged(), g.getTransformationProbability(), g.stats()["evaluations"]))
+    return out
+
+
+@pytest.mark.parametrize("config,res", [("small", 2.0), ("c1", 5.0)])
+def test_batch_equals_single_bitwise(b200, config, res):
+    from lidarslam_ros2_b200 import synth
+
+    src, tgt, _ = synth.registration_pair(config, res)
+    g = _engine(b200, tgt, res)
+    scans, guesses = _scans_and_guesses(src, 9)
+    ref = _single(g, scans, guesses)
+    for slots in (2, 1):
+        g.setBatchSlots(slots)
+        r = g.alignBatch(scans, guesses)
+        assert np.all(r["status"] == 0)
+        for k, (P, it, conv, tp, ev) in enumerate(ref):
+            assert np.array_equal(r["pose"][k], P), (slots, k, np.abs(r["pose"][k] - P).max())
+            assert r["iterations"][k] == it and bool(r["converged"][k]) == conv and r["evaluations"][k] == ev
+            assert r["trans_probability"][k] == tp
+    # the handle's getters describe the last registration of the batch
+    assert np.array_equal(g.getFinalTransformation(), ref[-1][0])
+    assert g.stats()["evaluations"] == sum(x[4] for x in ref)
+
+
+def test_batch_device_sources_and_identity_guess(b200):
+    import torch
+
+    from lidarslam_ros2_b200 import synth
+
+    src, tgt, _ = synth.registration_pair("small", 2.0)
+    g = _engine(b200, tgt)
+    scans, _ = _scans_and_guesses(src, 5)
+    ref = _single(g, scans, [None] * len(scans))
+    dev = [torch.from_numpy(np.concatenate([s, np.ones((len(s), 1), np.float32)], axis=1)).cuda() for s in scans]
+    torch.cuda.synchronize()
+    r = g.alignBatchDevice([d.data_ptr() for d in dev], [d.shape[0] for d in dev])
+    for k, (P, it, conv, tp, ev) in enumerate(ref):
+        assert np.array_equal(r["pose"][k], P) and r["iterations"][k] == it
+    # one registration, and an empty batch
+    r1 = g.alignBatchDevice([dev[2].data_ptr()], [dev[2].shape[0]])
+    assert np.array_equal(r1["pose"][0], ref[2][0])
+    r0 = g.alignBatch([])
+    assert r0["pose"].shape == (0, 4, 4)
+
+
+def test_batch_fallback_configurations(b200):
+    """step_max <= step_min runs the More-Thuente inner loop (K2 passes): the batch entry serves it one by one."""
+    from lidarslam_ros2_b200 import synth
+
+    src, tgt, _ = synth.registration_pair("tiny", 2.0)
+    g = _engine(b200, tgt)
+    g.setStepSize(0.004)  # < transformation_epsilon / 2
+    scans, guesses = _scans_and_guesses(src, 3)
+    ref = _single(g, scans, guesses)
+    r = g.alignBatch(scans, guesses)
+    for k, (P, it, conv, tp, ev) in enumerate(ref):
+        assert np.array_equal(r["pose"][k], P) and r["iterations"][k] == it
+    # no target: soft failure like align()
+    e = b200.NormalDistributionsTransform()
+    r = e.alignBatch(scans[:1])
+    assert r["status"][0] != 0 or not r["converged"][0]
+
+
+def test_align_batch_over_handles(b200, oracle_mod):
+    """b200reg_align_batch: independent handles (different targets), every result == the handle's own align()."""
+    from lidarslam_ros2_b200 import synth
+
+    engines, refs = [], []
+    for cfg, res in (("tiny", 2.0), ("small", 2.0), ("small", 5.0)):
+        src, tgt, _ = synth.registration_pair(cfg, 2.0)
+        g = _engine(b200, tgt, res)
+        g.setInputSource(src)
+        refs.append(g.align())
+        engines.append(g)
+    out = b200.align_batch(engines)
+    for k in range(len(engines)):
+        assert np.array_equal(out[k], refs[k])
+        assert np.array_equal(engines[k].getFinalTransformation(), refs[k])
+
+
+def test_get_aligned_matches_transformed_source(b200, oracle_mod, pair_small):
+    """b200reg_get_aligned = the `output` cloud of align(): source moved by the final transformation in un-fused float
+    arithmetic ((m0*x + m1*y) + m2*z) + m3, the solver's own definition of transformPointCloud."""
+    src, tgt, _ = pair_small
+    g = _engine(b200, tgt)
+    g.setInputSource(src)
+    T = g.align()
+    out = g.getAligned()
+    p = src[:, :3].astype(np.float32)
+    R, t = T[:3, :3].astype(np.float32), T[:3, 3].astype(np.float32)
+    ref = np.empty_like(p)
+    for r in range(3):
+        ref[:, r] = ((R[r, 0] * p[:, 0] + R[r, 1] * p[:, 1]) + R[r, 2] * p[:, 2]) + t[r]
+    assert out.shape == (len(src), 4)
+    np.testing.assert_array_equal(out[:, :3], ref)
+    assert np.all(out[:, 3] == 1.0)
+    # and against the oracle's transformed cloud
+    o = oracle_mod.NDT(resolution=2.0, transformation_epsilon=0.01)
+    o.set_target(tgt)
+    o.set_source(src)
+    To = o.align()
+    refo = (To[:3, :3].astype(np.float64) @ p.T.astype(np.float64)).T + To[:3, 3]
+    assert np.abs(out[:, :3] - refo).max() < 1e-3

@@ -5,18 +5,17 @@
 tag=${1:-rX}
 out=gpurun_out
 mkdir -p $out
-timeout 600 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; tail -2 $out/pytest_gpu_$tag.log
+timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; tail -3 $out/pytest_gpu_$tag.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; tail -2 $out/smoke_$tag.log
-timeout 400 python bench.py > $out/bench_$tag.json 2> $out/bench_$tag.err; tail -c 600 $out/bench_$tag.json
+timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_$tag.json 2> $out/bench_$tag.err; tail -c 1500 $out/bench_$tag.json; tail -5 $out/bench_$tag.err
+timeout 300 python bench.py --steps 20 --warmup 5 --slots 1 --no-c4 --no-cpu-baseline > $out/bench_slots1_$tag.json 2> $out/bench_slots1_$tag.err; tail -c 600 $out/bench_slots1_$tag.json
 timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; tail -c 400 $out/bench_ref_$tag.json
 # launch list of the profile command (cold-cache, serialised: compare shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
-  python tools/profile_step.py headline 3 > $out/prof_step_$tag.log 2>&1
-# one full capture of the solver kernel (launches 2 and 3)
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_solver_kernel -s 1 -c 2 \
-  -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 > $out/prof_full_$tag.log 2>&1
+  python tools/profile_step.py headline 3 8 > $out/prof_step_$tag.log 2>&1
+# one full capture of the solver kernel: the last launch = the batched one (3 single + 2 batched launches)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_solver_kernel -s 4 -c 1 \
+  -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 8 > $out/prof_full_$tag.log 2>&1
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page raw --csv > $out/ndt_solver_raw_$tag.csv 2>/dev/null
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page details --csv > $out/ndt_solver_details_$tag.csv 2>/dev/null
 ls -la $out | tail -12
-timeout 300 python bench.py --workload c3 > $out/bench_c3_$tag.json 2> $out/bench_c3_$tag.err; tail -c 300 $out/bench_c3_$tag.json
-timeout 400 python bench.py --workload c5 --frames 120 > $out/bench_c5_$tag.json 2> $out/bench_c5_$tag.err; tail -c 300 $out/bench_c5_$tag.json

@@ -1,5 +1,5 @@
-"""Short headline-workload run for ncu: a few aligns + fitness + voxel build (set target) so that every kernel of the
-hot path appears in the launch list."""
+"""Short headline-workload run for ncu: a few aligns + a batched launch + fitness + voxel build (set target) so that
+every kernel of the hot path appears in the launch list.  usage: profile_step.py [config] [n_align] [n_batch]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,11 +8,18 @@ import lidarslam_ros2_b200 as m
 from lidarslam_ros2_b200 import synth
 cfg = sys.argv[1] if len(sys.argv) > 1 else "headline"
 n_align = int(sys.argv[2]) if len(sys.argv) > 2 else 3
+n_batch = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 src, tgt, _ = synth.registration_pair(cfg, 2.0)
 g = m.NormalDistributionsTransform(); g.setResolution(2.0); g.setTransformationEpsilon(0.01)
 g.setInputTarget(tgt); g.setInputSource(src)
 for _ in range(n_align):
     T = g.align()
 print("fitness", g.getFitnessScore(), "stats", g.stats())
+if n_batch:
+    rng = np.random.default_rng(1)
+    scans = [(src + rng.normal(0, 0.003, size=src.shape)).astype(np.float32) for _ in range(n_batch)]
+    for _ in range(2):
+        r = g.alignBatch(scans)
+    print("batch", r["iterations"], g.stats())
 ds = m.voxel_grid_filter(src, 0.5)
 print("voxelgrid", ds.shape)
