@@ -228,6 +228,23 @@ typedef struct b200sm_loop_result {
 int b200sm_search_loop(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double threshold_loop_closure_score,
                        double distance_loop_closure, double range_of_searching_loop_closure, int search_submap_num,
                        b200sm_loop_result* out);
+/* ---- IMU de-skew (use_imu; sm.cpp:205-209, 222-235): LidarUndistortion of scanmatcher/include/scanmatcher/
+ * lidar_undistortion.hpp. getImu (:52-106) is the per-message ring-buffer update (host state); adjustDistortion
+ * (:110-226) runs as kernels on the uploaded scan: the half-turn switch is a first-index reduction, the carried IMU
+ * ring pointer an exclusive prefix-max scan, interpolation + rigid correction per point.                          */
+int b200sm_imu_set_scan_period(b200sm_t s, double scan_period);                        /* setScanPeriod :228  */
+int b200sm_imu_push(b200sm_t s, const float* angular_velocity3, const float* linear_acceleration3,
+                    const float* orientation_xyzw, double stamp_sec);                  /* getImu :52-106      */
+/* arm the de-skew for the NEXT frame given to b200sm_set_scan / b200sm_receive_cloud: it then runs on the device right
+ * after the upload, before the range filter — cloud_callback's order (sm.cpp:205-219)                              */
+int b200sm_deskew_next_scan(b200sm_t s, double scan_time_sec);
+/* adjustDistortion (:110-226) on a HOST cloud, in place (x, y, z rewritten; points in firing order)               */
+int b200sm_imu_adjust_distortion(b200sm_t s, float* points, size_t n, size_t stride_bytes, long intensity_offset_bytes,
+                                 double scan_time_sec);
+/* read-back for the parity tests: imu_ptr_front_, imu_ptr_last_, imu_ptr_last_iter_; one ring entry                */
+int b200sm_imu_get_state(b200sm_t s, int* ptr_front, int* ptr_last, int* ptr_last_iter);
+int b200sm_imu_get_sample(b200sm_t s, int index, double* stamp, float* rpy3, float* shift3, float* velo3);
+
 typedef struct b200sm_stats {
   size_t n_scan, n_filtered, n_targeted, n_submaps;
   int kernel_launches;

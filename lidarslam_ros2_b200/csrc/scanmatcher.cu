@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/b200reg.h"
+#include "deskew.hpp"
 #include "engine.hpp"
 
 namespace b200 {
@@ -142,6 +143,10 @@ struct b200sm_session {
   double position[3] = {0, 0, 0}, quat[4] = {0, 0, 0, 1};  // corrent_pose_stamped_.pose (x y z, qx qy qz qw)
   double previous_position[3] = {0, 0, 0};
   double latest_distance = 0, trans = 0;
+  // IMU de-skew (lidar_undistortion.hpp; use_imu, scanmatcher_component.cpp:205-209)
+  ImuDeskew imu;
+  bool deskew_armed = false;
+  double deskew_scan_time = 0;
 };
 
 namespace {
@@ -215,6 +220,14 @@ void upload_frame(b200sm_t s, const float* points, size_t n, size_t stride, long
   s->launches += 1;
   s->d_scan = s->upload.ptr;
   s->n_scan = n;
+  if (s->deskew_armed && n > 0) {  // cloud_callback: adjustDistortion before the range filter (sm.cpp:205-209)
+    s->deskew_armed = false;
+    const char* b = reinterpret_cast<const char*>(points);
+    const int before = s->imu.launches;
+    s->imu.adjust_distortion(s->upload.ptr, n, reinterpret_cast<const float*>(b), reinterpret_cast<const float*>(b + (n - 1) * stride),
+                             s->deskew_scan_time, s->stream);
+    s->launches += s->imu.launches - before;
+  }
   if (s->use_min_max_filter) {
     s->scan.ensure(n);
     s->counter.ensure(1);
@@ -623,6 +636,80 @@ int b200sm_get_stats(b200sm_t s, b200sm_stats* out) {
   out->kernel_launches = s->launches;
   out->trans = s->trans;
   out->latest_distance = s->latest_distance;
+  return B200REG_OK;
+}
+
+}  // extern "C"
+
+// ---- IMU de-skew: LidarUndistortion of scanmatcher/include/scanmatcher/lidar_undistortion.hpp ----
+extern "C" {
+
+int b200sm_imu_set_scan_period(b200sm_t s, double scan_period) {
+  if (!s || !(scan_period > 0)) return B200REG_ERR_ARG;
+  s->imu.scan_period = scan_period;
+  return B200REG_OK;
+}
+
+int b200sm_imu_push(b200sm_t s, const float* angular_velocity3, const float* linear_acceleration3, const float* orientation_xyzw,
+                    double stamp) {
+  if (!s || !angular_velocity3 || !linear_acceleration3 || !orientation_xyzw) return B200REG_ERR_ARG;
+  s->imu.get_imu(angular_velocity3, linear_acceleration3, orientation_xyzw, stamp);
+  return B200REG_OK;
+}
+
+int b200sm_deskew_next_scan(b200sm_t s, double scan_time) {
+  if (!s) return B200REG_ERR_ARG;
+  s->deskew_armed = true;
+  s->deskew_scan_time = scan_time;
+  return B200REG_OK;
+}
+
+int b200sm_imu_adjust_distortion(b200sm_t s, float* points, size_t n, size_t stride_bytes, long intensity_offset_bytes,
+                                 double scan_time) {
+  if (!s || (!points && n) || stride_bytes < 12 || (stride_bytes % 4) != 0 || (intensity_offset_bytes >= 0 && intensity_offset_bytes % 4 != 0))
+    return B200REG_ERR_ARG;
+  return sm_guarded(s, [&]() {
+    if (n == 0) return (int)B200REG_OK;
+    s->upload.ensure(n);
+    s->uploader.upload(points, n, stride_bytes, intensity_offset_bytes, 0.0f, s->upload.ptr, s->stream);
+    char* b = reinterpret_cast<char*>(points);
+    const int before = s->imu.launches;
+    s->imu.adjust_distortion(s->upload.ptr, n, reinterpret_cast<const float*>(b), reinterpret_cast<const float*>(b + (n - 1) * stride_bytes),
+                             scan_time, s->stream);
+    s->launches += 1 + s->imu.launches - before;
+    std::vector<float4> host(n);
+    B200_CUDA(cudaMemcpyAsync(host.data(), s->upload.ptr, n * sizeof(float4), cudaMemcpyDeviceToHost, s->stream));
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    for (size_t i = 0; i < n; i++) {  // x, y, z back into the caller's records; every other field is untouched
+      float* f = reinterpret_cast<float*>(b + i * stride_bytes);
+      f[0] = host[i].x;
+      f[1] = host[i].y;
+      f[2] = host[i].z;
+    }
+    return (int)B200REG_OK;
+  });
+}
+
+int b200sm_imu_get_state(b200sm_t s, int* ptr_front, int* ptr_last, int* ptr_last_iter) {
+  if (!s) return B200REG_ERR_ARG;
+  if (ptr_front) *ptr_front = s->imu.ptr_front;
+  if (ptr_last) *ptr_last = s->imu.ptr_last;
+  if (ptr_last_iter) *ptr_last_iter = s->imu.ptr_last_iter;
+  return B200REG_OK;
+}
+
+int b200sm_imu_get_sample(b200sm_t s, int index, double* stamp, float* rpy3, float* shift3, float* velo3) {
+  if (!s || index < 0 || index >= IMU_QUE) return B200REG_ERR_ARG;
+  if (stamp) *stamp = s->imu.time[index];
+  if (rpy3) {
+    rpy3[0] = s->imu.roll[index];
+    rpy3[1] = s->imu.pitch[index];
+    rpy3[2] = s->imu.yaw[index];
+  }
+  for (int c = 0; c < 3; c++) {
+    if (shift3) shift3[c] = s->imu.shift[index][c];
+    if (velo3) velo3[c] = s->imu.velo[index][c];
+  }
   return B200REG_OK;
 }
 

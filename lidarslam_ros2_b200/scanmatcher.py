@@ -78,6 +78,10 @@ class ScanMatcher:
         self._check(self._lib.b200sm_set_scan(self._h, self.registration._h, _ptr(p), n, 4 * w, 12 if w >= 4 else -1, C.byref(m)))
         return int(m.value)
 
+    def deskewNextScan(self, scan_time: float):
+        """use_imu: de-skew the next frame on the device before the range filter (b200sm_deskew_next_scan)."""
+        self._check(self._lib.b200sm_deskew_next_scan(self._s, float(scan_time)))
+
     def updateMap(self, final_transformation, position, quat_xyzw, adopt_now: bool = True):
         T = np.ascontiguousarray(np.asarray(final_transformation, dtype=np.float32).T).reshape(16)
         p = np.ascontiguousarray(position, dtype=np.float64)
@@ -157,3 +161,63 @@ def backend_registration(registration_method: str = "NDT", ndt_resolution: float
         reg.setRANSACIterations(0)
         return reg
     raise ValueError("registration_method must be NDT or GICP")
+
+
+class LidarUndistortion:
+    """scanmatcher/include/scanmatcher/lidar_undistortion.hpp on the GPU session (b200sm_imu_*): getImu keeps the IMU ring
+    on the host like the reference, adjustDistortion runs as CUDA kernels on the uploaded scan."""
+
+    def __init__(self, device: int = 0, scan_period: float = 0.1, session=None):
+        import ctypes as C
+
+        from . import _capi
+
+        self._C, self._lib = C, _capi.lib()
+        self._own = session is None
+        if session is None:
+            h = C.c_void_p()
+            rc = self._lib.b200sm_create(int(device), C.byref(h))
+            if rc != 0:
+                raise RuntimeError(f"b200sm_create failed ({rc}): no CUDA device? there is no CPU fallback")
+            self._s = h
+        else:
+            self._s = session
+        self.setScanPeriod(scan_period)
+
+    def __del__(self):
+        if getattr(self, "_own", False) and getattr(self, "_s", None):
+            self._lib.b200sm_destroy(self._s)
+            self._s = None
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError(f"b200sm error {rc}: {self._lib.b200sm_last_error(self._s).decode()}")
+
+    def setScanPeriod(self, scan_period: float):
+        self._check(self._lib.b200sm_imu_set_scan_period(self._s, float(scan_period)))
+
+    def getImu(self, angular_velo, acc, quat_xyzw, imu_time: float):
+        a = np.ascontiguousarray(angular_velo, dtype=np.float32)
+        b = np.ascontiguousarray(acc, dtype=np.float32)
+        q = np.ascontiguousarray(quat_xyzw, dtype=np.float32)
+        self._check(self._lib.b200sm_imu_push(self._s, a.ctypes.data, b.ctypes.data, q.ctypes.data, float(imu_time)))
+
+    def adjustDistortion(self, cloud, scan_time: float) -> np.ndarray:
+        """cloud: (N, >=3) float32 in firing order; returns the corrected copy (other columns untouched)."""
+        c = np.array(cloud, dtype=np.float32, copy=True, order="C")
+        ioff = 12 if c.shape[1] >= 4 else -1
+        self._check(self._lib.b200sm_imu_adjust_distortion(self._s, c.ctypes.data, len(c), c.strides[0], ioff, float(scan_time)))
+        return c
+
+    def pointers(self):
+        C = self._C
+        a, b, c = C.c_int(0), C.c_int(0), C.c_int(0)
+        self._check(self._lib.b200sm_imu_get_state(self._s, C.byref(a), C.byref(b), C.byref(c)))
+        return a.value, b.value, c.value
+
+    def sample(self, index: int):
+        C = self._C
+        t = C.c_double(0)
+        rpy, sh, ve = (np.zeros(3, dtype=np.float32) for _ in range(3))
+        self._check(self._lib.b200sm_imu_get_sample(self._s, int(index), C.byref(t), rpy.ctypes.data, sh.ctypes.data, ve.ctypes.data))
+        return t.value, rpy, sh, ve
