@@ -14,6 +14,7 @@
 #pragma once
 #include <array>
 #include <cfloat>
+#include <cstdio>
 #include <limits>
 #include <cstddef>
 #include <memory>
@@ -155,38 +156,81 @@ class RegistrationBase : public pcl::Registration<PointSource, PointTarget> {
   RegistrationBase(int kind, int device) : h_(kind, device) {}
 
  public:
+  // pcl::Registration::setInputTarget arms target_cloud_updated_, and the next align() -> initCompute() then builds a
+  // FLANN kd-tree over the WHOLE target on the host (hundreds of milliseconds for a 1 M-point map) that neither engine
+  // here ever queries. So the target is stored WITHOUT arming that rebuild; the cloud goes to the GPU instead.
+  // setKeepHostSearchTree(true) restores PCL's behaviour for callers that need PCL's own (non-virtual, host-side)
+  // getFitnessScore through a base-class pointer.
   void setInputTarget(const PointCloudTargetConstPtr& cloud) override {
-    Base::setInputTarget(cloud);
-    if (cloud && !cloud->empty()) b200reg_set_input_target(h_.get(), &cloud->points[0].x, cloud->size(), sizeof(PointTarget));
+    if (!cloud || cloud->points.empty()) {
+      PCL_ERROR_B200("[b200reg::setInputTarget] invalid or empty point cloud given, ignored");
+      return;
+    }
+    if (keep_host_tree_) Base::setInputTarget(cloud);
+    else this->target_ = cloud;
+    target_ok_ = report(b200reg_set_input_target(h_.get(), &cloud->points[0].x, cloud->size(), sizeof(PointTarget)), "setInputTarget");
   }
   void setInputSource(const PointCloudSourceConstPtr& cloud) override {
     Base::setInputSource(cloud);
-    if (cloud && !cloud->empty()) b200reg_set_input_source(h_.get(), &cloud->points[0].x, cloud->size(), sizeof(PointSource));
+    if (!cloud || cloud->points.empty()) {
+      source_ok_ = false;
+      return;
+    }
+    source_ok_ = report(b200reg_set_input_source(h_.get(), &cloud->points[0].x, cloud->size(), sizeof(PointSource)), "setInputSource");
   }
-  // pcl::Registration::getFitnessScore walks a host kd-tree over the target; answer from the GPU instead
+  void setKeepHostSearchTree(bool keep) { keep_host_tree_ = keep; }
+  // align() fills `output` with the transformed source (a device-to-host copy of the whole scan per call). Both nodes
+  // discard it (scanmatcher_component.cpp:350-358, graph_based_slam_component.cpp:229-231), so it is off by default:
+  // `output` then keeps PCL's pre-filled copy of the input. Switch it on for callers that read the aligned cloud.
+  void setComputeOutputCloud(bool on) { compute_output_ = on; }
   b200reg_t handle() const { return h_.get(); }  // for ScanMatcherSession
+  // getFitnessScore on the GPU (exact 1-NN). pcl::Registration::getFitnessScore is NOT virtual: call this through the
+  // concrete type, or through b200reg::getFitnessScore(registration_) below (gbs.cpp:231, sm.cpp:376).
   double getFitnessScore(double max_range = std::numeric_limits<double>::max()) {
     double v = std::numeric_limits<double>::max();
-    b200reg_get_fitness_score(h_.get(), max_range, &v);
+    report(b200reg_get_fitness_score(h_.get(), max_range, &v), "getFitnessScore");
     return v;
   }
+  const char* lastError() const { return b200reg_last_error(h_.get()); }
 
  protected:
   // the virtual hook pcl::Registration::align() calls (ndt_omp.h:257-268, gicp_omp.h:332-333)
   void computeTransformation(PointCloudSource& output, const Eigen::Matrix4f& guess) override {
-    b200reg_set_transformation_epsilon(h_.get(), this->transformation_epsilon_);
-    b200reg_set_maximum_iterations(h_.get(), this->max_iterations_);
-    b200reg_set_max_correspondence_distance(h_.get(), this->corr_dist_threshold_);
+    this->converged_ = false;
+    if (!target_ok_ || !source_ok_) {  // a failed upload must not be answered from the previous cloud
+      PCL_ERROR_B200("[b200reg::align] the last setInputTarget / setInputSource failed; not aligning against stale data");
+      return;
+    }
+    report(b200reg_set_transformation_epsilon(h_.get(), this->transformation_epsilon_), "setTransformationEpsilon");
+    report(b200reg_set_maximum_iterations(h_.get(), this->max_iterations_), "setMaximumIterations");
+    report(b200reg_set_max_correspondence_distance(h_.get(), this->corr_dist_threshold_), "setMaxCorrespondenceDistance");
     Eigen::Matrix4f final_t = Eigen::Matrix4f::Identity();
-    int rc = b200reg_align(h_.get(), guess.data(), final_t.data());
+    const int rc = b200reg_align(h_.get(), guess.data(), final_t.data());
     this->final_transformation_ = final_t;
     int conv = 0;
     b200reg_has_converged(h_.get(), &conv);
-    this->converged_ = (rc == B200REG_OK) && conv;
-    if (rc == B200REG_OK && !output.empty()) b200reg_get_aligned(h_.get(), &output.points[0].x, sizeof(PointSource));
+    this->converged_ = report(rc, "align") && conv;
+    if (rc == B200REG_OK && compute_output_ && !output.empty())
+      report(b200reg_get_aligned(h_.get(), &output.points[0].x, sizeof(PointSource)), "getAligned");
   }
+  bool report(int rc, const char* what) const {
+    if (rc == B200REG_OK) return true;
+    std::fprintf(stderr, "[b200reg::%s] error %d: %s\n", what, rc, b200reg_last_error(h_.get()));
+    return false;
+  }
+  static void PCL_ERROR_B200(const char* msg) { std::fprintf(stderr, "%s\n", msg); }
   Handle h_;
+  bool keep_host_tree_ = false, compute_output_ = false;
+  bool target_ok_ = false, source_ok_ = false;
 };
+
+// getFitnessScore for code that only holds the base-class pointer (graph_based_slam_component.cpp:231,
+// scanmatcher_component.cpp:376): GPU path for the engines of this header, PCL's own for anything else.
+template <typename PointSource, typename PointTarget>
+double getFitnessScore(pcl::Registration<PointSource, PointTarget>& reg, double max_range = std::numeric_limits<double>::max()) {
+  if (auto* p = dynamic_cast<RegistrationBase<PointSource, PointTarget>*>(&reg)) return p->getFitnessScore(max_range);
+  return reg.getFitnessScore(max_range);
+}
 
 template <typename PointSource, typename PointTarget>
 class NormalDistributionsTransform : public RegistrationBase<PointSource, PointTarget> {
@@ -198,7 +242,7 @@ class NormalDistributionsTransform : public RegistrationBase<PointSource, PointT
     this->transformation_epsilon_ = 0.1;  // ndt_omp_impl.hpp:71-72
     this->max_iterations_ = 35;
   }
-  void setResolution(float r) { b200reg_ndt_set_resolution(this->h_.get(), r); }
+  void setResolution(float r) { this->report(b200reg_ndt_set_resolution(this->h_.get(), r), "setResolution"); }
   void setStepSize(double s) { b200reg_ndt_set_step_size(this->h_.get(), s); }
   void setOulierRatio(double r) { b200reg_ndt_set_outlier_ratio(this->h_.get(), r); }
   void setNeighborhoodSearchMethod(NeighborSearchMethod m) { b200reg_ndt_set_neighborhood_search_method(this->h_.get(), m); }

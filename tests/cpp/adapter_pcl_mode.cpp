@@ -1,5 +1,8 @@
 // Type-checks include/b200reg_pcl.hpp in PCL mode (-DB200REG_WITH_PCL) against a minimal PCL-1.12-shaped stub
-// (tests/cpp/fake_pcl): the two-line patch of INTEGRATION.md section 2, as the nodes would write it.
+// (tests/cpp/fake_pcl): the two-line patch of INTEGRATION.md section 2, as the nodes would write it — and checks that
+// align() through the base-class pointer does NOT trigger pcl::Registration's lazy host kd-tree build over the target
+// (the stub counts them), which would put hundreds of milliseconds of CPU work in front of the GPU solve.
+// Exit codes: 3 = no GPU (engine refuses to construct), 0 = ok, anything else = failure.
 #include <cstdio>
 #include <memory>
 #include <stdexcept>
@@ -31,7 +34,24 @@ int main() {
     pcl::PointCloud<pcl::PointXYZI> output;
     registration->align(output, Eigen::Matrix4f::Identity());  // :353
     Eigen::Matrix4f T = registration->getFinalTransformation();
-    std::printf("converged=%d tx=%.3f fitness=%.5f\n", (int)registration->hasConverged(), T.data()[12], ndt->getFitnessScore());
+    const double fit = b200reg::getFitnessScore(*registration);  // gbs.cpp:231 with the one-line patch
+    std::printf("converged=%d tx=%.3f fitness=%.5f host_tree_builds=%d host_fitness_calls=%d\n", (int)registration->hasConverged(),
+                T.data()[12], fit, registration->host_tree_builds(), registration->host_fitness_calls());
+    if (!registration->hasConverged()) return 10;
+    if (registration->host_tree_builds() != 0) return 11;   // the adapter armed pcl::Registration's lazy kd-tree
+    if (registration->host_fitness_calls() != 0) return 12; // fitness came from the host tree, not from the GPU
+    if (output.size() != source->size() || output.points[5].x != source->points[5].x) return 13;  // output D2H is opt-in
+    // a new target (map update) still does not build a host tree; the aligned cloud on request
+    registration->setInputTarget(target);
+    ndt->setComputeOutputCloud(true);
+    registration->align(output);
+    if (registration->host_tree_builds() != 0) return 14;
+    if (output.points[5].x == source->points[5].x) return 15;
+    // PCL's own behaviour back on request
+    ndt->setKeepHostSearchTree(true);
+    registration->setInputTarget(target);
+    registration->align(output);
+    if (registration->host_tree_builds() != 1) return 16;
     auto gicp = std::make_shared<b200reg::GeneralizedIterativeClosestPoint<pcl::PointXYZI, pcl::PointXYZI>>();
     gicp->setMaxCorrespondenceDistance(5.0);
     registration = gicp;

@@ -82,7 +82,7 @@ def test_deskew_inside_the_frontend_frame(sm):
     import lidarslam_ros2_b200 as m
 
     s = sm.ScanMatcher(device=0, ndt_resolution=2.0, vg_size_for_input=0.0005, vg_size_for_map=0.1)
-    imu = sm.LidarUndistortion(session=s._s)
+    imu = sm.LidarUndistortion(session=s._h)
     o = deskew.LidarUndistortion(scan_period=0.1)
     _feed([imu, o], t0=10.0, n=100)
     cloud = _spinning_scan(n=8000, rings=8)

@@ -232,6 +232,25 @@ def test_cpp_adapter_end_to_end(b200):
     assert out.returncode == 0, out.stdout + out.stderr
 
 
+def test_cpp_adapter_pcl_mode_keeps_the_host_tree_out(b200):
+    """PCL mode of the adapter against the PCL-1.12-shaped stub (tests/cpp/fake_pcl): align() through the base-class pointer
+    runs pcl::Registration::initCompute(), which would build a host kd-tree over the whole target if the adapter armed
+    target_cloud_updated_. The stub counts those builds; the program exits non-zero if one happens, if the fitness came from
+    the host tree, or if the aligned-cloud copy is not opt-in."""
+    import os
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "adapter_pcl_mode")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-Wall", "-Werror", "-DB200REG_WITH_PCL",
+                           "-I" + os.path.join(root, "tests", "cpp", "fake_pcl"), "-I" + os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp", "adapter_pcl_mode.cpp"), "-o", exe,
+                           "-L" + os.path.join(root, "lidarslam_ros2_b200", "csrc"), "-lb200reg",
+                           "-Wl,-rpath," + os.path.join(root, "lidarslam_ros2_b200", "csrc")])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, (out.returncode, out.stdout + out.stderr)
+
+
 @pytest.mark.parametrize("cfg", ["c2", "headline"])
 def test_align_parity_full_size(b200, oracle_mod, cfg):
     """BASELINE.json's full sizes (C2: ~60k vs 500k; headline: ~100k vs 1M), res 2.0, node parameters: pose and iteration

@@ -5,7 +5,7 @@
 tag=${1:-rX}
 out=gpurun_out
 mkdir -p $out
-timeout 900 python -m pytest tests -m gpu -x -q > $out/pytest_gpu_$tag.log 2>&1; tail -3 $out/pytest_gpu_$tag.log
+timeout 1200 python -m pytest tests -m gpu -q > $out/pytest_gpu_$tag.log 2>&1; tail -3 $out/pytest_gpu_$tag.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; tail -2 $out/smoke_$tag.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_$tag.json 2> $out/bench_$tag.err; tail -c 1500 $out/bench_$tag.json; tail -5 $out/bench_$tag.err
 timeout 300 python bench.py --steps 20 --warmup 5 --slots 1 --no-c4 --no-cpu-baseline > $out/bench_slots1_$tag.json 2> $out/bench_slots1_$tag.err; tail -c 600 $out/bench_slots1_$tag.json
@@ -18,4 +18,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_
   -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 8 > $out/prof_full_$tag.log 2>&1
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page raw --csv > $out/ndt_solver_raw_$tag.csv 2>/dev/null
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page details --csv > $out/ndt_solver_details_$tag.csv 2>/dev/null
+timeout 600 python tools/diag_gicp.py tiny small c1 > $out/diag_gicp_$tag.log 2>&1; tail -40 $out/diag_gicp_$tag.log
 ls -la $out | tail -12
