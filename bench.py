@@ -477,10 +477,11 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     mine = batch.shard_pairs(args.pairs, rank, world)
     sweep = batch.LoopSweep(m, device=local_rank, resolution=2.0, max_iterations=100)
     dev = torch.device("cuda", local_rank)
+    comm = batch.RowComm(rank, world, local_rank) if world > 1 else None  # ncclAllGather issued by libb200reg.so (b200comm.h)
     if mine:  # warm-up: allocations and first-launch costs (two pairs, twice)
         for _ in range(2):
             sweep.run([data[i][0] for i in mine[:2]], [data[i][1] for i in mine[:2]], mine[:2])
-    batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev)  # NCCL warm-up
+    batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev, comm=comm)  # NCCL warm-up
     launches0 = sweep.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if world > 1:
@@ -488,7 +489,7 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     torch.cuda.synchronize()
     e0.record()
     rows = sweep.run([data[i][0] for i in mine], [data[i][1] for i in mine], mine)
-    res = batch.gather_rows(rows, args.pairs, rank, world, device=dev)  # the one collective: all-gather of the result rows
+    res = batch.gather_rows(rows, args.pairs, rank, world, device=dev, comm=comm)  # the one collective: ncclAllGather of the rows
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -504,7 +505,7 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     out = {
         "metric": "loop-closure candidate registrations/sec (64 scan<->submap pairs, sharded)", "value": args.pairs / (ms_max * 1e-3),
         "unit": "registrations/s", "n_gpus": world, "pairs": args.pairs, "ms_per_pair": ms_max / args.pairs, "ms_total": ms_max,
-        "per_rank_ms": per_rank_ms, "scaling": "strong", "collective": "one all-gather of 20-float result rows, inside the timed region",
+        "per_rank_ms": per_rank_ms, "scaling": "strong", "collective": "ONE ncclAllGather of 20-float result rows, issued from C (b200comm_all_gather_rows), inside the timed region",
         "workload": f"c4: {args.pairs} independent NDT pairs, 32-ring scan (~56k) vs 200k-pt submap, res 2.0, max_iter 100, DIRECT7, "
                     "setInputTarget+setInputSource+align+getFitnessScore per pair from host buffers; pair i -> rank i mod N",
         "h2d_bytes_per_pair": int(np.mean([16 * (len(data[i][0]) + len(data[i][1])) for i in mine])) if mine else 0,

@@ -132,6 +132,22 @@ int b200reg_ndt_align_batch(b200reg_t h, int count, const float* const* sources,
  * be complete when the call is made and stay untouched until it returns */
 int b200reg_ndt_align_batch_device(b200reg_t h, int count, const void* const* dev_sources, const size_t* n_points,
                                    const float* guesses, b200reg_batch_result* results);
+/* The loop-closure candidate sweep on one GPU (generalises gbs.cpp:187-233 from the arg-min candidate to all of them):
+ * `count` independent (source, target) pairs, each through the node's own sequence setInputTarget (gbs.cpp:227) ->
+ * setInputSource (:181) -> align (:230) -> getFitnessScore (:231) with the handle's parameters. Two internal engines
+ * (stream + buffers each) driven by two host threads take the pairs in turn, so that the upload and voxel-map build of
+ * one pair overlap the solve and fitness pass of the other. Results equal those of the sequential calls.
+ * guesses: 16*count floats column-major or NULL (identity). Sharding pairs across GPUs is the caller's (one process per
+ * GPU, include/b200comm.h for the all-gather of the result rows). */
+typedef struct b200reg_sweep_result {
+  float final_T[16];         /* column-major */
+  double fitness;            /* getFitnessScore(fitness_max_range) */
+  double trans_probability;
+  int converged, iterations, status, pad;
+} b200reg_sweep_result;
+int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sources, const size_t* n_src,
+                      const float* const* targets, const size_t* n_tgt, size_t stride_bytes, const float* guesses,
+                      double fitness_max_range, b200reg_sweep_result* results);
 /* registrations in flight per batch launch (1 or 2; default 2). Developer / measurement switch. */
 int b200reg_ndt_set_batch_slots(b200reg_t h, int slots);
 

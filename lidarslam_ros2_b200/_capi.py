@@ -30,7 +30,7 @@ SYMBOLS = [
     "b200reg_set_input_target_device", "b200reg_set_input_source_device",
     "b200reg_align", "b200reg_get_final_transformation", "b200reg_has_converged",
     "b200reg_get_fitness_score", "b200reg_get_aligned", "b200reg_align_batch",
-    "b200reg_ndt_align_batch", "b200reg_ndt_align_batch_device", "b200reg_ndt_set_batch_slots",
+    "b200reg_ndt_align_batch", "b200reg_ndt_align_batch_device", "b200reg_ndt_set_batch_slots", "b200reg_ndt_sweep",
     "b200reg_voxelgrid", "b200reg_get_stats", "b200reg_ndt_derivatives", "b200reg_ndt_hessian_radius",
     "b200reg_ndt_num_voxels", "b200reg_ndt_get_voxels", "b200reg_nn1",
     "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
@@ -39,6 +39,8 @@ SYMBOLS = [
     "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats", "b200sm_search_loop",
     "b200sm_imu_set_scan_period", "b200sm_imu_push", "b200sm_deskew_next_scan", "b200sm_imu_adjust_distortion",
     "b200sm_imu_get_state", "b200sm_imu_get_sample",
+    # include/b200comm.h
+    "b200comm_unique_id", "b200comm_create", "b200comm_destroy", "b200comm_all_gather_rows", "b200comm_rank", "b200comm_last_error",
 ]
 
 
@@ -56,6 +58,11 @@ class SmStats(C.Structure):
 class BatchResult(C.Structure):
     _fields_ = [("final_T", C.c_float * 16), ("trans_probability", C.c_double), ("converged", C.c_int), ("iterations", C.c_int),
                 ("evaluations", C.c_int), ("status", C.c_int), ("hits_total", C.c_longlong)]
+
+
+class SweepResult(C.Structure):
+    _fields_ = [("final_T", C.c_float * 16), ("fitness", C.c_double), ("trans_probability", C.c_double), ("converged", C.c_int),
+                ("iterations", C.c_int), ("status", C.c_int), ("pad", C.c_int)]
 
 
 class Stats(C.Structure):
@@ -122,6 +129,7 @@ def lib() -> C.CDLL:
     L.b200reg_ndt_align_batch.argtypes = [vp, i, vp, vp, sz, vp, vp]
     L.b200reg_ndt_align_batch_device.argtypes = [vp, i, vp, vp, vp, vp]
     L.b200reg_ndt_set_batch_slots.argtypes = [vp, i]
+    L.b200reg_ndt_sweep.argtypes = [vp, i, vp, vp, vp, vp, sz, vp, d, vp]
     L.b200reg_voxelgrid.argtypes = [i, vp, sz, sz, C.c_long, f, vp, sz, C.POINTER(sz)]
     L.b200reg_get_stats.argtypes = [vp, C.POINTER(Stats)]
     L.b200reg_ndt_derivatives.argtypes = [vp, vp, vp, i, C.POINTER(d), vp, vp]
@@ -154,9 +162,16 @@ def lib() -> C.CDLL:
     L.b200sm_imu_adjust_distortion.argtypes = [vp, vp, sz, sz, C.c_long, d]
     L.b200sm_imu_get_state.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.b200sm_imu_get_sample.argtypes = [vp, i, C.POINTER(d), vp, vp, vp]
+    L.b200comm_unique_id.argtypes = [vp]
+    L.b200comm_create.argtypes = [vp, i, i, i, C.POINTER(vp)]
+    L.b200comm_destroy.argtypes = [vp]
+    L.b200comm_all_gather_rows.argtypes = [vp, vp, i, i, vp]
+    L.b200comm_rank.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.b200comm_last_error.argtypes = []
+    L.b200comm_last_error.restype = C.c_char_p
     for name in SYMBOLS:
         fn = getattr(L, name)
-        if name not in ("b200reg_last_error", "b200sm_last_error", "b200sm_destroy"):
+        if name not in ("b200reg_last_error", "b200sm_last_error", "b200sm_destroy", "b200comm_last_error"):
             fn.restype = i
     _lib = L
     return L

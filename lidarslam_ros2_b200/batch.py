@@ -42,13 +42,63 @@ def unpack_rows(rows: np.ndarray):
     }
 
 
-def gather_rows(local_rows: np.ndarray, n_pairs: int, rank: int, world: int, device=None):
-    """All-gather the per-rank result rows (NCCL on GPUs, gloo on CPU). Ranks own ceil/floor(n_pairs/world) pairs;
-    rows are padded to the maximum count with index -1 and dropped after the gather."""
+class RowComm:
+    """The sweep's collective from C (include/b200comm.h): ncclGetUniqueId on rank 0, the 128-byte id handed to the other
+    ranks out of band (here: torch.distributed's rendezvous — only as the bootstrap channel), ncclCommInitRank, and then
+    ONE ncclAllGather of the packed result rows per sweep, issued by libb200reg.so itself."""
+
+    def __init__(self, rank: int, world: int, device: int):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _capi
+
+        self._lib, self._C = _capi.lib(), C
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            rc = self._lib.b200comm_unique_id(ident)
+            if rc != 0:
+                raise RuntimeError("b200comm_unique_id: " + self._lib.b200comm_last_error().decode())
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=torch.device("cuda", device) if dist.get_backend() == "nccl" else None)
+        dist.broadcast(t, src=0)
+        ident = (C.c_ubyte * 128)(*[int(v) for v in t.cpu().tolist()])
+        h = C.c_void_p()
+        rc = self._lib.b200comm_create(ident, int(rank), int(world), int(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("b200comm_create: " + self._lib.b200comm_last_error().decode())
+        self._h, self.rank, self.world = h, rank, world
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._lib.b200comm_destroy(self._h)
+            self._h = None
+
+    def all_gather_rows(self, rows: np.ndarray) -> np.ndarray:
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        per, width = rows.shape
+        out = np.empty((self.world * per, width), dtype=np.float32)
+        rc = self._lib.b200comm_all_gather_rows(self._h, rows.ctypes.data, int(per), int(width), out.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("b200comm_all_gather_rows: " + self._lib.b200comm_last_error().decode())
+        return out
+
+
+def gather_rows(local_rows: np.ndarray, n_pairs: int, rank: int, world: int, device=None, comm: "RowComm | None" = None):
+    """All-gather the per-rank result rows. Ranks own ceil/floor(n_pairs/world) pairs; rows are padded to the maximum
+    count with index -1 and dropped after the gather. With `comm` the collective is the C-side ncclAllGather
+    (b200comm_all_gather_rows); without it torch.distributed carries it (gloo in the CPU tests)."""
+    per = (n_pairs + world - 1) // world
+    if comm is not None and world > 1:
+        buf = np.full((per, ROW), -1.0, dtype=np.float32)
+        if len(local_rows):
+            buf[:len(local_rows)] = np.asarray(local_rows, dtype=np.float32).reshape(-1, ROW)
+        allr = comm.all_gather_rows(buf)
+        return unpack_rows(allr[allr[:, 19] >= 0])
     import torch
     import torch.distributed as dist
 
-    per = (n_pairs + world - 1) // world
     buf = torch.full((per, ROW), -1.0, dtype=torch.float32)
     if len(local_rows):
         buf[:len(local_rows)] = torch.from_numpy(np.asarray(local_rows, dtype=np.float32).reshape(-1, ROW))
@@ -89,5 +139,14 @@ class LoopSweep:
         return int(self.ndt.stats()["kernel_launches"])
 
     def run(self, sources, targets, indices) -> np.ndarray:
+        """b200reg_ndt_sweep: the pairs pipelined over two internal engines (two host threads, two streams)."""
+        if len(indices) == 0:
+            return np.zeros((0, ROW), dtype=np.float32)
+        r = self.ndt.sweep(sources, targets)
+        rows = [pack_row(i, r["pose"][k], r["fitness"][k], bool(r["converged"][k]), int(r["iterations"][k])) for k, i in enumerate(indices)]
+        return np.array(rows, dtype=np.float32).reshape(-1, ROW)
+
+    def run_sequential(self, sources, targets, indices) -> np.ndarray:
+        """The same pairs one after the other through the public single-pair calls (reference for the parity test)."""
         rows = [pack_row(i, *register_pair(self.ndt, s, t)) for s, t, i in zip(sources, targets, indices)]
         return np.array(rows, dtype=np.float32).reshape(-1, ROW)

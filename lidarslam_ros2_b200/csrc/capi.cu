@@ -4,8 +4,10 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200reg.h"
@@ -39,6 +41,8 @@ struct b200reg_engine {
   bool have_target = false, have_source = false;
   bool map_valid = false, nn_valid = false;
   float map_resolution = 0;
+  Bounds target_bounds{};            // min/max of the target, measured once (during the upload when it comes from the host)
+  bool target_bounds_valid = false;
 
   VoxelMap map;
   NnGrid nn;
@@ -47,6 +51,7 @@ struct b200reg_engine {
 
   DeviceBuffer<int> nn_idx;
   DeviceBuffer<float> nn_d2;
+  DeviceBuffer<unsigned> scratch_bounds;
   DeviceBuffer<double> scratch_d;   // >= 64 doubles
   DeviceBuffer<float> scratch_f;    // >= 16 floats
   DeviceBuffer<float4> query_buf;
@@ -66,6 +71,8 @@ struct b200reg_engine {
   CloudUploader batch_uploader;
   std::vector<NdtSolver::BatchItem> batch_items;
   int batch_slots = NDT_BATCH_SLOTS_DEFAULT;
+  int sibling_launches_seen = 0;
+  b200reg_engine* sibling = nullptr;  // second engine of b200reg_ndt_sweep (own stream and buffers), created on first use
 };
 
 namespace {
@@ -107,11 +114,23 @@ int fail(b200reg_t h, int code, const char* msg) {
   return code;
 }
 
+// min/max of the target cloud: both the NDT voxel grid and the NN grid are sized from them
+const Bounds* target_bounds(b200reg_t h) {
+  if (!h->target_bounds_valid) {
+    h->scratch_bounds.ensure(8);
+    h->target_bounds = cloud_bounds(h->d_target.ptr, h->n_target, h->scratch_bounds.ptr, h->stream);
+    h->target_bounds_valid = true;
+    h->other_launches += 1;
+  }
+  return &h->target_bounds;
+}
+
 void ensure_map(b200reg_t h) {
   if (h->map_valid && h->map_resolution == h->ndt.resolution) return;
+  const Bounds* tb = target_bounds(h);
   B200_CUDA(cudaEventRecord(h->ev0, h->stream));
   bool ok = h->map.build(h->d_target.ptr, h->n_target, h->ndt.resolution, h->min_points_per_voxel,
-                         h->min_covar_eigvalue_mult, h->stream);
+                         h->min_covar_eigvalue_mult, h->stream, tb);
   B200_CUDA(cudaEventRecord(h->ev1, h->stream));
   B200_CUDA(cudaEventSynchronize(h->ev1));
   B200_CUDA(cudaEventElapsedTime(&h->target_build_ms, h->ev0, h->ev1));
@@ -123,7 +142,7 @@ void ensure_map(b200reg_t h) {
 
 void ensure_nn(b200reg_t h) {
   if (h->nn_valid) return;
-  h->nn.build(h->d_target.ptr, h->n_target, h->stream);
+  h->nn.build(h->d_target.ptr, h->n_target, h->stream, target_bounds(h));
   h->nn_valid = true;
 }
 
@@ -228,12 +247,18 @@ int set_cloud(b200reg_t h, bool target, const float* base, size_t n, size_t stri
     // "caller memory may be reused on return" (b200reg.h): the copy runs on the handle's own stream, so wait for it —
     // the producer (a torch allocator, the frontend session's stream) is free to overwrite the buffer afterwards
     B200_CUDA(cudaStreamSynchronize(h->stream));
+  } else if (target) {
+    dst.ensure(n);
+    h->uploader.upload_with_bounds(base, n, stride, -1, 1.0f, dst.ptr, h->stream);  // bounds measured in the unpack pass
+    B200_CUDA(cudaStreamSynchronize(h->stream));  // the caller may reuse its buffer: wait for the copy engine
+    h->target_bounds = h->uploader.finish_bounds();
   } else {
     upload_cloud(base, n, stride, dst, h->uploader, h->stream);
     // the caller may reuse its buffer (and the staging copy is reused by the next upload): wait for the copy engine
     B200_CUDA(cudaStreamSynchronize(h->stream));
   }
   if (target) {
+    h->target_bounds_valid = !dev;
     h->n_target = n;
     h->have_target = true;
     h->map_valid = false;
@@ -297,6 +322,7 @@ int b200reg_destroy(b200reg_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->sibling) b200reg_destroy(h->sibling);
   cudaStream_t s = h->stream;
   delete h;
   if (s) cudaStreamDestroy(s);
@@ -924,3 +950,83 @@ int b200reg_ndt_set_batch_slots(b200reg_t h, int slots) {
 }
 
 }  // extern "C"
+
+// ---- loop-closure candidate sweep on one GPU (generalises gbs.cpp:187-233 from the arg-min candidate to all of them) ----
+namespace {
+int sweep_one(b200reg_t e, const float* src, size_t n_src, const float* tgt, size_t n_tgt, size_t stride, const float* guess,
+              double max_range, b200reg_sweep_result* out) {
+  std::memset(out, 0, sizeof(*out));
+  set_identity(out->final_T);
+  out->fitness = DBL_MAX;
+  return guarded(e, [&]() {
+    int rc = set_cloud(e, true, tgt, n_tgt, stride, nullptr);   // setInputTarget: upload + voxel map (gbs.cpp:227)
+    if (rc == B200REG_OK) rc = set_cloud(e, false, src, n_src, stride, nullptr);  // setInputSource (gbs.cpp:181)
+    if (rc == B200REG_OK) rc = ndt_align_begin(e, guess);       // align (gbs.cpp:230)
+    if (rc == B200REG_OK) rc = ndt_align_end(e);
+    row_to_col(e->final_T, out->final_T);
+    out->converged = e->converged;
+    out->iterations = e->iterations;
+    out->trans_probability = e->trans_probability;
+    if (rc == B200REG_OK) {                                     // getFitnessScore (gbs.cpp:231)
+      ensure_nn(e);
+      e->nn_idx.ensure(e->n_source);
+      e->nn_d2.ensure(e->n_source);
+      const float bound = (max_range < 3.0e38) ? (float)max_range * 1.0001f + 1e-30f : 3.402823466e+38f;
+      nn1_query(e->nn, e->d_source.ptr, e->n_source, e->final_T, e->nn_idx.ptr, e->nn_d2.ptr, e->stream, bound);
+      double sum = 0;
+      long long cnt = 0;
+      fitness_reduce(e->nn_d2.ptr, e->nn_idx.ptr, e->n_source, max_range, e->scratch_d.ptr, &sum, &cnt, e->stream);
+      e->other_launches += 3;
+      out->fitness = cnt > 0 ? sum / (double)cnt : DBL_MAX;
+    }
+    return rc;
+  });
+}
+}  // namespace
+
+extern "C" int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sources, const size_t* n_src,
+                                 const float* const* targets, const size_t* n_tgt, size_t stride_bytes, const float* guesses,
+                                 double fitness_max_range, b200reg_sweep_result* results) {
+  if (!h || h->kind != B200REG_NDT || count < 0 || (count > 0 && (!sources || !n_src || !targets || !n_tgt || !results)))
+    return B200REG_ERR_ARG;
+  if (stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
+  if (count == 0) return B200REG_OK;
+  if (!h->sibling && count > 1) {
+    b200reg_t sib = nullptr;
+    const int rc = b200reg_create(B200REG_NDT, h->device, &sib);
+    if (rc != B200REG_OK) return rc;
+    h->sibling = sib;
+  }
+  b200reg_t eng[2] = {h, count > 1 ? h->sibling : nullptr};
+  if (eng[1]) {  // the second engine follows the first one's parameters
+    eng[1]->ndt = h->ndt;
+    eng[1]->min_points_per_voxel = h->min_points_per_voxel;
+    eng[1]->min_covar_eigvalue_mult = h->min_covar_eigvalue_mult;
+  }
+  // Two host threads, one engine (stream + buffers) each, take the pairs from a shared counter: the upload and voxel-map
+  // build of one pair overlap the solve and fitness pass of the other, and the host-side waits of the two overlap too.
+  // Every pair is computed exactly as the sequential calls would compute it (the result does not depend on which
+  // engine served it).
+  std::atomic<int> next{0};
+  std::atomic<int> worst{B200REG_OK};
+  auto worker = [&](b200reg_t e) {
+    for (;;) {
+      const int i = next.fetch_add(1);
+      if (i >= count) break;
+      const int rc = sweep_one(e, sources[i], n_src[i], targets[i], n_tgt[i], stride_bytes, guesses ? guesses + 16 * i : nullptr,
+                               fitness_max_range, &results[i]);
+      results[i].status = rc;
+      if (rc != B200REG_OK) worst.store(rc);
+    }
+  };
+  if (eng[1]) {
+    std::thread t(worker, eng[1]);
+    worker(eng[0]);
+    t.join();
+    h->other_launches += eng[1]->solver.launches + eng[1]->map.launches + eng[1]->nn.launches + eng[1]->other_launches - h->sibling_launches_seen;
+    h->sibling_launches_seen = eng[1]->solver.launches + eng[1]->map.launches + eng[1]->nn.launches + eng[1]->other_launches;
+  } else {
+    worker(eng[0]);
+  }
+  return worst.load();
+}

@@ -24,7 +24,91 @@ __global__ void unpack_points_kernel(const unsigned char* __restrict__ raw, size
   v.w = w_off >= 0 ? *reinterpret_cast<const float*>(p + w_off) : w_default;
   dst[i] = v;
 }
+// same + min/max of the finite points (the NDT voxel grid and the NN grid of a target are sized from them): one pass less
+// over the cloud and no separate round trip for the bounds
+__global__ void unpack_points_bounds_kernel(const unsigned char* __restrict__ raw, size_t n, size_t stride, long w_off, float w_default,
+                                            float4* __restrict__ dst, unsigned* __restrict__ out6) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  float mn[3] = {3.402823466e+38f, 3.402823466e+38f, 3.402823466e+38f}, mx[3] = {-3.402823466e+38f, -3.402823466e+38f, -3.402823466e+38f};
+  if (i < n) {
+    const unsigned char* p = raw + i * stride;
+    const float* f = reinterpret_cast<const float*>(p);
+    float4 v;
+    v.x = f[0];
+    v.y = f[1];
+    v.z = f[2];
+    v.w = w_off >= 0 ? *reinterpret_cast<const float*>(p + w_off) : w_default;
+    dst[i] = v;
+    if (isfinite(v.x) && isfinite(v.y) && isfinite(v.z)) {
+      mn[0] = mx[0] = v.x;
+      mn[1] = mx[1] = v.y;
+      mn[2] = mx[2] = v.z;
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], d));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], d));
+    }
+  __shared__ float smn[8][3], smx[8][3];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+    for (int a = 0; a < 3; a++) {
+      smn[warp][a] = mn[a];
+      smx[warp][a] = mx[a];
+    }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    const int a = threadIdx.x;
+    float lo = smn[0][a], hi = smx[0][a];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++) {
+      lo = fminf(lo, smn[w][a]);
+      hi = fmaxf(hi, smx[w][a]);
+    }
+    if (lo <= hi) {  // at least one finite point in this block
+      atomicMin(&out6[a], float_to_ordered(lo));
+      atomicMax(&out6[3 + a], float_to_ordered(hi));
+    }
+  }
+}
 }  // namespace
+
+// upload + bounds: the result is valid after the caller has synchronised the stream (finish_bounds)
+void CloudUploader::upload_with_bounds(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst,
+                                       cudaStream_t s) {
+  if (n == 0) return;
+  const size_t bytes = n * stride;
+  raw.ensure(bytes);
+  bounds_dev.ensure(8);
+  bounds_host.ensure(8);
+  const bool pinned = is_pinned(host);
+  const void* src = host;
+  if (!pinned) {
+    staging.ensure(bytes);
+    std::memcpy(staging.ptr, host, bytes);
+    src = staging.ptr;
+  }
+  const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
+  std::memcpy(bounds_host.ptr, init, sizeof(init));
+  B200_CUDA(cudaMemcpyAsync(bounds_dev.ptr, bounds_host.ptr, sizeof(init), cudaMemcpyHostToDevice, s));
+  B200_CUDA(cudaMemcpyAsync(raw.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+  unpack_points_bounds_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(raw.ptr, n, stride, w_off, w_default, dst, bounds_dev.ptr);
+  B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(bounds_host.ptr, bounds_dev.ptr, sizeof(init), cudaMemcpyDeviceToHost, s));
+  launches += 1;
+}
+Bounds CloudUploader::finish_bounds() const {
+  const unsigned* res = bounds_host.ptr;
+  Bounds b;
+  b.any = !(res[0] == 0xffffffffu && res[3] == 0u);
+  for (int a = 0; a < 3; a++) {
+    b.mn[a] = ordered_to_float(res[a]);
+    b.mx[a] = ordered_to_float(res[3 + a]);
+  }
+  return b;
+}
 
 void CloudUploader::upload(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst, cudaStream_t s) {
   if (n == 0) return;

@@ -66,12 +66,15 @@ struct RankIndexScratch {
 void rank_index_clear(RankWord* table, int n_words, cudaStream_t s);
 // fills .prefix from .bits; returns (synchronously) the number of set bits
 unsigned rank_index_scan(RankWord* table, int n_words, RankIndexScratch& scratch, cudaStream_t s);
+// same, enqueue only: the number of set bits is left in *d_total (device memory)
+void rank_index_scan_async(RankWord* table, int n_words, RankIndexScratch& scratch, unsigned* d_total, cudaStream_t s);
 
-// min/max of the finite points of a float4 cloud → host (synchronises the stream). Returns #finite points.
+// min/max of the finite points of a cloud
 struct Bounds {
   float mn[3], mx[3];
   bool any;
 };
+// min/max of the finite points of a float4 cloud → host (synchronises the stream)
 Bounds cloud_bounds(const float4* pts, size_t n, unsigned* d_scratch8, cudaStream_t s);
 // PCL grid geometry from bounds (voxel_grid_covariance_omp_impl.hpp:67-103); returns false on int32 overflow
 bool make_grid_geom(const Bounds& b, float leaf, GridGeom& g);
@@ -84,6 +87,11 @@ struct CloudUploader {
   int launches = 0;
   // w_off >= 0: byte offset of the float that goes to .w (intensity); otherwise .w = w_default
   void upload(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst, cudaStream_t s);
+  // upload + min/max of the finite points in the same pass; finish_bounds() is valid once the stream has been synchronised
+  DeviceBuffer<unsigned> bounds_dev;
+  PinnedBuffer<unsigned> bounds_host;
+  void upload_with_bounds(const void* host, size_t n, size_t stride, long w_off, float w_default, float4* dst, cudaStream_t s);
+  Bounds finish_bounds() const;
   // batched form (no synchronisation between clouds): reserve once, then upload_at per cloud at its byte offset
   void reserve(size_t raw_bytes, bool need_staging);
   static bool is_pinned(const void* host);
@@ -113,12 +121,16 @@ struct VoxelMap {
   DeviceBuffer<int> tmp_npts;
   DeviceBuffer<unsigned char> tmp_valid;
   DeviceBuffer<unsigned> bounds_scratch;
+  DeviceBuffer<unsigned> counts;   // [0] occupied leaves, [1] valid voxels (device side of the build)
+  PinnedBuffer<unsigned> h_counts;
   RankIndexScratch scan_scratch;
   int launches = 0;
 
-  // returns false if the grid overflows int32 (map left empty, like voxel_grid_covariance_omp_impl.hpp:79-84)
+  // returns false if the grid overflows int32 (map left empty, like voxel_grid_covariance_omp_impl.hpp:79-84).
+  // known_bounds: min/max of the cloud when the caller already has them (measured during the upload).
+  // One host synchronisation (the final counts), none when... see voxel_map.cu.
   bool build(const float4* pts, size_t n, float leaf, int min_points_per_voxel, double min_covar_eigvalue_mult,
-             cudaStream_t s);
+             cudaStream_t s, const Bounds* known_bounds = nullptr);
 };
 
 // ---- exact nearest-neighbour grid over a cloud (K8 fitness, GICP) ---------------------------------------
@@ -141,7 +153,7 @@ struct NnGrid {
   DeviceBuffer<unsigned> unresolved_count;
   int launches = 0;
   bool valid = false;
-  void build(const float4* pts, size_t n, cudaStream_t s);
+  void build(const float4* pts, size_t n, cudaStream_t s, const Bounds* known_bounds = nullptr);
 };
 // 1-NN of n queries (optionally transformed by T, 3x4 row-major; nullptr = none). d2 accumulated in f32 as
 // ((dx*dx + dy*dy) + dz*dz); ties → lower index. idx = -1 when the target is empty.

@@ -281,14 +281,19 @@ NnView nn_view(const NnGrid& grid) {
   return V;
 }
 
-void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
+void NnGrid::build(const float4* pts, size_t n, cudaStream_t s, const Bounds* known_bounds) {
   valid = false;
   n_points = n;
   n_cells_occupied = 0;
   if (n == 0) return;
-  bounds_scratch.ensure(8);
-  Bounds b = cloud_bounds(pts, n, bounds_scratch.ptr, s);
-  launches += 1;
+  Bounds b;
+  if (known_bounds) {
+    b = *known_bounds;
+  } else {
+    bounds_scratch.ensure(8);
+    b = cloud_bounds(pts, n, bounds_scratch.ptr, s);
+    launches += 1;
+  }
   if (!b.any) return;
   double ext[3];
   for (int a = 0; a < 3; a++) {
@@ -312,9 +317,19 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
     n_cells *= dims[a];
   }
   n_words = (int)((n_cells + 31) / 32);
+  // No host round trip below: the cell lists are sized by the upper bound min(points, cells) on the occupied cells; the
+  // exclusive scan runs over that many counters (the tail past the occupied cells is zero, so cell_start[rank + 1] of
+  // the last occupied cell is the total, as the queries expect).
+  const size_t occ_max = (size_t)std::min<long long>((long long)n, n_cells);
   index.ensure((size_t)n_words);
   cell_of_point.ensure(n);
+  cell_start.ensure(occ_max + 1);
+  cursor.ensure(occ_max);
+  sorted.ensure(n);
+  scan_scratch.total.ensure(1);
   rank_index_clear(index.ptr, n_words, s);
+  B200_CUDA(cudaMemsetAsync(cell_start.ptr, 0, sizeof(unsigned) * (occ_max + 1), s));
+  B200_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned) * occ_max, s));
   NnGeom g;
   for (int a = 0; a < 3; a++) {
     g.origin[a] = origin[a];
@@ -324,25 +339,19 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s) {
   g.inv_h = inv_h;
   const int blocks = (int)((n + 255) / 256);
   nn_mark_kernel<<<blocks, 256, 0, s>>>(pts, n, g, index.ptr, cell_of_point.ptr);
-  n_cells_occupied = rank_index_scan(index.ptr, n_words, scan_scratch, s);
-  launches += 4;
-  if (n_cells_occupied == 0) return;
-  cell_start.ensure(n_cells_occupied + 1);
-  cursor.ensure(n_cells_occupied);
-  sorted.ensure(n);
-  B200_CUDA(cudaMemsetAsync(cell_start.ptr, 0, sizeof(unsigned) * (n_cells_occupied + 1), s));
-  B200_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned) * n_cells_occupied, s));
+  rank_index_scan_async(index.ptr, n_words, scan_scratch, scan_scratch.total.ptr, s);
   nn_count_kernel<<<blocks, 256, 0, s>>>(n, cell_of_point.ptr, index.ptr, cell_start.ptr);
   {
-    const int n_tiles = (int)((n_cells_occupied + USCAN_TILE - 1) / USCAN_TILE);
+    const int n_tiles = (int)((occ_max + USCAN_TILE - 1) / USCAN_TILE);
     scan_tmp.ensure((size_t)n_tiles + 1);
-    uscan_local_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, n_cells_occupied, scan_tmp.ptr);
-    uscan_tiles_kernel<<<1, 1024, 0, s>>>(scan_tmp.ptr, n_tiles, cell_start.ptr + n_cells_occupied);
-    if (n_tiles > 1) uscan_apply_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, n_cells_occupied, scan_tmp.ptr);
+    uscan_local_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, occ_max, scan_tmp.ptr);
+    uscan_tiles_kernel<<<1, 1024, 0, s>>>(scan_tmp.ptr, n_tiles, cell_start.ptr + occ_max);
+    if (n_tiles > 1) uscan_apply_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, occ_max, scan_tmp.ptr);
   }
   nn_scatter_kernel<<<blocks, 256, 0, s>>>(pts, n, cell_of_point.ptr, index.ptr, cell_start.ptr, cursor.ptr, sorted.ptr);
-  launches += 3;
+  launches += 9;
   B200_CUDA(cudaGetLastError());
+  n_cells_occupied = occ_max;  // upper bound; the exact count stays on the device (scan_scratch.total)
   valid = true;
 }
 

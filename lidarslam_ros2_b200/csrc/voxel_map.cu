@@ -100,13 +100,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) rank_scan_apply_kernel(RankWord*
   }
 }
 
-unsigned rank_index_scan(RankWord* table, int n_words, RankIndexScratch& scratch, cudaStream_t s) {
+// fills .prefix from .bits and leaves the number of set bits in *d_total (device memory); nothing waits
+void rank_index_scan_async(RankWord* table, int n_words, RankIndexScratch& scratch, unsigned* d_total, cudaStream_t s) {
   const int n_blocks = (n_words + SCAN_TILE - 1) / SCAN_TILE;
   scratch.block_sums.ensure((size_t)n_blocks + 1);
-  scratch.total.ensure(1);
   rank_scan_local_kernel<<<n_blocks, SCAN_THREADS, 0, s>>>(table, n_words, scratch.block_sums.ptr);
-  rank_scan_blocks_kernel<<<1, 1024, 0, s>>>(scratch.block_sums.ptr, n_blocks, scratch.total.ptr);
+  rank_scan_blocks_kernel<<<1, 1024, 0, s>>>(scratch.block_sums.ptr, n_blocks, d_total);
   if (n_blocks > 1) rank_scan_apply_kernel<<<n_blocks, SCAN_THREADS, 0, s>>>(table, n_words, scratch.block_sums.ptr);
+}
+
+unsigned rank_index_scan(RankWord* table, int n_words, RankIndexScratch& scratch, cudaStream_t s) {
+  scratch.total.ensure(1);
+  rank_index_scan_async(table, n_words, scratch, scratch.total.ptr, s);
   unsigned total = 0;
   B200_CUDA(cudaMemcpyAsync(&total, scratch.total.ptr, sizeof(unsigned), cudaMemcpyDeviceToHost, s));
   B200_CUDA(cudaStreamSynchronize(s));
@@ -288,11 +293,11 @@ __device__ void d_sym_eigen3(const double* ain, double* ev, double* V) {
 
 // one thread per occupied leaf (voxel_grid_covariance_omp_impl.hpp:282-367)
 __global__ void __launch_bounds__(128) vm_finalize_kernel(const double* __restrict__ acc, const int* __restrict__ leaf_of_rank,
-                                                          size_t n_occ, int min_points, double eig_mult,
+                                                          const unsigned* __restrict__ n_occ_ptr, int min_points, double eig_mult,
                                                           VoxelRecord* rec, double* icov_d, float4* centroids, int* npts,
                                                           unsigned char* valid, RankWord* valid_table) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (r >= n_occ) return;
+  if (r >= (size_t)*n_occ_ptr) return;  // the occupied-leaf count stays on the device: no host round trip mid-build
   const double* a = acc + r * 10;
   const int n_i = (int)(a[9] + 0.5);
   valid[r] = 0;
@@ -347,14 +352,14 @@ __global__ void __launch_bounds__(128) vm_finalize_kernel(const double* __restri
   atomicOr(&valid_table[leaf >> 5].bits, 1u << (leaf & 31));
 }
 
-__global__ void __launch_bounds__(128) vm_compact_kernel(size_t n_occ, const unsigned char* __restrict__ valid,
+__global__ void __launch_bounds__(128) vm_compact_kernel(const unsigned* __restrict__ n_occ_ptr, const unsigned char* __restrict__ valid,
                                                          const int* __restrict__ leaf_of_rank,
                                                          const RankWord* __restrict__ valid_table,
                                                          const VoxelRecord* __restrict__ rec_in, const double* __restrict__ icov_in,
                                                          const float4* __restrict__ cen_in, const int* __restrict__ npts_in,
                                                          VoxelRecord* rec, double* icov_d, float4* centroids, int* npts) {
   size_t r = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (r >= n_occ || !valid[r]) return;
+  if (r >= (size_t)*n_occ_ptr || !valid[r]) return;
   unsigned q = rank_of(valid_table, leaf_of_rank[r]);
   rec[q] = rec_in[r];
   for (int k = 0; k < 9; k++) icov_d[(size_t)q * 9 + k] = icov_in[r * 9 + k];
@@ -363,54 +368,64 @@ __global__ void __launch_bounds__(128) vm_compact_kernel(size_t n_occ, const uns
 }
 
 bool VoxelMap::build(const float4* pts, size_t n, float leaf, int min_points_per_voxel, double min_covar_eigvalue_mult,
-                     cudaStream_t s) {
+                     cudaStream_t s, const Bounds* known_bounds) {
   n_voxels = 0;
   n_occupied = 0;
-  bounds_scratch.ensure(8);
-  Bounds b = cloud_bounds(pts, n, bounds_scratch.ptr, s);
-  launches += 1;
+  Bounds b;
+  if (known_bounds) {  // the caller measured the cloud while uploading it (cloud_codec.cu): no extra pass, no round trip
+    b = *known_bounds;
+  } else {
+    bounds_scratch.ensure(8);
+    b = cloud_bounds(pts, n, bounds_scratch.ptr, s);
+    launches += 1;
+  }
   if (!b.any) return true;
   if (!make_grid_geom(b, leaf, geom)) {
     geom.n_cells = 0;
     geom.n_words = 0;
     return false;
   }
+  // Everything below is enqueued without a single host round trip: buffers are sized by the upper bound
+  // min(points, cells) on the occupied leaves, the kernels read the actual counts from device memory, and both counts
+  // come back in ONE copy at the end.
+  const size_t occ_max = (size_t)std::min<long long>((long long)n, geom.n_cells);
   index_all.ensure((size_t)geom.n_words);
   index.ensure((size_t)geom.n_words);
   cell_of_point.ensure(n);
+  counts.ensure(2);
+  h_counts.ensure(2);
+  acc.ensure(occ_max * 10);
+  leaf_of_rank.ensure(occ_max);
+  tmp_records.ensure(occ_max);
+  tmp_icov.ensure(occ_max * 9);
+  tmp_centroids.ensure(occ_max);
+  tmp_npts.ensure(occ_max);
+  tmp_valid.ensure(occ_max);
+  records.ensure(occ_max + 1);
+  icov_d.ensure(occ_max * 9 + 9);
+  centroids.ensure(occ_max + 1);
+  npts.ensure(occ_max + 1);
   rank_index_clear(index_all.ptr, geom.n_words, s);
   rank_index_clear(index.ptr, geom.n_words, s);
+  B200_CUDA(cudaMemsetAsync(acc.ptr, 0, sizeof(double) * occ_max * 10, s));
   const int blocks = (int)((n + 255) / 256);
   vm_mark_kernel<<<blocks, 256, 0, s>>>(pts, n, geom, index_all.ptr, cell_of_point.ptr);
-  n_occupied = rank_index_scan(index_all.ptr, geom.n_words, scan_scratch, s);
-  launches += 4;
-  if (n_occupied == 0) return true;
-  acc.ensure(n_occupied * 10);
-  leaf_of_rank.ensure(n_occupied);
-  tmp_records.ensure(n_occupied);
-  tmp_icov.ensure(n_occupied * 9);
-  tmp_centroids.ensure(n_occupied);
-  tmp_npts.ensure(n_occupied);
-  tmp_valid.ensure(n_occupied);
-  B200_CUDA(cudaMemsetAsync(acc.ptr, 0, sizeof(double) * n_occupied * 10, s));
+  rank_index_scan_async(index_all.ptr, geom.n_words, scan_scratch, counts.ptr, s);
   vm_accumulate_kernel<<<blocks, 256, 0, s>>>(pts, n, cell_of_point.ptr, index_all.ptr, acc.ptr, leaf_of_rank.ptr);
-  const int vblocks = (int)((n_occupied + 127) / 128);
-  vm_finalize_kernel<<<vblocks, 128, 0, s>>>(acc.ptr, leaf_of_rank.ptr, n_occupied, min_points_per_voxel,
+  const int vblocks = (int)((occ_max + 127) / 128);
+  vm_finalize_kernel<<<vblocks, 128, 0, s>>>(acc.ptr, leaf_of_rank.ptr, counts.ptr, min_points_per_voxel,
                                              min_covar_eigvalue_mult, tmp_records.ptr, tmp_icov.ptr, tmp_centroids.ptr,
                                              tmp_npts.ptr, tmp_valid.ptr, index.ptr);
-  n_voxels = rank_index_scan(index.ptr, geom.n_words, scan_scratch, s);
-  launches += 5;
-  records.ensure(n_voxels + 1);
-  icov_d.ensure(n_voxels * 9 + 9);
-  centroids.ensure(n_voxels + 1);
-  npts.ensure(n_voxels + 1);
-  if (n_voxels > 0) {
-    vm_compact_kernel<<<vblocks, 128, 0, s>>>(n_occupied, tmp_valid.ptr, leaf_of_rank.ptr, index.ptr, tmp_records.ptr,
-                                              tmp_icov.ptr, tmp_centroids.ptr, tmp_npts.ptr, records.ptr, icov_d.ptr,
-                                              centroids.ptr, npts.ptr);
-    launches += 1;
-  }
+  rank_index_scan_async(index.ptr, geom.n_words, scan_scratch, counts.ptr + 1, s);
+  vm_compact_kernel<<<vblocks, 128, 0, s>>>(counts.ptr, tmp_valid.ptr, leaf_of_rank.ptr, index.ptr, tmp_records.ptr,
+                                            tmp_icov.ptr, tmp_centroids.ptr, tmp_npts.ptr, records.ptr, icov_d.ptr,
+                                            centroids.ptr, npts.ptr);
+  launches += 11;
   B200_CUDA(cudaGetLastError());
+  B200_CUDA(cudaMemcpyAsync(h_counts.ptr, counts.ptr, 2 * sizeof(unsigned), cudaMemcpyDeviceToHost, s));
+  B200_CUDA(cudaStreamSynchronize(s));
+  n_occupied = h_counts.ptr[0];
+  n_voxels = h_counts.ptr[1];
   return true;
 }
 

@@ -231,6 +231,30 @@ class NormalDistributionsTransform(_Registration):
         self._check(rc, soft=(_capi.ERR_NO_TARGET,))
         return self._batch_out(res, K)
 
+    def sweep(self, sources, targets, guesses=None, fitness_max_range: float = np.finfo(np.float64).max) -> dict:
+        """The loop-closure candidate sweep on this GPU (b200reg_ndt_sweep): K independent (source, target) pairs through
+        setInputTarget + setInputSource + align + getFitnessScore, pipelined over two internal engines."""
+        K = len(sources)
+        ss = [_as_cloud(c) for c in sources]
+        ts = [_as_cloud(c) for c in targets]
+        stride = ss[0].strides[0] if K else 16
+        if any(c.strides[0] != stride for c in ss + ts):
+            raise ValueError("sweep: all clouds must share one row stride")
+        sp = (C.c_void_p * K)(*[c.ctypes.data for c in ss])
+        tp = (C.c_void_p * K)(*[c.ctypes.data for c in ts])
+        sn = (C.c_size_t * K)(*[len(c) for c in ss])
+        tn = (C.c_size_t * K)(*[len(c) for c in ts])
+        g = np.ascontiguousarray(np.stack([_colmajor(x) for x in guesses])) if guesses is not None else None
+        res = (_capi.SweepResult * max(K, 1))()
+        self._check(self._lib.b200reg_ndt_sweep(self._h, K, sp, sn, tp, tn, stride, _ptr(g) if g is not None else None,
+                                                float(fitness_max_range), res))
+        return {"pose": np.stack([_from_colmajor(np.frombuffer(res[k].final_T, dtype=np.float32).copy()) for k in range(K)]) if K
+                else np.zeros((0, 4, 4), np.float32),
+                "fitness": np.array([res[k].fitness for k in range(K)]),
+                "converged": np.array([res[k].converged for k in range(K)], dtype=np.int32),
+                "iterations": np.array([res[k].iterations for k in range(K)], dtype=np.int32),
+                "status": np.array([res[k].status for k in range(K)], dtype=np.int32)}
+
     def setBatchSlots(self, slots: int):
         self._check(self._lib.b200reg_ndt_set_batch_slots(self._h, int(slots)))
 

@@ -153,3 +153,44 @@ def test_get_aligned_matches_transformed_source(b200, oracle_mod, pair_small):
     To = o.align()
     refo = (To[:3, :3].astype(np.float64) @ p.T.astype(np.float64)).T + To[:3, 3]
     assert np.abs(out[:, :3] - refo).max() < 1e-3
+
+
+def test_sweep_equals_sequential_pairs(b200):
+    """b200reg_ndt_sweep (two engines, two host threads) == the same pairs through setInputTarget + setInputSource + align +
+    getFitnessScore one after the other, bitwise (each pair is computed by exactly the same kernels on the same inputs)."""
+    from lidarslam_ros2_b200 import batch, synth
+
+    srcs, tgts, idx = [], [], []
+    for k, (cfg, res) in enumerate((("small", 2.0), ("tiny", 2.0), ("c1", 2.0), ("small", 2.0), ("tiny", 2.0))):
+        s, t, _ = synth.registration_pair(cfg, 2.0)
+        rng = np.random.default_rng(k)
+        srcs.append((s + rng.normal(0, 0.003, size=s.shape)).astype(np.float32))
+        tgts.append(t)
+        idx.append(10 + k)
+    sw = batch.LoopSweep(b200, device=0, resolution=2.0, max_iterations=100)
+    a = sw.run_sequential(srcs, tgts, idx)
+    for _ in range(2):
+        b = sw.run(srcs, tgts, idx)
+        np.testing.assert_array_equal(a, b)
+    assert sw.run([], [], []).shape == (0, batch.ROW)
+
+
+def test_comm_all_gather_world1(b200):
+    """include/b200comm.h on one GPU: ncclGetUniqueId + ncclCommInitRank(world 1) + ncclAllGather through the C entry points
+    (the N > 1 path is the same call; bench.py --gpus N exercises it)."""
+    import ctypes as C
+
+    from lidarslam_ros2_b200 import _capi
+
+    L = _capi.lib()
+    ident = (C.c_ubyte * 128)()
+    assert L.b200comm_unique_id(ident) == 0, L.b200comm_last_error()
+    h = C.c_void_p()
+    assert L.b200comm_create(ident, 0, 1, 0, C.byref(h)) == 0, L.b200comm_last_error()
+    rows = np.arange(3 * 20, dtype=np.float32).reshape(3, 20)
+    out = np.zeros_like(rows)
+    assert L.b200comm_all_gather_rows(h, rows.ctypes.data, 3, 20, out.ctypes.data) == 0, L.b200comm_last_error()
+    np.testing.assert_array_equal(out, rows)
+    r, w = C.c_int(-1), C.c_int(-1)
+    assert L.b200comm_rank(h, C.byref(r), C.byref(w)) == 0 and (r.value, w.value) == (0, 1)
+    assert L.b200comm_destroy(h) == 0

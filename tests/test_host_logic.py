@@ -18,8 +18,8 @@ def test_cabi_library_exports_every_declared_symbol():
 
     from lidarslam_ros2_b200 import _capi
 
-    header = open(os.path.join(ROOT, "include", "b200reg.h")).read()
-    declared = set(re.findall(r"\b(b200(?:reg|sm)_[a-z0-9_]+)\s*\(", header))
+    header = open(os.path.join(ROOT, "include", "b200reg.h")).read() + open(os.path.join(ROOT, "include", "b200comm.h")).read()
+    declared = set(re.findall(r"\b(b200(?:reg|sm|comm)_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed"
     assert os.path.exists(_capi.LIB_PATH), "build the library first: python -c 'import __graft_entry__ as g; g.build()'"
     lib = C.CDLL(_capi.LIB_PATH)
@@ -189,7 +189,8 @@ def test_abi_header_is_plain_c():
     with tempfile.TemporaryDirectory() as d:
         src = os.path.join(d, "hdr.c")
         with open(src, "w") as f:
-            f.write('#include "b200reg.h"\nint main(void){b200reg_stats s; b200sm_stats t; b200sm_loop_result r; (void)s; (void)t; (void)r; return 0;}\n')
+            f.write('#include "b200reg.h"\n#include "b200comm.h"\nint main(void){b200reg_stats s; b200sm_stats t; b200sm_loop_result r; '
+                    'b200reg_batch_result b; b200reg_sweep_result w; b200comm_t c = 0; (void)s; (void)t; (void)r; (void)b; (void)w; (void)c; return 0;}\n')
         subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
                                "-fsyntax-only", src])
 
