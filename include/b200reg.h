@@ -261,6 +261,17 @@ int b200sm_imu_adjust_distortion(b200sm_t s, float* points, size_t n, size_t str
 int b200sm_imu_get_state(b200sm_t s, int* ptr_front, int* ptr_last, int* ptr_last_iter);
 int b200sm_imu_get_sample(b200sm_t s, int index, double* stamp, float* rpy3, float* shift3, float* velo3);
 
+/* Every candidate instead of the closest one: all older submaps that pass the two gates of
+ * gbs.cpp:187-204 are registered against the newest submap, each exactly like b200sm_search_loop does its single one
+ * (id_min = the candidate's submap id, min_dist = its distance), on the device-resident submaps — nothing is uploaded.
+ * out[0..*n_out) in ascending submap id. shard_rank / shard_world (0 / 1 on one GPU) deal the candidates out across
+ * processes (candidate k -> rank k mod shard_world; *n_candidates_total = all of them); the rows are then all-gathered
+ * with include/b200comm.h.                                                                                          */
+int b200sm_search_loop_all(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double threshold_loop_closure_score,
+                           double distance_loop_closure, double range_of_searching_loop_closure, int search_submap_num,
+                           int shard_rank, int shard_world, b200sm_loop_result* out, size_t capacity, size_t* n_out,
+                           size_t* n_candidates_total);
+
 typedef struct b200sm_stats {
   size_t n_scan, n_filtered, n_targeted, n_submaps;
   int kernel_launches;

@@ -36,7 +36,7 @@ SYMBOLS = [
     "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
     "b200sm_create", "b200sm_destroy", "b200sm_last_error", "b200sm_set_params", "b200sm_set_initial_pose",
     "b200sm_set_scan", "b200sm_update_map", "b200sm_receive_cloud", "b200sm_num_submaps", "b200sm_get_targeted",
-    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats", "b200sm_search_loop",
+    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats", "b200sm_search_loop", "b200sm_search_loop_all",
     "b200sm_imu_set_scan_period", "b200sm_imu_push", "b200sm_deskew_next_scan", "b200sm_imu_adjust_distortion",
     "b200sm_imu_get_state", "b200sm_imu_get_sample",
     # include/b200comm.h
@@ -156,6 +156,7 @@ def lib() -> C.CDLL:
     L.b200sm_get_filtered_scan.argtypes = [vp, vp, sz, C.POINTER(sz)]
     L.b200sm_get_stats.argtypes = [vp, C.POINTER(SmStats)]
     L.b200sm_search_loop.argtypes = [vp, vp, f, d, d, d, i, C.POINTER(SmLoopResult)]
+    L.b200sm_search_loop_all.argtypes = [vp, vp, f, d, d, d, i, i, i, vp, sz, C.POINTER(sz), C.POINTER(sz)]
     L.b200sm_imu_set_scan_period.argtypes = [vp, d]
     L.b200sm_imu_push.argtypes = [vp, vp, vp, vp, d]
     L.b200sm_deskew_next_scan.argtypes = [vp, d]

@@ -16,6 +16,7 @@
 
 using namespace b200;
 
+static size_t g_vg_dense_budget = (size_t)4 << 20;  // b200reg_voxelgrid: dense-bitmap budget in words (debug hook below)
 static constexpr int NDT_BATCH_SLOTS_DEFAULT = 2;  // registrations in flight per batch launch (engine.hpp / ndt_solver.cuh)
 
 struct b200reg_engine {
@@ -559,6 +560,7 @@ int b200reg_voxelgrid(int device, const float* in, size_t n, size_t stride_bytes
       B200_CUDA(cudaStreamCreateWithFlags(&streams[device], cudaStreamNonBlocking));
     }
     VoxelGridFilter& F = *filters[device];
+    F.dense_word_budget = g_vg_dense_budget;
     cudaStream_t s = streams[device];
     *m = 0;
     if (n == 0) return B200REG_OK;
@@ -741,6 +743,13 @@ int b200reg_ndt_get_voxels(b200reg_t h, int* leaf_idx, int* npts, double* mean3,
     }
     return (int)B200REG_OK;
   });
+}
+
+// developer / test hook, not part of include/b200reg.h: size budget (8-byte words) up to which b200reg_voxelgrid uses the
+// dense occupancy bitmap; beyond it the two-level sparse index (voxelgrid.cu). 0 forces the sparse path.
+int b200reg_debug_set_voxelgrid_dense_budget(size_t words) {
+  g_vg_dense_budget = words;
+  return B200REG_OK;
 }
 
 // developer instrumentation, not part of include/b200reg.h: per-round phase stamps of the last solver launch

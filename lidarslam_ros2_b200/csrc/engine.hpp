@@ -258,15 +258,23 @@ void transform_cloud_device(const float4* in, size_t n, float4* out, const float
 struct VoxelGridFilter {
   DeviceBuffer<float4> in;   // xyz + intensity
   DeviceBuffer<float4> out;
-  DeviceBuffer<RankWord> index;
+  DeviceBuffer<RankWord> index;     // dense rank index, or level 1 (pages) of the sparse one
+  DeviceBuffer<RankWord> index_l2;  // sparse form: 32 words per occupied page
   DeviceBuffer<int> cell_of_point;
   DeviceBuffer<double> acc;  // n_vox x 5
   DeviceBuffer<unsigned> bounds_scratch;
+  DeviceBuffer<unsigned> count_dev;
+  PinnedBuffer<unsigned> count_host;
   RankIndexScratch scan_scratch;
   PinnedBuffer<float4> staging;
   int launches = 0;
-  // device-resident core: returns number of output points, or -1 on grid overflow (output = input)
-  long long filter_device(const float4* d_in, size_t n, float leaf, cudaStream_t s);
+  // the dense occupancy bitmap is used up to this many 8-byte words (32 MB); larger bounding boxes take the two-level
+  // sparse index whose memory is O(points), like pcl::VoxelGrid's (voxelgrid.cu)
+  size_t dense_word_budget = (size_t)4 << 20;
+  bool last_sparse = false;
+  // device-resident core: returns number of output points, or -1 on grid overflow (output = input).
+  // known_bounds: min/max of d_in when the caller already has them. One host synchronisation at the end (the count).
+  long long filter_device(const float4* d_in, size_t n, float leaf, cudaStream_t s, const Bounds* known_bounds = nullptr);
 };
 
 }  // namespace b200

@@ -1383,7 +1383,7 @@ void initial_pose(const float* T, const double* p6, double* p0, float* init_fina
   init.mode = EVAL_DERIV;
   init.compute_hessian = compute_hessian;
   init.job = 0;
-  init.pad = 0;
+  for (int k = 0; k < 4; k++) init.pad[k] = 0;
 }
 }  // namespace
 

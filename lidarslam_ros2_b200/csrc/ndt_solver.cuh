@@ -20,15 +20,16 @@ enum EvalMode : int {
 enum SolverPhase : int { PH_INITIAL = 0, PH_LS_FIRST = 1, PH_LS_ITER = 2, PH_LS_HESSIAN = 3 };
 
 // what every CTA needs for one evaluation round; written by the controller (or by the host for round 0)
-struct NdtControl {
+struct alignas(16) NdtControl {  // size is a multiple of 16 bytes: arrays of it are read with 16-byte shared-memory loads
   float T[12];     // 3x4 row-major transform applied to the source points
   float jang[24];  // 8 x 3 f32 angle-Jacobian table   (ndt_omp_impl.hpp:337-345)
   float hang[45];  // 15 x 3 f32 angle-Hessian table    (ndt_omp_impl.hpp:371-391)
   int mode;        // EvalMode
   int compute_hessian;
   int job;         // batch launches: index of the registration this block belongs to (evaluators restage on a change)
-  int pad;
+  int pad[4];
 };
+static_assert(sizeof(NdtControl) % 16 == 0, "NdtControl must keep 16-byte alignment in arrays");
 constexpr int NDT_CONTROL_WORDS = sizeof(NdtControl) / 4;
 
 // controller state (lives in global memory: a different CTA may run the controller every round)

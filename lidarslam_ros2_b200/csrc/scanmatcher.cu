@@ -524,6 +524,126 @@ int b200sm_get_filtered_scan(b200sm_t s, float* out_xyzi, size_t capacity, size_
 
 // GraphBasedSlamComponent::searchLoop (graph_based_slam_component.cpp:144-258) over the session's own submaps — the map
 // array the frontend publishes is the backend's input, here it never left the device.
+}  // extern "C"
+
+namespace {
+
+Mat34f pose_f32(const Submap& sub) {  // affine.matrix().cast<float>()
+  Mat34f T;
+  for (int k = 0; k < 12; k++) T.m[k] = (float)sub.pose[k];
+  return T;
+}
+
+struct LoopCandidate {
+  int id;
+  double dist;
+};
+
+// the gates of :187-204: travelled distance apart, position close — every submap that passes them, ascending id
+std::vector<LoopCandidate> loop_candidates(b200sm_t s, double distance_loop_closure, double range_of_searching_loop_closure) {
+  std::vector<LoopCandidate> out;
+  const int n_sub = (int)s->submaps.size();
+  if (n_sub == 0) return out;
+  const Submap& latest = *s->submaps[n_sub - 1];
+  for (int i = 0; i < n_sub; i++) {
+    const Submap& sub = *s->submaps[i];
+    const double dx = latest.pose[3] - sub.pose[3], dy = latest.pose[7] - sub.pose[7], dz = latest.pose[11] - sub.pose[11];
+    const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
+    if (latest.distance - sub.distance > distance_loop_closure && dist < range_of_searching_loop_closure) out.push_back({i, dist});
+  }
+  return out;
+}
+
+// source = latest submap in the map frame (:165-176), handed to the registration object once per search
+int loop_set_source(b200sm_t s, b200reg_t reg) {
+  const Submap& latest = *s->submaps.back();
+  s->loop_src.ensure(std::max<size_t>(latest.n, 1));
+  if (latest.n == 0) return sm_fail(s, B200REG_ERR_NO_SOURCE, "search_loop: empty source");
+  transform_f32_kernel<<<(int)((latest.n + 255) / 256), 256, 0, s->stream>>>(latest.cloud, latest.n, pose_f32(latest), s->loop_src.ptr);
+  B200_CUDA(cudaGetLastError());
+  s->launches += 1;
+  B200_CUDA(cudaStreamSynchronize(s->stream));
+  const int rc = b200reg_set_input_source_device(reg, s->loop_src.ptr, latest.n);
+  if (rc != B200REG_OK) s->err = std::string("search_loop: ") + b200reg_last_error(reg);
+  return rc;
+}
+
+// one candidate: target = VoxelGrid(voxel_leaf_size) of the submaps id - search_submap_num .. id + search_submap_num
+// (:206-225), align without guess (:229), getFitnessScore (:230), loop edge when the score passes (:232-246).
+// The reference does not test the upper index (undefined behaviour when the window runs past the newest submap);
+// here indices beyond the array are skipped like the negative ones. Nothing is uploaded: the submaps live in HBM.
+int loop_evaluate(b200sm_t s, b200reg_t reg, const LoopCandidate& cand, float voxel_leaf_size, double threshold_loop_closure_score,
+                  int search_submap_num, b200sm_loop_result* out) {
+  const int n_sub = (int)s->submaps.size();
+  const Submap& latest = *s->submaps[n_sub - 1];
+  const int id_min = cand.id;
+  out->is_candidate = 1;
+  out->id_min = id_min;
+  out->min_dist = cand.dist;
+  size_t total = 0;
+  for (int j = 0; j <= 2 * search_submap_num; j++) {
+    const int idx = id_min + j - search_submap_num;
+    if (idx < 0 || idx >= n_sub) continue;
+    total += s->submaps[idx]->n;
+  }
+  s->loop_tgt.ensure(std::max<size_t>(total, 1));
+  size_t off = 0;
+  for (int j = 0; j <= 2 * search_submap_num; j++) {
+    const int idx = id_min + j - search_submap_num;
+    if (idx < 0 || idx >= n_sub) continue;
+    const Submap& sub = *s->submaps[idx];
+    if (sub.n) transform_f32_kernel<<<(int)((sub.n + 255) / 256), 256, 0, s->stream>>>(sub.cloud, sub.n, pose_f32(sub), s->loop_tgt.ptr + off);
+    off += sub.n;
+    s->launches += 1;
+  }
+  B200_CUDA(cudaGetLastError());
+  size_t m = 0;
+  const float4* tgt = filter_on_device(s, s->vg_target, s->loop_tgt.ptr, total, voxel_leaf_size, &m);
+  if (m == 0) return sm_fail(s, B200REG_ERR_NO_TARGET, "search_loop: empty target");
+  B200_CUDA(cudaStreamSynchronize(s->stream));
+  int rc = b200reg_set_input_target_device(reg, tgt, m);
+  float fin[16];
+  if (rc == B200REG_OK) rc = b200reg_align(reg, nullptr, fin);  // :229, no guess
+  double fitness = 0;
+  if (rc == B200REG_OK) rc = b200reg_get_fitness_score(reg, 1.7976931348623157e308, &fitness);  // :230
+  if (rc != B200REG_OK) {
+    s->err = std::string("search_loop: ") + b200reg_last_error(reg);
+    return rc;
+  }
+  out->n_source = latest.n;
+  out->n_target = m;
+  out->fitness = fitness;
+  std::memcpy(out->final_T, fin, sizeof(fin));
+  if (fitness < threshold_loop_closure_score) {  // :232-246: loop edge (id_min, newest), relative pose from^-1 * (final * init)
+    out->accepted = 1;
+    double F[16], to[16], rel[16];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) F[r * 4 + c] = (double)fin[c * 4 + r];
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) {
+        double a = 0;
+        for (int k = 0; k < 4; k++) a += F[r * 4 + k] * latest.pose[k * 4 + c];
+        to[r * 4 + c] = a;
+      }
+    const double* fr = s->submaps[id_min]->pose;  // Isometry3d::inverse(): R^T, -R^T t
+    double inv[16] = {fr[0], fr[4], fr[8], 0, fr[1], fr[5], fr[9], 0, fr[2], fr[6], fr[10], 0, 0, 0, 0, 1};
+    for (int r = 0; r < 3; r++) inv[r * 4 + 3] = -(inv[r * 4 + 0] * fr[3] + inv[r * 4 + 1] * fr[7] + inv[r * 4 + 2] * fr[11]);
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) {
+        double a = 0;
+        for (int k = 0; k < 4; k++) a += inv[r * 4 + k] * to[k * 4 + c];
+        rel[r * 4 + c] = a;
+      }
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) out->relative_pose[c * 4 + r] = rel[r * 4 + c];
+  }
+  return B200REG_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
 int b200sm_search_loop(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double threshold_loop_closure_score,
                        double distance_loop_closure, double range_of_searching_loop_closure, int search_submap_num,
                        b200sm_loop_result* out) {
@@ -531,97 +651,51 @@ int b200sm_search_loop(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double 
   return sm_guarded(s, [&]() {
     std::memset(out, 0, sizeof(*out));
     out->id_min = -1;
-    const int n_sub = (int)s->submaps.size();
-    if (n_sub == 0) return (int)B200REG_OK;
-    const Submap& latest = *s->submaps[n_sub - 1];
-    // candidate = older submap reached again: travelled distance apart, position close; the closest one wins (:187-204)
-    double min_dist = 1.7976931348623157e308;
-    int id_min = 0;
-    bool is_candidate = false;
-    for (int i = 0; i < n_sub; i++) {
-      const Submap& sub = *s->submaps[i];
-      const double dx = latest.pose[3] - sub.pose[3], dy = latest.pose[7] - sub.pose[7], dz = latest.pose[11] - sub.pose[11];
-      const double dist = std::sqrt(dx * dx + dy * dy + dz * dz);
-      if (latest.distance - sub.distance > distance_loop_closure && dist < range_of_searching_loop_closure) {
-        is_candidate = true;
-        if (dist < min_dist) {
-          id_min = i;
-          min_dist = dist;
-        }
+    // the closest of the submaps that pass the gates wins (:193-201; the first one on a tie, like the strict `<`)
+    const std::vector<LoopCandidate> cands = loop_candidates(s, distance_loop_closure, range_of_searching_loop_closure);
+    if (cands.empty()) return (int)B200REG_OK;
+    LoopCandidate best = cands[0];
+    for (const LoopCandidate& c : cands)
+      if (c.dist < best.dist) best = c;
+    out->is_candidate = 1;
+    out->id_min = best.id;
+    out->min_dist = best.dist;
+    int rc = loop_set_source(s, reg);
+    if (rc != B200REG_OK) return rc;
+    return loop_evaluate(s, reg, best, voxel_leaf_size, threshold_loop_closure_score, search_submap_num, out);
+  });
+}
+
+// The generalisation SURVEY.md section 8f row 2 names: EVERY submap that passes the two gates is registered against the
+// newest one (the reference keeps only the closest), all on the device-resident submaps. shard_rank / shard_world
+// (0 / 1 on one GPU) deal the candidates out across processes: candidate k (ascending submap id) belongs to rank
+// k mod shard_world; the caller all-gathers the rows (include/b200comm.h).
+int b200sm_search_loop_all(b200sm_t s, b200reg_t reg, float voxel_leaf_size, double threshold_loop_closure_score,
+                           double distance_loop_closure, double range_of_searching_loop_closure, int search_submap_num,
+                           int shard_rank, int shard_world, b200sm_loop_result* out, size_t capacity, size_t* n_out,
+                           size_t* n_candidates_total) {
+  if (!s || !reg || !n_out || !(voxel_leaf_size > 0) || search_submap_num < 0 || shard_world < 1 || shard_rank < 0 ||
+      shard_rank >= shard_world || (!out && capacity))
+    return B200REG_ERR_ARG;
+  return sm_guarded(s, [&]() {
+    *n_out = 0;
+    const std::vector<LoopCandidate> cands = loop_candidates(s, distance_loop_closure, range_of_searching_loop_closure);
+    if (n_candidates_total) *n_candidates_total = cands.size();
+    if (cands.empty()) return (int)B200REG_OK;
+    bool have_source = false;
+    for (size_t k = 0; k < cands.size(); k++) {
+      if ((int)(k % (size_t)shard_world) != shard_rank) continue;
+      if (*n_out >= capacity) break;
+      if (!have_source) {
+        const int rc = loop_set_source(s, reg);
+        if (rc != B200REG_OK) return rc;
+        have_source = true;
       }
-    }
-    out->is_candidate = is_candidate ? 1 : 0;
-    if (!is_candidate) return (int)B200REG_OK;
-    out->id_min = id_min;
-    out->min_dist = min_dist;
-    auto pose_f32 = [](const Submap& sub) {  // affine.matrix().cast<float>()
-      Mat34f T;
-      for (int k = 0; k < 12; k++) T.m[k] = (float)sub.pose[k];
-      return T;
-    };
-    // source = latest submap in the map frame (:165-176)
-    s->loop_src.ensure(std::max<size_t>(latest.n, 1));
-    if (latest.n) transform_f32_kernel<<<(int)((latest.n + 255) / 256), 256, 0, s->stream>>>(latest.cloud, latest.n, pose_f32(latest), s->loop_src.ptr);
-    // target = VoxelGrid(voxel_leaf_size) of the submaps id_min - search_submap_num .. id_min + search_submap_num (:206-225).
-    // The reference does not test the upper index (undefined behaviour when the window runs past the newest submap);
-    // here indices beyond the array are skipped like the negative ones.
-    size_t total = 0;
-    for (int j = 0; j <= 2 * search_submap_num; j++) {
-      const int idx = id_min + j - search_submap_num;
-      if (idx < 0 || idx >= n_sub) continue;
-      total += s->submaps[idx]->n;
-    }
-    s->loop_tgt.ensure(std::max<size_t>(total, 1));
-    size_t off = 0;
-    for (int j = 0; j <= 2 * search_submap_num; j++) {
-      const int idx = id_min + j - search_submap_num;
-      if (idx < 0 || idx >= n_sub) continue;
-      const Submap& sub = *s->submaps[idx];
-      if (sub.n) transform_f32_kernel<<<(int)((sub.n + 255) / 256), 256, 0, s->stream>>>(sub.cloud, sub.n, pose_f32(sub), s->loop_tgt.ptr + off);
-      off += sub.n;
-      s->launches += 1;
-    }
-    B200_CUDA(cudaGetLastError());
-    size_t m = 0;
-    const float4* tgt = filter_on_device(s, s->vg_target, s->loop_tgt.ptr, total, voxel_leaf_size, &m);
-    if (latest.n == 0 || m == 0) return sm_fail(s, B200REG_ERR_NO_TARGET, "search_loop: empty source or target");
-    B200_CUDA(cudaStreamSynchronize(s->stream));
-    int rc = b200reg_set_input_source_device(reg, s->loop_src.ptr, latest.n);
-    if (rc == B200REG_OK) rc = b200reg_set_input_target_device(reg, tgt, m);
-    float fin[16];
-    if (rc == B200REG_OK) rc = b200reg_align(reg, nullptr, fin);  // :229, no guess
-    double fitness = 0;
-    if (rc == B200REG_OK) rc = b200reg_get_fitness_score(reg, 1.7976931348623157e308, &fitness);  // :230
-    if (rc != B200REG_OK) {
-      s->err = std::string("search_loop: ") + b200reg_last_error(reg);
-      return rc;
-    }
-    out->n_source = latest.n;
-    out->n_target = m;
-    out->fitness = fitness;
-    std::memcpy(out->final_T, fin, sizeof(fin));
-    if (fitness < threshold_loop_closure_score) {  // :232-246: loop edge (id_min, newest), relative pose from^-1 * (final * init)
-      out->accepted = 1;
-      double F[16], to[16], rel[16];
-      for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) F[r * 4 + c] = (double)fin[c * 4 + r];
-      for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) {
-          double a = 0;
-          for (int k = 0; k < 4; k++) a += F[r * 4 + k] * latest.pose[k * 4 + c];
-          to[r * 4 + c] = a;
-        }
-      const double* fr = s->submaps[id_min]->pose;  // Isometry3d::inverse(): R^T, -R^T t
-      double inv[16] = {fr[0], fr[4], fr[8], 0, fr[1], fr[5], fr[9], 0, fr[2], fr[6], fr[10], 0, 0, 0, 0, 1};
-      for (int r = 0; r < 3; r++) inv[r * 4 + 3] = -(inv[r * 4 + 0] * fr[3] + inv[r * 4 + 1] * fr[7] + inv[r * 4 + 2] * fr[11]);
-      for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) {
-          double a = 0;
-          for (int k = 0; k < 4; k++) a += inv[r * 4 + k] * to[k * 4 + c];
-          rel[r * 4 + c] = a;
-        }
-      for (int r = 0; r < 4; r++)
-        for (int c = 0; c < 4; c++) out->relative_pose[c * 4 + r] = rel[r * 4 + c];
+      b200sm_loop_result* r = out + *n_out;
+      std::memset(r, 0, sizeof(*r));
+      const int rc = loop_evaluate(s, reg, cands[k], voxel_leaf_size, threshold_loop_closure_score, search_submap_num, r);
+      if (rc != B200REG_OK) return rc;
+      *n_out += 1;
     }
     return (int)B200REG_OK;
   });

@@ -106,6 +106,28 @@ class ScanMatcher:
                 out["relative_pose"] = np.array(r.relative_pose, dtype=np.float64).reshape(4, 4).T.copy()
         return out
 
+    def searchLoopAll(self, registration, voxel_leaf_size: float = 0.2, threshold_loop_closure_score: float = 1.0,
+                      distance_loop_closure: float = 20.0, range_of_searching_loop_closure: float = 20.0,
+                      search_submap_num: int = 3, shard_rank: int = 0, shard_world: int = 1) -> list:
+        """Every gated candidate instead of the closest one (b200sm_search_loop_all); one dict per candidate, ascending id."""
+        cap = max(1, self.numSubmaps())
+        arr = (_capi.SmLoopResult * cap)()
+        n, tot = C.c_size_t(0), C.c_size_t(0)
+        self._check(self._lib.b200sm_search_loop_all(self._h, registration._h, float(voxel_leaf_size), float(threshold_loop_closure_score),
+                                                     float(distance_loop_closure), float(range_of_searching_loop_closure),
+                                                     int(search_submap_num), int(shard_rank), int(shard_world), arr, cap,
+                                                     C.byref(n), C.byref(tot)))
+        out = []
+        for k in range(n.value):
+            r = arr[k]
+            d = {"is_candidate": True, "id_min": int(r.id_min), "accepted": bool(r.accepted), "min_dist": float(r.min_dist),
+                 "fitness": float(r.fitness), "n_source": int(r.n_source), "n_target": int(r.n_target),
+                 "final": np.array(r.final_T, dtype=np.float32).reshape(4, 4).T.copy(), "n_candidates_total": int(tot.value)}
+            if r.accepted:
+                d["relative_pose"] = np.array(r.relative_pose, dtype=np.float64).reshape(4, 4).T.copy()
+            out.append(d)
+        return out
+
     # ---- read-back ----
     def stats(self) -> dict:
         st = _capi.SmStats()

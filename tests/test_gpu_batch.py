@@ -194,3 +194,29 @@ def test_comm_all_gather_world1(b200):
     r, w = C.c_int(-1), C.c_int(-1)
     assert L.b200comm_rank(h, C.byref(r), C.byref(w)) == 0 and (r.value, w.value) == (0, 1)
     assert L.b200comm_destroy(h) == 0
+
+
+def test_voxelgrid_sparse_index_equals_dense(b200, oracle_mod):
+    """pcl::VoxelGrid on a bounding box too large for a dense occupancy bitmap: the two-level sparse rank index (O(points)
+    memory) must give the dense path's output — same leaves in the same (ascending leaf index) order — and the oracle's."""
+    import ctypes as C
+
+    from lidarslam_ros2_b200 import _capi, synth
+
+    src, _, _ = synth.registration_pair("c1", 2.0)
+    pts = np.concatenate([src[:, :3], np.linspace(0, 1, len(src), dtype=np.float32)[:, None]], axis=1)
+    L = _capi.lib()
+    L.b200reg_debug_set_voxelgrid_dense_budget.argtypes = [C.c_size_t]
+    try:
+        for leaf in (0.5, 0.05):
+            L.b200reg_debug_set_voxelgrid_dense_budget(4 << 20)
+            dense = b200.voxel_grid_filter(pts, leaf)
+            L.b200reg_debug_set_voxelgrid_dense_budget(0)
+            sparse = b200.voxel_grid_filter(pts, leaf)
+            assert dense.shape == sparse.shape and len(dense) > 100
+            np.testing.assert_allclose(sparse, dense, rtol=0, atol=1e-6)
+            ref = oracle_mod.voxelgrid(pts, leaf)
+            assert ref.shape == sparse.shape
+            np.testing.assert_allclose(sparse, ref, atol=5e-5)
+    finally:
+        L.b200reg_debug_set_voxelgrid_dense_budget(4 << 20)

@@ -89,23 +89,52 @@ def test_gicp_align_parity(b200, oracle_mod):
     assert dt < 1e-3 and dr < 1e-3, (dt, dr)
 
 
-def test_gicp_on_lidar_scene(b200, oracle_mod, pair_tiny):
+@pytest.mark.parametrize("cfg", ["tiny", "small", "c1"])
+def test_gicp_on_lidar_scene(b200, oracle_mod, cfg):
+    """LiDAR-like scenes (ray-cast rings against the street canyon): the weakly constrained direction along the canyon makes
+    the capped inner BFGS (20 iterations, gicp_omp_impl.hpp:218-230) path-dependent — its line search compares f32 cost
+    values (:264-270) — so parity needs the same un-fused float arithmetic on both sides (gicp.cu is built with -fmad=false;
+    round 1 compared 5e-2 m here). Node parameters (scanmatcher_component.cpp:116-120) and the class defaults."""
     from lidarslam_ros2_b200 import synth
 
-    src, tgt, _ = pair_tiny
+    src, tgt, _ = synth.registration_pair(cfg, 2.0)
+    for eps in (1e-8, None):
+        g = b200.GeneralizedIterativeClosestPoint()
+        g.setMaxCorrespondenceDistance(5.0)
+        o = oracle_mod.GICP(max_correspondence_distance=5.0)
+        if eps is not None:
+            g.setTransformationEpsilon(eps)
+            o.set("transformation_epsilon", eps)
+        g.setInputTarget(tgt)
+        g.setInputSource(src)
+        o.set_target(tgt)
+        o.set_source(src)
+        Tg, To = g.align(), o.align()
+        dt, dr = synth.pose_error(Tg, To)
+        assert g.hasConverged() == o.converged
+        assert dt < 1e-3 and dr < 1e-3, (cfg, eps, dt, dr, g.stats()["iterations"], o.iterations)
+        assert g.numCorrespondences() == o.num_correspondences()
+        assert abs(g.getFitnessScore() - o.fitness()) <= 1e-3 * o.fitness()
+
+
+def test_gicp_parity_baseline_c3_size(b200, oracle_mod):
+    """BASELINE config 3 at full size: GICP, 64-ring scan (~94k pts) against the 1M-point map, corr_dist_threshold 5.0,
+    transformation_epsilon 1e-8 (sm.cpp:118-119), k = 20; outer iterations bounded to keep the CPU side to about a minute."""
+    from lidarslam_ros2_b200 import synth
+
+    src, tgt, T_gt = synth.registration_pair("headline", 2.0)
     g = b200.GeneralizedIterativeClosestPoint()
     g.setMaxCorrespondenceDistance(5.0)
+    g.setTransformationEpsilon(1e-8)
+    g.setMaximumIterations(6)
+    o = oracle_mod.GICP(max_correspondence_distance=5.0, transformation_epsilon=1e-8, max_iterations=6)
     g.setInputTarget(tgt)
     g.setInputSource(src)
-    o = oracle_mod.GICP(max_correspondence_distance=5.0)
     o.set_target(tgt)
     o.set_source(src)
     Tg, To = g.align(), o.align()
     dt, dr = synth.pose_error(Tg, To)
-    # A sparse LiDAR scan has line-like 20-NN neighbourhoods (points of one ring): the covariance then has two nearly
-    # equal small singular values and the direction that receives gicp_epsilon (last column of U, gicp_omp_impl.hpp:
-    # 110-120) is decided by rounding noise / the SVD's sweep order — implementation-defined even between Eigen versions.
-    # Only a loose agreement can be asserted here; the tight 1e-3 parity is asserted on well-conditioned surfaces above.
-    assert g.hasConverged() == o.converged
-    assert dt < 5e-2 and dr < 1e-2, (dt, dr)
-    assert abs(g.getFitnessScore() - o.fitness()) <= 0.05 * o.fitness()
+    assert dt < 1e-3 and dr < 1e-3, (dt, dr)
+    assert g.numCorrespondences() == o.num_correspondences()
+    et, er = synth.pose_error(Tg, T_gt)
+    assert et < 0.15 and er < 5e-3  # and it registers: close to the pose the scan was ray-cast from

@@ -176,3 +176,39 @@ def test_search_loop_parity():
     assert dt < 2e-3 and dr < 1e-3
     none = g.searchLoop(greg, voxel_leaf_size=0.3, distance_loop_closure=50.0, range_of_searching_loop_closure=1.0, search_submap_num=1)
     assert not none["is_candidate"] and none["id_min"] == -1
+
+
+@pytest.mark.gpu
+def test_search_loop_all_candidates():
+    """b200sm_search_loop_all: every gated candidate, each registered exactly like searchLoop registers its single one. With a
+    wide gate on the out-and-back drive several old submaps qualify; the closest one must reproduce searchLoop bitwise, the
+    set must be the gate's set, and the shards of a 2-way split must reassemble the full list."""
+    from lidarslam_ros2_b200.scanmatcher import ScanMatcher, backend_registration
+
+    kw = dict(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.3, num_targeted_cloud=3)
+    g = ScanMatcher(**kw)
+    poses = []
+    for scan, T in _out_and_back():
+        g.setScan(scan)
+        g.updateMap(T.astype(np.float32), T[:3, 3], osm.quat_from_matrix(T[:3, :3]), adopt_now=False)
+        poses.append(T)
+    greg = backend_registration("NDT", ndt_resolution=2.0)
+    args = dict(voxel_leaf_size=0.3, distance_loop_closure=5.0, range_of_searching_loop_closure=4.5, search_submap_num=1)
+    single = g.searchLoop(greg, **args)
+    allc = g.searchLoopAll(greg, **args)
+    assert len(allc) >= 2 and allc[0]["n_candidates_total"] == len(allc)
+    ids = [c["id_min"] for c in allc]
+    assert ids == sorted(ids)
+    # the gate, recomputed here: travelled distance > 5 m behind the newest submap and position within 4.5 m
+    latest = poses[-1][:3, 3]
+    dist_along = np.concatenate([[0.0], np.cumsum([np.linalg.norm(poses[k][:3, 3] - poses[k - 1][:3, 3]) for k in range(1, len(poses))])])
+    want = [k for k in range(len(poses)) if dist_along[-1] - dist_along[k] > 5.0 and np.linalg.norm(latest - poses[k][:3, 3]) < 4.5]
+    assert ids == want, (ids, want)
+    best = min(allc, key=lambda c: c["min_dist"])
+    assert best["id_min"] == single["id_min"] and np.array_equal(best["final"], single["final"]) and best["fitness"] == single["fitness"]
+    assert all(c["fitness"] > 0 and c["n_target"] > 0 for c in allc)
+    shards = g.searchLoopAll(greg, shard_rank=0, shard_world=2, **args) + g.searchLoopAll(greg, shard_rank=1, shard_world=2, **args)
+    shards.sort(key=lambda c: c["id_min"])
+    assert [c["id_min"] for c in shards] == ids
+    for a, b in zip(shards, allc):
+        assert np.array_equal(a["final"], b["final"]) and a["fitness"] == b["fitness"]
