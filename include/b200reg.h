@@ -169,6 +169,10 @@ typedef struct b200reg_stats {
   int kernel_launches;    /* kernels launched by this handle since creation                              */
   int grid_ctas, block_threads, index_in_smem;
   long long n_voxels, n_cells, n_source, n_target;
+  /* GICP: the persistent inner-loop kernel(s) of the last align (estimateRigidTransformationBFGS on the device)      */
+  float gicp_inner_ms;             /* their summed device time (CUDA events on the handle's stream)                  */
+  int gicp_inner_launches;         /* = outer iterations                                                            */
+  double gicp_pair_evaluations;    /* sum over cost / gradient evaluations of the number of correspondences          */
 } b200reg_stats;
 int b200reg_get_stats(b200reg_t h, b200reg_stats* out);
 
@@ -260,6 +264,12 @@ int b200sm_imu_adjust_distortion(b200sm_t s, float* points, size_t n, size_t str
 /* read-back for the parity tests: imu_ptr_front_, imu_ptr_last_, imu_ptr_last_iter_; one ring entry                */
 int b200sm_imu_get_state(b200sm_t s, int* ptr_front, int* ptr_last, int* ptr_last_iter);
 int b200sm_imu_get_sample(b200sm_t s, int index, double* stamp, float* rpy3, float* shift3, float* velo3);
+
+/* A backend in its OWN process gets the submaps as lidarslam_msgs/SubMap (voxel-filtered cloud in the sensor frame, pose,
+ * travelled distance; gbs.cpp:91-101): append one to the session (uploaded once, then device-resident like the
+ * frontend's own). pose: 4x4 column-major double (Eigen::Affine3d::matrix().data()).                                 */
+int b200sm_import_submap(b200sm_t s, const float* points, size_t n, size_t stride_bytes, long intensity_offset_bytes,
+                         const double* pose_colmajor16, double distance);
 
 /* Every candidate instead of the closest one: all older submaps that pass the two gates of
  * gbs.cpp:187-204 are registered against the newest submap, each exactly like b200sm_search_loop does its single one

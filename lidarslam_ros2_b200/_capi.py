@@ -8,7 +8,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 REPO_ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "csrc", "libb200reg.so")
+LIB_PATH = os.path.join(_HERE, "csrc", os.environ.get("B200REG_LIB_VARIANT", "libb200reg.so"))  # variant: developer A/B builds
 
 OK, ERR_ARG, ERR_NO_TARGET, ERR_NO_SOURCE, ERR_CUDA, ERR_TIMEOUT, ERR_GRID = 0, -1, -2, -3, -4, -5, -6
 NDT, GICP = 0, 1
@@ -36,7 +36,7 @@ SYMBOLS = [
     "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
     "b200sm_create", "b200sm_destroy", "b200sm_last_error", "b200sm_set_params", "b200sm_set_initial_pose",
     "b200sm_set_scan", "b200sm_update_map", "b200sm_receive_cloud", "b200sm_num_submaps", "b200sm_get_targeted",
-    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats", "b200sm_search_loop", "b200sm_search_loop_all",
+    "b200sm_get_submap", "b200sm_get_filtered_scan", "b200sm_get_stats", "b200sm_search_loop", "b200sm_search_loop_all", "b200sm_import_submap",
     "b200sm_imu_set_scan_period", "b200sm_imu_push", "b200sm_deskew_next_scan", "b200sm_imu_adjust_distortion",
     "b200sm_imu_get_state", "b200sm_imu_get_sample",
     # include/b200comm.h
@@ -73,6 +73,7 @@ class Stats(C.Structure):
         ("kernel_launches", C.c_int),
         ("grid_ctas", C.c_int), ("block_threads", C.c_int), ("index_in_smem", C.c_int),
         ("n_voxels", C.c_longlong), ("n_cells", C.c_longlong), ("n_source", C.c_longlong), ("n_target", C.c_longlong),
+        ("gicp_inner_ms", C.c_float), ("gicp_inner_launches", C.c_int), ("gicp_pair_evaluations", C.c_double),
     ]
 
 
@@ -157,6 +158,7 @@ def lib() -> C.CDLL:
     L.b200sm_get_stats.argtypes = [vp, C.POINTER(SmStats)]
     L.b200sm_search_loop.argtypes = [vp, vp, f, d, d, d, i, C.POINTER(SmLoopResult)]
     L.b200sm_search_loop_all.argtypes = [vp, vp, f, d, d, d, i, i, i, vp, sz, C.POINTER(sz), C.POINTER(sz)]
+    L.b200sm_import_submap.argtypes = [vp, vp, sz, sz, C.c_long, vp, d]
     L.b200sm_imu_set_scan_period.argtypes = [vp, d]
     L.b200sm_imu_push.argtypes = [vp, vp, vp, vp, d]
     L.b200sm_deskew_next_scan.argtypes = [vp, d]

@@ -516,7 +516,7 @@ int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out) {
 }
 
 int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes) {
-  if (!h || !out || stride_bytes < 12) return B200REG_ERR_ARG;
+  if (!h || !out || stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
   return guarded(h, [&]() {
     if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "no input source");
     h->d_aligned.ensure(h->n_source);
@@ -542,7 +542,9 @@ int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes) {
 // ---- VoxelGrid ---------------------------------------------------------------------------------------------
 int b200reg_voxelgrid(int device, const float* in, size_t n, size_t stride_bytes, long intensity_offset_bytes, float leaf,
                       float* out, size_t out_capacity, size_t* m) {
-  if (!in || !out || !m || stride_bytes < 12 || !(leaf > 0)) return B200REG_ERR_ARG;
+  if (!in || !out || !m || stride_bytes < 12 || (stride_bytes % 4) != 0 || !(leaf > 0) ||
+      (intensity_offset_bytes >= 0 && (intensity_offset_bytes % 4) != 0))
+    return B200REG_ERR_ARG;  // float fields: records and offsets are 4-byte aligned
   static std::mutex mu;
   std::lock_guard<std::mutex> lock(mu);
   try {
@@ -617,6 +619,9 @@ int b200reg_get_stats(b200reg_t h, b200reg_stats* out) {
   out->n_cells = h->map.geom.n_cells;
   out->n_source = (long long)h->n_source;
   out->n_target = (long long)h->n_target;
+  out->gicp_inner_ms = h->gicp_solver.inner_ms;
+  out->gicp_inner_launches = h->gicp_solver.inner_launches;
+  out->gicp_pair_evaluations = h->gicp_solver.inner_pair_evaluations;
   return B200REG_OK;
 }
 
@@ -686,7 +691,7 @@ int b200reg_ndt_hessian_radius(b200reg_t h, const float* T, const double* p6, do
 }
 
 int b200reg_ndt_calculate_score(b200reg_t h, const float* base, size_t n, size_t stride_bytes, double* out) {
-  if (!h || h->kind != B200REG_NDT || !base || !out || stride_bytes < 12) return B200REG_ERR_ARG;
+  if (!h || h->kind != B200REG_NDT || !base || !out || stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
   return guarded(h, [&]() {
     if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
     ensure_map(h);
@@ -785,7 +790,7 @@ int b200reg_gicp_num_correspondences(b200reg_t h, int* out) {
 }
 
 int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, int* idx, float* d2) {
-  if (!h || !base || !idx || !d2 || stride_bytes < 12) return B200REG_ERR_ARG;
+  if (!h || !base || !idx || !d2 || stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
   return guarded(h, [&]() {
     if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "no input target");
     if (n == 0) return (int)B200REG_OK;

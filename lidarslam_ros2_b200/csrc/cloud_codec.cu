@@ -4,6 +4,7 @@
 // scanmatcher_component.cpp:202, 457) — and re-packs them on the CPU. Here the raw records go to the GPU in ONE bulk
 // copy (straight from the caller's buffer when it is pinned, else through a pinned staging copy made with memcpy) and a
 // kernel unpacks them into the float4 (x, y, z, w) layout every other kernel reads.
+#include <algorithm>
 #include <cstring>
 
 #include "engine.hpp"
@@ -73,6 +74,21 @@ __global__ void unpack_points_bounds_kernel(const unsigned char* __restrict__ ra
     }
   }
 }
+// host -> device copy of `bytes`. Pinned memory goes out in one DMA; pageable memory (a pcl::PointCloud, a numpy array) is
+// staged through the pinned buffer in 2 MB pieces, each piece's DMA enqueued as soon as it is staged, so that the copy
+// engine works on piece k while the CPU copies piece k + 1 (the staging buffer holds the whole cloud: no piece is reused).
+void staged_h2d(void* d_dst, const void* host, size_t bytes, bool pinned, unsigned char* staging, cudaStream_t s) {
+  if (pinned) {
+    B200_CUDA(cudaMemcpyAsync(d_dst, host, bytes, cudaMemcpyHostToDevice, s));
+    return;
+  }
+  constexpr size_t PIECE = (size_t)2 << 20;
+  for (size_t off = 0; off < bytes; off += PIECE) {
+    const size_t len = std::min(PIECE, bytes - off);
+    std::memcpy(staging + off, static_cast<const unsigned char*>(host) + off, len);
+    B200_CUDA(cudaMemcpyAsync(static_cast<unsigned char*>(d_dst) + off, staging + off, len, cudaMemcpyHostToDevice, s));
+  }
+}
 }  // namespace
 
 // upload + bounds: the result is valid after the caller has synchronised the stream (finish_bounds)
@@ -84,16 +100,11 @@ void CloudUploader::upload_with_bounds(const void* host, size_t n, size_t stride
   bounds_dev.ensure(8);
   bounds_host.ensure(8);
   const bool pinned = is_pinned(host);
-  const void* src = host;
-  if (!pinned) {
-    staging.ensure(bytes);
-    std::memcpy(staging.ptr, host, bytes);
-    src = staging.ptr;
-  }
+  if (!pinned) staging.ensure(bytes);
   const unsigned init[6] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u};
   std::memcpy(bounds_host.ptr, init, sizeof(init));
   B200_CUDA(cudaMemcpyAsync(bounds_dev.ptr, bounds_host.ptr, sizeof(init), cudaMemcpyHostToDevice, s));
-  B200_CUDA(cudaMemcpyAsync(raw.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+  staged_h2d(raw.ptr, host, bytes, pinned, staging.ptr, s);
   unpack_points_bounds_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(raw.ptr, n, stride, w_off, w_default, dst, bounds_dev.ptr);
   B200_CUDA(cudaGetLastError());
   B200_CUDA(cudaMemcpyAsync(bounds_host.ptr, bounds_dev.ptr, sizeof(init), cudaMemcpyDeviceToHost, s));
@@ -114,16 +125,9 @@ void CloudUploader::upload(const void* host, size_t n, size_t stride, long w_off
   if (n == 0) return;
   const size_t bytes = n * stride;
   raw.ensure(bytes);
-  cudaPointerAttributes attr{};
-  const bool pinned = cudaPointerGetAttributes(&attr, host) == cudaSuccess && attr.type == cudaMemoryTypeHost;
-  if (!pinned) cudaGetLastError();  // older drivers report unregistered memory as an error
-  const void* src = host;
-  if (!pinned) {
-    staging.ensure(bytes);
-    std::memcpy(staging.ptr, host, bytes);
-    src = staging.ptr;
-  }
-  B200_CUDA(cudaMemcpyAsync(raw.ptr, src, bytes, cudaMemcpyHostToDevice, s));
+  const bool pinned = is_pinned(host);
+  if (!pinned) staging.ensure(bytes);
+  staged_h2d(raw.ptr, host, bytes, pinned, staging.ptr, s);
   unpack_points_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(raw.ptr, n, stride, w_off, w_default, dst);
   B200_CUDA(cudaGetLastError());
   launches += 1;
@@ -146,12 +150,7 @@ void CloudUploader::upload_at(const void* host, bool pinned, size_t n, size_t st
                               size_t byte_offset, cudaStream_t s) {
   if (n == 0) return;
   const size_t bytes = n * stride;
-  const void* src = host;
-  if (!pinned) {
-    std::memcpy(staging.ptr + byte_offset, host, bytes);
-    src = staging.ptr + byte_offset;
-  }
-  B200_CUDA(cudaMemcpyAsync(raw.ptr + byte_offset, src, bytes, cudaMemcpyHostToDevice, s));
+  staged_h2d(raw.ptr + byte_offset, host, bytes, pinned, staging.ptr + byte_offset, s);
   unpack_points_kernel<<<(int)((n + 255) / 256), 256, 0, s>>>(raw.ptr + byte_offset, n, stride, w_off, w_default, dst);
   B200_CUDA(cudaGetLastError());
   launches += 1;

@@ -47,6 +47,11 @@ class GicpSolver {
   // true: estimateRigidTransformationBFGS runs as ONE persistent cooperative kernel per outer iteration (BFGS on the
   // device); false: host-side BFGS, one K7 launch + synchronisation per functor evaluation
   bool device_bfgs = true;
+  // accounting of the last align(): device time of the persistent inner kernel(s), their launches, and the
+  // (correspondence, evaluation) products they processed (algorithmic bytes = that times 72)
+  float inner_ms = 0;
+  int inner_launches = 0;
+  double inner_pair_evaluations = 0;
 
  private:
   void fdf(const float* T_rowmajor16, bool want_grad, double* f, double* g_t3, double* R9);
@@ -55,6 +60,7 @@ class GicpSolver {
   GicpInnerWork* d_inner_work_ = nullptr;
   GicpInnerResult* h_inner_result_ = nullptr;  // pinned
   unsigned inner_epoch_ = 0;
+  cudaEvent_t ev0_ = nullptr, ev1_ = nullptr;
   int sm_count_ = 0;
   int device_ = 0;
   cudaStream_t stream_ = nullptr;

@@ -26,6 +26,10 @@
 // Algorithmic HBM bytes per evaluation: N_src*16 + N_src*probes*8 + N_hit*48 + 28*8.
 #include "ndt_solver.cuh"
 
+#ifndef B200_SKIP_EMPTY_PROBES
+#define B200_SKIP_EMPTY_PROBES 1  // developer switch for A/B measurements (build with -DB200_SKIP_EMPTY_PROBES=0)
+#endif
+
 namespace b200 {
 
 namespace {
@@ -257,9 +261,13 @@ __device__ __forceinline__ void process_point(const NdtLaunch& L, const NdtContr
       r[4] = (xz && (unsigned)(rj - 1) < (unsigned)g.div_b[1]) ? probe_lin(idx, lin - g.mul[1]) : -1;
       r[5] = (xy && (unsigned)(rk + 1) < (unsigned)g.div_b[2]) ? probe_lin(idx, lin + g.mul[2]) : -1;
       r[6] = (xy && (unsigned)(rk - 1) < (unsigned)g.div_b[2]) ? probe_lin(idx, lin - g.mul[2]) : -1;
+      // A neighbour that NO lane of the warp has (the +-z cells of ground points, the far side of a facade) is skipped as a
+      // whole: a warp holds 32 consecutive points of one LiDAR ring, so its lanes mostly miss the same cells. Masked lanes
+      // contribute exact zeros, so skipping a probe nobody hit changes no bit of the sums.
 #pragma unroll
       for (int k = 0; k < 7; k++)
-        accumulate_pair<HESS>(load_record(L.records + max(r[k], 0)), r[k] >= 0, xt, d1f, gd2, ps);
+        if (!B200_SKIP_EMPTY_PROBES || __any_sync(__activemask(), r[k] >= 0))  // (a lane that hit is in the mask itself)
+          accumulate_pair<HESS>(load_record(L.records + max(r[k], 0)), r[k] >= 0, xt, d1f, gd2, ps);
     } else {
       accumulate_pair<HESS>(load_record(L.records + max(r[0], 0)), r[0] >= 0, xt, d1f, gd2, ps);
     }

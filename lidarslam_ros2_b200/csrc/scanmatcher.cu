@@ -393,7 +393,9 @@ int b200sm_set_initial_pose(b200sm_t s, const double* position3, const double* q
 
 int b200sm_set_scan(b200sm_t s, b200reg_t reg, const float* points, size_t n, size_t stride_bytes, long intensity_offset_bytes,
                     size_t* n_filtered) {
-  if (!s || !reg || !points || n == 0 || stride_bytes < 12) return B200REG_ERR_ARG;
+  if (!s || !reg || !points || n == 0 || stride_bytes < 12 || (stride_bytes % 4) != 0 ||
+      (intensity_offset_bytes >= 0 && (intensity_offset_bytes % 4) != 0))
+    return B200REG_ERR_ARG;
   return sm_guarded(s, [&]() {
     upload_frame(s, points, n, stride_bytes, intensity_offset_bytes);
     const int rc = set_source_from_scan(s, reg);
@@ -428,7 +430,9 @@ int b200sm_update_map(b200sm_t s, b200reg_t reg, const float* final_T_colmajor16
 
 int b200sm_receive_cloud(b200sm_t s, b200reg_t reg, const float* points, size_t n, size_t stride_bytes, long intensity_offset_bytes,
                          double* pose7_out, float* final_T_colmajor16_out, int* map_updated) {
-  if (!s || !reg || !points || n == 0 || stride_bytes < 12) return B200REG_ERR_ARG;
+  if (!s || !reg || !points || n == 0 || stride_bytes < 12 || (stride_bytes % 4) != 0 ||
+      (intensity_offset_bytes >= 0 && (intensity_offset_bytes % 4) != 0))
+    return B200REG_ERR_ARG;
   return sm_guarded(s, [&]() {
     if (map_updated) *map_updated = 0;
     int kind = B200REG_NDT;
@@ -697,6 +701,32 @@ int b200sm_search_loop_all(b200sm_t s, b200reg_t reg, float voxel_leaf_size, dou
       if (rc != B200REG_OK) return rc;
       *n_out += 1;
     }
+    return (int)B200REG_OK;
+  });
+}
+
+// A backend that runs in its own process receives the frontend's submaps as lidarslam_msgs/SubMap messages (already
+// voxel-filtered cloud in the sensor frame + pose + travelled distance, graph_based_slam_component.cpp:91-101): this entry
+// point appends one to the session so that b200sm_search_loop / _all work on device-resident copies there too.
+int b200sm_import_submap(b200sm_t s, const float* points, size_t n, size_t stride_bytes, long intensity_offset_bytes,
+                         const double* pose_colmajor16, double distance) {
+  if (!s || (!points && n) || !pose_colmajor16 || stride_bytes < 12 || (stride_bytes % 4) != 0 ||
+      (intensity_offset_bytes >= 0 && intensity_offset_bytes % 4 != 0))
+    return B200REG_ERR_ARG;
+  return sm_guarded(s, [&]() {
+    std::unique_ptr<Submap> sub(new Submap());
+    sub->cloud = s->arena.alloc(std::max<size_t>(n, 1));
+    sub->n = n;
+    if (n) {
+      s->uploader.upload(points, n, stride_bytes, intensity_offset_bytes, 0.0f, sub->cloud, s->stream);
+      B200_CUDA(cudaStreamSynchronize(s->stream));  // the caller may reuse its buffer
+      s->launches += 1;
+    }
+    for (int r = 0; r < 4; r++)
+      for (int c = 0; c < 4; c++) sub->pose[r * 4 + c] = pose_colmajor16[c * 4 + r];
+    sub->distance = distance;
+    s->latest_distance = distance;
+    s->submaps.push_back(std::move(sub));
     return (int)B200REG_OK;
   });
 }

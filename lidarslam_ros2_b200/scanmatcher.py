@@ -106,6 +106,13 @@ class ScanMatcher:
                 out["relative_pose"] = np.array(r.relative_pose, dtype=np.float64).reshape(4, 4).T.copy()
         return out
 
+    def importSubmap(self, cloud, pose_matrix, distance: float):
+        """Append a submap received as a message (filtered cloud, 4x4 pose, travelled distance): b200sm_import_submap."""
+        p = _as_cloud(cloud)
+        n, w = p.shape
+        M = np.ascontiguousarray(np.asarray(pose_matrix, dtype=np.float64).T).reshape(16)
+        self._check(self._lib.b200sm_import_submap(self._h, _ptr(p), n, 4 * w, 12 if w >= 4 else -1, _ptr(M), float(distance)))
+
     def searchLoopAll(self, registration, voxel_leaf_size: float = 0.2, threshold_loop_closure_score: float = 1.0,
                       distance_loop_closure: float = 20.0, range_of_searching_loop_closure: float = 20.0,
                       search_submap_num: int = 3, shard_rank: int = 0, shard_world: int = 1) -> list:

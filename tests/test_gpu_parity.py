@@ -217,6 +217,54 @@ def test_edge_cases(b200, oracle_mod, pair_tiny):
     _check_pose(g2.align(), o2.align())
 
 
+def test_kdtree_mode_dense_target(b200, oracle_mod):
+    """KDTREE mode (radiusSearch over voxel centroids, voxel_grid_covariance_omp.h:470-499) on a dense target: the voxel
+    centroid is the f32 cast of an order-independent f64 sum here and a float running sum in the reference
+    (voxel_grid_covariance_omp_impl.hpp:262, 287) — a documented deviation of a few float ulp that could flip a voxel sitting
+    exactly on the search radius. Poses must still agree within the north_star tolerance, the hit counts within 1e-4."""
+    from lidarslam_ros2_b200 import synth
+
+    src, tgt, _ = synth.registration_pair("c2", 2.0)
+    g, o = _mk(b200, oracle_mod, src, tgt, 2.0, method=0)
+    vg, vo = g.voxels(), o.voxels()
+    np.testing.assert_array_equal(vg["idx"], vo["idx"])
+    assert np.abs(vg["centroid"] - vo["centroid"]).max() < 5e-4  # well-populated voxels: float-sum rounding of the reference
+    _check_pose(g.align(), o.align())
+    assert g.getFinalNumIteration() == o.iterations
+    p = np.array([0.2, -0.1, 0.03, 0.004, -0.003, 0.015])
+    T = oracle_mod.pose_to_matrix(p)
+    sg, gg, Hg = g.derivatives(T, p, True)
+    so, go, Ho = o.derivatives(T, p, True)
+    assert abs(sg - so) <= 1e-4 * abs(so)
+
+
+def test_invalid_strides_are_rejected(b200):
+    """Records hold float fields: a stride or an intensity offset that is not a multiple of 4 would fault inside the unpack
+    kernel (misaligned address poisons the CUDA context) — it must be refused at the boundary instead."""
+    import ctypes as C
+
+    from lidarslam_ros2_b200 import _capi
+
+    L = _capi.lib()
+    g = b200.NormalDistributionsTransform()
+    buf = np.zeros(4000, dtype=np.uint8)
+    assert L.b200reg_set_input_target(g._h, buf.ctypes.data, 100, 14) == _capi.ERR_ARG
+    assert L.b200reg_set_input_source(g._h, buf.ctypes.data, 100, 18) == _capi.ERR_ARG
+    m = C.c_size_t(0)
+    out = np.zeros(4000, dtype=np.uint8)
+    assert L.b200reg_voxelgrid(0, buf.ctypes.data, 100, 16, 13, 0.5, out.ctypes.data, 100, C.byref(m)) == _capi.ERR_ARG
+    # and the context is still healthy
+    src, tgt, _ = b200.synth.registration_pair("tiny", 2.0) if hasattr(b200, "synth") else (None, None, None)
+    if src is None:
+        from lidarslam_ros2_b200 import synth
+        src, tgt, _ = synth.registration_pair("tiny", 2.0)
+    g.setResolution(2.0)
+    g.setInputTarget(tgt)
+    g.setInputSource(src)
+    g.align()
+    assert g.hasConverged()
+
+
 def test_cpp_adapter_end_to_end(b200):
     """The C++ adapter (include/b200reg_pcl.hpp) driven like apps/align.cpp: recovers a known shift on the GPU."""
     import os

@@ -212,3 +212,27 @@ def test_search_loop_all_candidates():
     assert [c["id_min"] for c in shards] == ids
     for a, b in zip(shards, allc):
         assert np.array_equal(a["final"], b["final"]) and a["fitness"] == b["fitness"]
+
+
+@pytest.mark.gpu
+def test_imported_submaps_give_the_same_loop_search():
+    """A backend in its own process: submaps read back from the frontend session (the SubMap messages) and imported into a
+    fresh session must give the identical loop search."""
+    from lidarslam_ros2_b200.scanmatcher import ScanMatcher, backend_registration
+
+    kw = dict(ndt_resolution=2.0, vg_size_for_input=0.4, vg_size_for_map=0.3, num_targeted_cloud=3)
+    g = ScanMatcher(**kw)
+    for scan, T in _out_and_back():
+        g.setScan(scan)
+        g.updateMap(T.astype(np.float32), T[:3, 3], osm.quat_from_matrix(T[:3, :3]), adopt_now=False)
+    b = ScanMatcher(**kw)
+    for i in range(g.numSubmaps()):
+        cloud, M, dist = g.submap(i)
+        b.importSubmap(cloud, M, dist)
+    assert b.numSubmaps() == g.numSubmaps()
+    reg = backend_registration("NDT", ndt_resolution=2.0)
+    args = dict(voxel_leaf_size=0.3, distance_loop_closure=5.0, range_of_searching_loop_closure=1.0, search_submap_num=1)
+    ra, rb = g.searchLoop(reg, **args), b.searchLoop(reg, **args)
+    assert ra["id_min"] == rb["id_min"] and ra["accepted"] == rb["accepted"]
+    assert np.array_equal(ra["final"], rb["final"]) and ra["fitness"] == rb["fitness"]
+    assert np.array_equal(ra["relative_pose"], rb["relative_pose"])
