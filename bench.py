@@ -599,7 +599,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--no-c4", action="store_true", help="skip the loop-closure sweep object of the headline line")
-    ap.add_argument("--slots", type=int, default=2, help="registrations in flight per batched launch (1 or 2)")
+    ap.add_argument("--slots", type=int, default=3, help="registrations in flight per batched launch (1..3)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -768,7 +768,7 @@ def main():
             "details": {"n_voxels": int(st["n_voxels"]), "grid_ctas": st["grid_ctas"], "block_threads": st["block_threads"],
                         "index_in_smem": st["index_in_smem"], "slots_in_flight": args.slots,
                         "step": "the K steps are K independent registrations (own scan buffer each) issued as ONE "
-                                "b200reg_ndt_align_batch_device call = one persistent launch, 2 registrations in flight",
+                                f"b200reg_ndt_align_batch_device call = one persistent launch, {args.slots} registrations in flight",
                         "parallelism": f"replicas x{world} + 1 NCCL all-gather of the poses inside the timed region" if world > 1 else "1 GPU",
                         "batch_bitwise_equals_single_align": bool(bitwise),
                         "mean_iterations": float(rb["iterations"].mean()), "converged": int(rb["converged"].sum())},

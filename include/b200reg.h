@@ -111,9 +111,9 @@ int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, flo
 
 /* K independent NDT registrations against the handle's CURRENT target in ONE persistent launch — repeated
  * align() calls of apps/align.cpp:32-36 ("10times"), multi-hypothesis initial guesses, or the candidate scans of a
- * loop-closure sweep sharing one map. Two registrations are in flight inside the kernel: while one registration's
+ * loop-closure sweep sharing one map. Up to three registrations are in flight inside the kernel: while one registration's
  * Newton step (fixed-order reduction, 6x6 solve, next pose) runs on its controller SM, the evaluator SMs compute the
- * other registration's derivatives, so the sequential part of ndt_omp_impl.hpp:121-166 no longer idles the GPU.
+ * other registrations' derivatives, so the sequential part of ndt_omp_impl.hpp:121-166 no longer idles the GPU.
  * Every result is BITWISE the result b200reg_align gives for the same (source, guess).
  * guesses: 16*count floats column-major, or NULL (identity). results[k].status is B200REG_OK or an error code.
  * After the call the handle's getters (final transformation, converged, ...) describe the LAST registration;
@@ -148,7 +148,7 @@ typedef struct b200reg_sweep_result {
 int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sources, const size_t* n_src,
                       const float* const* targets, const size_t* n_tgt, size_t stride_bytes, const float* guesses,
                       double fitness_max_range, b200reg_sweep_result* results);
-/* registrations in flight per batch launch (1 or 2; default 2). Developer / measurement switch. */
+/* registrations in flight per batch launch (1..3; default 3). Developer / measurement switch. */
 int b200reg_ndt_set_batch_slots(b200reg_t h, int slots);
 
 /* ---- pcl::VoxelGrid<PointXYZI>::filter (sm.cpp:266-269,311-314,325-328,444-447; gbs.cpp:225-226) ------ */

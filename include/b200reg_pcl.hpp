@@ -166,8 +166,12 @@ class RegistrationBase : public pcl::Registration<PointSource, PointTarget> {
       PCL_ERROR_B200("[b200reg::setInputTarget] invalid or empty point cloud given, ignored");
       return;
     }
-    if (keep_host_tree_) Base::setInputTarget(cloud);
-    else this->target_ = cloud;
+    if (keep_host_tree_) {
+      Base::setInputTarget(cloud);
+    } else {
+      this->target_ = cloud;
+      this->target_cloud_updated_ = false;  // (PCL constructs it `true`: even the first align() would build the tree)
+    }
     target_ok_ = report(b200reg_set_input_target(h_.get(), &cloud->points[0].x, cloud->size(), sizeof(PointTarget)), "setInputTarget");
   }
   void setInputSource(const PointCloudSourceConstPtr& cloud) override {

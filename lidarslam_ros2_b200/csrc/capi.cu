@@ -17,7 +17,7 @@
 using namespace b200;
 
 static size_t g_vg_dense_budget = (size_t)4 << 20;  // b200reg_voxelgrid: dense-bitmap budget in words (debug hook below)
-static constexpr int NDT_BATCH_SLOTS_DEFAULT = 2;  // registrations in flight per batch launch (engine.hpp / ndt_solver.cuh)
+static constexpr int NDT_BATCH_SLOTS_DEFAULT = 3;  // registrations in flight per batch launch (engine.hpp / ndt_solver.cuh)
 
 struct b200reg_engine {
   int kind = B200REG_NDT;

@@ -242,7 +242,7 @@ class NdtSolver {
   NdtJob* h_jobs_ = nullptr;       // ... and its pinned host image
   NdtResult* h_batch_results_ = nullptr;  // pinned + device-visible: the controllers write the results there
   size_t jobs_cap_ = 0;
-  void fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& cfg, int mode, size_t& dyn_smem);
+  void fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& cfg, int mode, int n_slots, size_t& dyn_smem);
   int eval_ctas_for(size_t n_src) const;
 };
 

@@ -46,7 +46,9 @@ constexpr int ACC_SLOTS = 27;      // 6 gradient + 21 upper-triangular Hessian s
 constexpr int ACC_STRIDE = SOLVER_THREADS + 1;
 constexpr int ACC_BYTES = ACC_SLOTS * ACC_STRIDE * 4;
 constexpr int SOLVER_MAX_INDEX_SMEM = 64 * 1024;  // the rank index is staged in shared memory up to this size
-constexpr int SOLVER_MAX_DYN_SMEM = SOLVER_MAX_INDEX_SMEM + ACC_BYTES;  // the rest of the SM stays L1 for the voxel-record gathers (a 100 KB index in shared memory measured slower)  // padded row: slot-major reads by 32 lanes hit 32 different banks
+constexpr int PTS_BYTES = SMEM_POINTS * 16;  // per slot
+constexpr int ACC_BYTES_PAD = (ACC_BYTES + 127) & ~127;
+constexpr int SOLVER_MAX_DYN_SMEM = SOLVER_MAX_INDEX_SMEM + ACC_BYTES_PAD + NDT_MAX_SLOTS * PTS_BYTES;  // the rest of the SM stays L1 for the voxel-record gathers (a 100 KB index in shared memory measured slower)  // padded row: slot-major reads by 32 lanes hit 32 different banks
 constexpr long long SPIN_TIMEOUT_CYCLES = 4000000000LL;  // ~2 s device-side watchdog, never reached in normal runs
 
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
@@ -1064,11 +1066,11 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
   __shared__ __align__(16) NdtControl ctl_s[NDT_MAX_SLOTS];
   __shared__ int abort_flag;
   __shared__ __align__(8) unsigned long long tma_bar;
-  __shared__ float4 pts_s[NDT_MAX_SLOTS][SMEM_POINTS];
   __shared__ const float4* slot_src[NDT_MAX_SLOTS];
   __shared__ int slot_nsrc[NDT_MAX_SLOTS], slot_job[NDT_MAX_SLOTS];
-  // dynamic shared memory: [rank index, L.acc_offset bytes][per-thread f32 accumulators]
+  // dynamic shared memory: [rank index, L.acc_offset bytes][per-thread f32 accumulators][staged points, one block per slot]
   float (*acc_s)[ACC_STRIDE] = reinterpret_cast<float (*)[ACC_STRIDE]>(dyn_smem + L.acc_offset);
+  float4 (*pts_s)[SMEM_POINTS] = reinterpret_cast<float4 (*)[SMEM_POINTS]>(dyn_smem + L.pts_offset);
   const RankWord* idx = L.index_in_smem ? reinterpret_cast<const RankWord*>(dyn_smem) : L.index;
 
   // stage the voxel rank index into shared memory with TMA bulk copies (once per launch)
@@ -1395,7 +1397,7 @@ void initial_pose(const float* T, const double* p6, double* p0, float* init_fina
 }
 }  // namespace
 
-void NdtSolver::fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& cfg, int mode, size_t& dyn_smem) {
+void NdtSolver::fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& cfg, int mode, int n_slots, size_t& dyn_smem) {
   L.index = map.index.ptr;
   L.records = map.records.ptr;
   L.icov_d = map.icov_d.ptr;
@@ -1422,7 +1424,10 @@ void NdtSolver::fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& 
   const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 127) & ~(size_t)127;
   L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= (size_t)SOLVER_MAX_INDEX_SMEM) ? 1 : 0;
   L.acc_offset = L.index_in_smem ? (int)index_bytes : 0;
-  dyn_smem = std::max((size_t)L.acc_offset + ACC_BYTES, sizeof(CtlShared));
+  L.pts_offset = L.acc_offset + ACC_BYTES_PAD;
+  // (a single registration stages one block of points: the shared-memory carve-out, and with it the L1 left for the
+  // voxel-record gathers, stays what it was before batching existed)
+  dyn_smem = std::max((size_t)L.pts_offset + (size_t)n_slots * PTS_BYTES, sizeof(CtlShared));
   dyn_smem = (dyn_smem + 127) & ~(size_t)127;
   index_in_smem_ = L.index_in_smem;
   if (!fits_checked_) {  // the largest configuration (64 KB index + accumulators) fits or nothing does
@@ -1445,7 +1450,7 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
                        const float* T_rowmajor16, const double* p6, int compute_hessian, int resume) {
   NdtLaunch L{};
   size_t dyn_smem = 0;
-  fill_common(L, map, cfg, mode, dyn_smem);
+  fill_common(L, map, cfg, mode, 1, dyn_smem);
   L.src = src;
   L.result_host = h_result_;
   h_result_->error = 3;  // "the kernel never wrote a result"
@@ -1502,12 +1507,13 @@ void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n,
   B200_CUDA(cudaMemsetAsync(&d_work_->next_job, 0, sizeof(unsigned), stream_));
   NdtLaunch L{};
   size_t dyn_smem = 0;
-  fill_common(L, map, cfg, NDT_MODE_ALIGN, dyn_smem);
+  const int n_slots = std::max(1, std::min(std::min(slots, NDT_MAX_SLOTS), n));
+  fill_common(L, map, cfg, NDT_MODE_ALIGN, n_slots, dyn_smem);
   L.timing = 0;
   L.result_host = h_batch_results_;
   L.jobs = d_jobs_;
   L.n_jobs = n;
-  L.n_slots = std::max(1, std::min(std::min(slots, NDT_MAX_SLOTS), n));
+  L.n_slots = n_slots;
   L.n_src = (int)n_max;
   grid_ = eval_ctas_for(n_max) + L.n_slots;
   block_ = SOLVER_THREADS;

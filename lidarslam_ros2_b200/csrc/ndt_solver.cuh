@@ -9,7 +9,7 @@ constexpr int NDT_MAX_CTAS = 256;  // one CTA per SM
 // Registrations in flight inside one batch launch = controller CTAs. Every launch (single or batched) leaves this many
 // SMs to controllers, so that the evaluator count — and with it the point partition and the fixed summation order —
 // is the same for b200reg_align and for b200reg_ndt_align_batch: a batched result is bitwise the single-align result.
-constexpr int NDT_MAX_SLOTS = 2;
+constexpr int NDT_MAX_SLOTS = 3;
 
 enum EvalMode : int {
   EVAL_DERIV = 0,        // fused derivative pass (K1)
@@ -104,6 +104,7 @@ struct NdtLaunch {
   int mode;    // NdtMode
   unsigned epoch;         // launch counter of this handle (high half of the control block's sequence numbers)
   int acc_offset;         // byte offset of the per-thread accumulators in dynamic shared memory (after the rank index)
+  int pts_offset;         // byte offset of the staged source points (n_slots x SMEM_POINTS float4) after the accumulators
   int scalar_controller;  // 1: disable the warp-parallel controller fast path (developer switch)
   int timing;  // 1: record per-phase globaltimer stamps into work->timing (developer instrumentation)
   int resume;  // 1: state/control already in work (after a K2 pass); first round skips the evaluation

@@ -80,7 +80,7 @@ class ScanMatcher:
 
     def deskewNextScan(self, scan_time: float):
         """use_imu: de-skew the next frame on the device before the range filter (b200sm_deskew_next_scan)."""
-        self._check(self._lib.b200sm_deskew_next_scan(self._s, float(scan_time)))
+        self._check(self._lib.b200sm_deskew_next_scan(self._h, float(scan_time)))
 
     def updateMap(self, final_transformation, position, quat_xyzw, adopt_now: bool = True):
         T = np.ascontiguousarray(np.asarray(final_transformation, dtype=np.float32).T).reshape(16)

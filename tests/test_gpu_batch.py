@@ -61,7 +61,7 @@ def test_batch_equals_single_bitwise(b200, config, res):
     g = _engine(b200, tgt, res)
     scans, guesses = _scans_and_guesses(src, 9)
     ref = _single(g, scans, guesses)
-    for slots in (2, 1):
+    for slots in (3, 2, 1):
         g.setBatchSlots(slots)
         r = g.alignBatch(scans, guesses)
         assert np.all(r["status"] == 0)

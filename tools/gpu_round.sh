@@ -5,11 +5,26 @@
 tag=${1:-rX}
 out=gpurun_out
 mkdir -p $out
-timeout 1200 python -m pytest tests -m gpu -q > $out/pytest_gpu_$tag.log 2>&1; tail -3 $out/pytest_gpu_$tag.log
+timeout 1500 python -m pytest tests -m gpu -q --durations=8 > $out/pytest_gpu_$tag.log 2>&1; tail -14 $out/pytest_gpu_$tag.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > $out/smoke_$tag.log 2>&1; tail -2 $out/smoke_$tag.log
 timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_$tag.json 2> $out/bench_$tag.err; tail -c 1500 $out/bench_$tag.json; tail -5 $out/bench_$tag.err
-timeout 300 python bench.py --steps 20 --warmup 5 --slots 1 --no-c4 --no-cpu-baseline > $out/bench_slots1_$tag.json 2> $out/bench_slots1_$tag.err; tail -c 600 $out/bench_slots1_$tag.json
-timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; tail -c 400 $out/bench_ref_$tag.json
+for s in 2 1; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --slots $s --no-c4 --no-cpu-baseline > $out/bench_slots${s}_$tag.json 2> $out/bench_slots${s}_$tag.err
+done
+B200REG_LIB_VARIANT=libb200reg_noskip.so timeout 300 python bench.py --steps 20 --warmup 5 --no-c4 --no-cpu-baseline > $out/bench_noskip_$tag.json 2> $out/bench_noskip_$tag.err
+python - <<PY
+import json
+for f in ["bench_$tag", "bench_slots2_$tag", "bench_slots1_$tag", "bench_noskip_$tag"]:
+    try:
+        l = json.loads(open("$out/" + f + ".json").read().strip().splitlines()[-1])
+        print(f, "value %.0f  e2e %.0f  pageable %.0f  single %.0f  frac %.3f  us/eval %.2f" % (l["value"], l["e2e"]["value"], l["e2e"]["pageable"]["value"], l["single_align"]["value"], l["roofline"]["frac"], l["roofline"]["us_per_evaluation"]))
+    except Exception as e:
+        print(f, "ERR", e)
+PY
+timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; tail -c 300 $out/bench_ref_$tag.json
+timeout 300 python tools/diag_c4.py 8 > $out/diag_c4_$tag.log 2>&1; tail -6 $out/diag_c4_$tag.log
+timeout 600 python bench.py --workload c3 > $out/bench_c3_$tag.json 2> $out/bench_c3_$tag.err; tail -c 1200 $out/bench_c3_$tag.json; tail -3 $out/bench_c3_$tag.err
+timeout 600 python bench.py --workload c5 --frames 120 > $out/bench_c5_$tag.json 2> $out/bench_c5_$tag.err; tail -c 700 $out/bench_c5_$tag.json; tail -3 $out/bench_c5_$tag.err
 # launch list of the profile command (cold-cache, serialised: compare shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
   python tools/profile_step.py headline 3 8 > $out/prof_step_$tag.log 2>&1
@@ -18,5 +33,4 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_
   -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 8 > $out/prof_full_$tag.log 2>&1
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page raw --csv > $out/ndt_solver_raw_$tag.csv 2>/dev/null
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page details --csv > $out/ndt_solver_details_$tag.csv 2>/dev/null
-timeout 600 python tools/diag_gicp.py tiny small c1 > $out/diag_gicp_$tag.log 2>&1; tail -40 $out/diag_gicp_$tag.log
-ls -la $out | tail -12
+ls -la $out | tail -8
