@@ -138,7 +138,8 @@ class ClockSampler:
                 mask |= int(rs[i])
             return {"sm_mhz": float(np.median(vals)) if vals else None, "sm_max_mhz": float(mx.value) or None, "samples": n,
                     "reasons": sorted(name for bit, name in self.REASONS if mask & bit),
-                    "source": f"nvml from a native thread, every {self.period_us} us inside the timed region (+1 before, +1 after)"}
+                    "source": f"nvml from a native thread inside the timed region: every {self.period_us} us for the first 16 samples, "
+                              "then 2 ms, then 20 ms (+1 sample before, +1 after)"}
         self._one_shot()
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
                 "reasons": sorted(name for bit, name in self.REASONS if self.mask & bit),
@@ -218,6 +219,11 @@ def host_threads() -> int:
         return os.cpu_count() or 1
 
 
+def cpu_thread_candidates():
+    hw = host_threads()
+    return sorted({c for c in (hw, max(1, hw // 2), 32, 16, 8) if c <= hw}, reverse=True)
+
+
 def workload_config(name: str, scans, tgt) -> dict:
     """The `config` object — identical in the GPU arm and in the reference arm (same workload, same inputs)."""
     desc = WORKLOADS[name][2]
@@ -235,10 +241,9 @@ def make_cpu_ndt(res, threads):
 
 
 def best_cpu_threads(scans, tgt, res):
-    """Thread count the CPU path runs fastest with on this box: all hardware threads, or one per physical core (SMT
-    siblings often hurt this cache-bound loop). One probe align each after a common warm-up."""
-    hw = host_threads()
-    cand = sorted({hw, max(1, hw // 2)}, reverse=True)
+    """Thread count the CPU path runs fastest with on this box: all hardware threads, one per physical core (SMT siblings
+    often hurt this cache-bound loop), or fewer (the std::map walks stop scaling early). One probe align each."""
+    cand = cpu_thread_candidates()
     best = None
     for c in cand:
         n = make_cpu_ndt(res, c)
@@ -374,7 +379,17 @@ def run_c5(args, rank, local_rank, world, m):
     import oracle.scanmatcher as osm
 
     oracle.build()
-    o = osm.ScanMatcher(num_threads=host_threads(), **kw)
+    best = None
+    for c in cpu_thread_candidates():  # fastest thread count for this callback on this box (three probe frames each)
+        op = osm.ScanMatcher(num_threads=c, **kw)
+        c0 = time.perf_counter()
+        for scan, _ in frames[:3]:
+            op.receive_cloud(scan)
+        dtc = time.perf_counter() - c0
+        if best is None or dtc < best[0]:
+            best = (dtc, c)
+    cpu_threads = best[1]
+    o = osm.ScanMatcher(num_threads=cpu_threads, **kw)
     n_cpu, t_cpu, dpose = 0, 0.0, 0.0
     g2 = ScanMatcher(device=local_rank, **kw)
     for scan, _ in frames[:min(len(frames), args.cpu_frames)]:
@@ -400,7 +415,7 @@ def run_c5(args, rank, local_rank, world, m):
         "gpu_launches": mid["launches"],
         "clocks": clocks,
         "roofline": None,
-        "cpu_baseline": {"value": n_cpu / t_cpu if t_cpu > 0 else None, "unit": "frames/s", "cores": host_threads(), "kind": "port",
+        "cpu_baseline": {"value": n_cpu / t_cpu if t_cpu > 0 else None, "unit": "frames/s", "cores": cpu_threads, "kind": "port",
                          "sample": f"first {n_cpu} frames of the same stream through oracle/scanmatcher.py", "pose_parity_max_m": dpose},
     }
     print(json.dumps(line), flush=True)
@@ -564,7 +579,18 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
         try:  # the reference's CPU path on a bounded sample of the same pairs (rank 0's first two)
             import oracle
 
-            nt = host_threads()
+            best = None
+            for c in cpu_thread_candidates():  # the thread count this path runs fastest with on this box (one probe pair each)
+                o = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7, num_threads=c)
+                c0 = time.perf_counter()
+                o.set_target(data[mine[0]][1])
+                o.set_source(data[mine[0]][0])
+                o.align()
+                o.fitness()
+                dtc = time.perf_counter() - c0
+                if best is None or dtc < best[0]:
+                    best = (dtc, c)
+            nt = best[1]
             o = oracle.NDT(resolution=2.0, transformation_epsilon=0.01, max_iterations=100, search_method=oracle.DIRECT7, num_threads=nt)
             t_cpu, n_cpu, dmax, rmax = 0.0, 0, 0.0, 0.0
             for i in mine[:2]:

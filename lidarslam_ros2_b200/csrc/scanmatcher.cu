@@ -131,6 +131,7 @@ struct b200sm_session {
   DeviceBuffer<unsigned> counter;
   VoxelGridFilter vg_input, vg_map, vg_target;
   size_t n_filtered = 0;
+  const float4* d_filtered = nullptr;  // VoxelGrid(vg_size_for_input) of the scan — the scan itself when the grid would overflow
   SubmapArena arena;
   std::vector<std::unique_ptr<Submap>> submaps;
   DeviceBuffer<float4> targeted;
@@ -261,6 +262,7 @@ int set_source_from_scan(b200sm_t s, b200reg_t reg) {
   size_t m = 0;
   const float4* f = filter_on_device(s, s->vg_input, s->d_scan, s->n_scan, s->vg_size_for_input, &m);
   s->n_filtered = m;
+  s->d_filtered = f;
   if (m == 0) return sm_fail(s, B200REG_ERR_ARG, "scan is empty after filtering");
   B200_CUDA(cudaStreamSynchronize(s->stream));  // the engine copies on its own stream
   const int rc = b200reg_set_input_source_device(reg, f, m);
@@ -523,7 +525,7 @@ int b200sm_get_submap(b200sm_t s, size_t index, float* out_xyzi, size_t capacity
 
 int b200sm_get_filtered_scan(b200sm_t s, float* out_xyzi, size_t capacity, size_t* n) {
   if (!s) return B200REG_ERR_ARG;
-  return sm_guarded(s, [&]() { return read_back(s, s->vg_input.out.ptr, s->n_filtered, out_xyzi, capacity, n); });
+  return sm_guarded(s, [&]() { return read_back(s, s->d_filtered, s->d_filtered ? s->n_filtered : 0, out_xyzi, capacity, n); });
 }
 
 // GraphBasedSlamComponent::searchLoop (graph_based_slam_component.cpp:144-258) over the session's own submaps — the map
