@@ -142,6 +142,9 @@ struct NnGrid {
   int n_words = 0;
   size_t n_points = 0, n_cells_occupied = 0;
   DeviceBuffer<RankWord> index;
+  DeviceBuffer<unsigned> coarse;      // 6 ordered uints per 8x8x8 block of cells: bounding box of its points (far queries)
+  int cdims[3] = {0, 0, 0};
+  int n_coarse = 0;
   DeviceBuffer<unsigned> cell_start;  // n_cells_occupied + 1
   DeviceBuffer<float4> sorted;        // xyz + original index (int bits) in w
   DeviceBuffer<int> cell_of_point;

@@ -23,7 +23,7 @@ __device__ __forceinline__ unsigned rank_of(const RankWord* __restrict__ table, 
 }
 
 __global__ void __launch_bounds__(256) nn_mark_kernel(const float4* __restrict__ pts, size_t n, NnGeom g, RankWord* table,
-                                                      int* cell_of_point) {
+                                                      int* cell_of_point, unsigned* coarse, int cd0, int cd1) {
   size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   if (i >= n) return;
   float4 p = pts[i];
@@ -34,8 +34,22 @@ __global__ void __launch_bounds__(256) nn_mark_kernel(const float4* __restrict__
     int iz = nn_cell_coord(p.z, g.origin[2], g.inv_h, g.dims[2]);
     cell = ix + g.dims[0] * (iy + g.dims[1] * iz);
     atomicOr(&table[cell >> 5].bits, 1u << (cell & 31));
+    // tight bounding box of the 8x8x8 block of cells this point falls into (far-query pruning)
+    unsigned* a = coarse + 6 * (size_t)((ix >> NN_COARSE_SHIFT) + cd0 * ((iy >> NN_COARSE_SHIFT) + cd1 * (iz >> NN_COARSE_SHIFT)));
+    atomicMin(a + 0, float_to_ordered(p.x));
+    atomicMin(a + 1, float_to_ordered(p.y));
+    atomicMin(a + 2, float_to_ordered(p.z));
+    atomicMax(a + 3, float_to_ordered(p.x));
+    atomicMax(a + 4, float_to_ordered(p.y));
+    atomicMax(a + 5, float_to_ordered(p.z));
   }
   cell_of_point[i] = cell;
+}
+
+__global__ void nn_coarse_init_kernel(unsigned* coarse, int n_coarse) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_coarse * 6) return;
+  coarse[i] = (i % 6 < 3) ? 0xffffffffu : 0u;  // min = +inf, max = -inf in the ordered encoding: empty
 }
 
 __global__ void __launch_bounds__(256) nn_count_kernel(size_t n, const int* __restrict__ cell_of_point,
@@ -166,80 +180,99 @@ __global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4*
   if (!resolved) unresolved_list[atomicAdd(unresolved_count, 1u)] = (int)i;
 }
 
-// Phase 2: one CTA per unresolved query. With a finite search radius the CTA shares the cells of the cube of that
-// radius; without one it scans the whole (cell-sorted) cloud. Lexicographic (d2, index) minimum, so the result does
-// not depend on the visiting order.
-__global__ void __launch_bounds__(256) nn1_bruteforce_kernel(NnQueryParams P, const float4* __restrict__ queries,
-                                                             const unsigned* __restrict__ unresolved_count,
-                                                             const int* __restrict__ unresolved_list, int* out_idx,
-                                                             float* out_d2) {
-  __shared__ float sd[8];
-  __shared__ int si[8];
+// Phase 2: one WARP per unresolved query (an outlier: nothing within NN_MAX_RINGS rings of its cell — a scan point beyond the
+// end of a local map, a query far outside the target's bounding box). A kd-tree answers those in O(log n); ring volumes grow
+// with r^3 and a linear scan of the cloud costs n per query (round 1: 0.5 ms of a 1.4 ms loop-closure pair). Here the
+// coarse level prunes: pass A takes the smallest "farthest corner" distance over the occupied 8x8x8 blocks — an upper
+// bound on the NN distance, every occupied block holds a point inside its box; pass B visits, warp-cooperatively, only the
+// blocks whose box is not farther than the current bound, tightening it as it goes. Lexicographic (d2, index) minimum,
+// blocks at EQUAL distance are visited too, so the result is the exact NN with the lower-index tie-break of the ring search.
+__global__ void __launch_bounds__(256) nn1_far_kernel(NnQueryParams P, const float4* __restrict__ queries,
+                                                      const unsigned* __restrict__ unresolved_count,
+                                                      const int* __restrict__ unresolved_list, int* out_idx, float* out_d2) {
   const unsigned total = *unresolved_count;
-  for (unsigned u = blockIdx.x; u < total; u += gridDim.x) {
+  const int lane = threadIdx.x & 31;
+  const unsigned warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = gridDim.x * (blockDim.x >> 5);
+  const NnView& V = P.V;
+  const NnGeom& g = V.g;
+  for (unsigned u = warp_global; u < total; u += n_warps) {
     const int qi = unresolved_list[u];
     float qx, qy, qz;
     nn_query_point(P, queries[qi], qx, qy, qz);
-    float best = FLT_MAX;
-    int best_i = -1;
-    auto consider = [&](float4 t) {
-      const float d2 = nn_dist2(qx, qy, qz, t);
-      const int ti = __float_as_int(t.w);
-      if (d2 < best || (d2 == best && ti < best_i)) {
-        best = d2;
-        best_i = ti;
-      }
-    };
-    if (P.max_d2 < 3.0e38f) {
-      // the caller only wants neighbours within sqrt(max_d2): the CTA shares the cells of the cube of that radius
-      // around the query's cell (every point within the radius lies in it, also for queries outside the grid)
-      const NnGeom& g = P.V.g;
-      const int R = (int)ceilf(sqrtf(P.max_d2) * g.inv_h) + 1;
-      const int cx = nn_cell_coord(qx, g.origin[0], g.inv_h, g.dims[0]);
-      const int cy = nn_cell_coord(qy, g.origin[1], g.inv_h, g.dims[1]);
-      const int cz = nn_cell_coord(qz, g.origin[2], g.inv_h, g.dims[2]);
-      const int x0 = max(cx - R, 0), x1 = min(cx + R, g.dims[0] - 1);
-      const int y0 = max(cy - R, 0), y1 = min(cy + R, g.dims[1] - 1);
-      const int z0 = max(cz - R, 0), z1 = min(cz + R, g.dims[2] - 1);
-      const int nx = x1 - x0 + 1, ny = y1 - y0 + 1, nz = z1 - z0 + 1;
-      const long long cells = (long long)nx * ny * nz;
-      for (long long c = threadIdx.x; c < cells; c += blockDim.x) {
-        const int x = x0 + (int)(c % nx), y = y0 + (int)((c / nx) % ny), z = z0 + (int)(c / ((long long)nx * ny));
-        const int cell = x + g.dims[0] * (y + g.dims[1] * z);
-        const uint2 w = __ldg(reinterpret_cast<const uint2*>(P.V.index + (cell >> 5)));
-        const unsigned bit = cell & 31;
-        if (!((w.x >> bit) & 1u)) continue;
-        const unsigned rk = w.y + __popc(w.x & ((1u << bit) - 1u));
-        const unsigned st = __ldg(P.V.cell_start + rk), en = __ldg(P.V.cell_start + rk + 1);
-        for (unsigned k = st; k < en; k++) consider(__ldg(P.V.sorted + k));
-      }
-    } else {
-      for (int k = threadIdx.x; k < P.n_points; k += blockDim.x) consider(__ldg(P.V.sorted + k));
+    float best = out_d2[qi];  // what the ring phase found (FLT_MAX / -1 when nothing)
+    int best_i = out_idx[qi];
+    // ---- pass A: an upper bound on the NN distance ----
+    float ub = best_i >= 0 ? best : FLT_MAX;
+    for (int c = lane; c < V.n_coarse; c += 32) {
+      const unsigned* a = V.coarse + 6 * (size_t)c;
+      const unsigned m0 = __ldg(a), M0 = __ldg(a + 3);
+      if (m0 > M0) continue;  // empty block
+      const float fx = fmaxf(fabsf(qx - ordered_to_float(m0)), fabsf(qx - ordered_to_float(M0)));
+      const float fy = fmaxf(fabsf(qy - ordered_to_float(__ldg(a + 1))), fabsf(qy - ordered_to_float(__ldg(a + 4))));
+      const float fz = fmaxf(fabsf(qz - ordered_to_float(__ldg(a + 2))), fabsf(qz - ordered_to_float(__ldg(a + 5))));
+      ub = fminf(ub, (fx * fx + fy * fy + fz * fz) * 1.0001f);
     }
 #pragma unroll
-    for (int d = 16; d > 0; d >>= 1) {
-      const float od = __shfl_xor_sync(0xffffffffu, best, d);
-      const int oi = __shfl_xor_sync(0xffffffffu, best_i, d);
-      if (oi >= 0 && (od < best || (od == best && (best_i < 0 || oi < best_i)))) {
-        best = od;
-        best_i = oi;
+    for (int d = 16; d > 0; d >>= 1) ub = fminf(ub, __shfl_xor_sync(0xffffffffu, ub, d));
+    float bound = fminf(ub, P.max_d2);  // nothing farther can be the answer (or matter to the caller)
+    // ---- pass B: the blocks that can hold it ----
+    for (int base = 0; base < V.n_coarse; base += 32) {
+      const int c = base + lane;
+      float lb = FLT_MAX;
+      if (c < V.n_coarse) {
+        const unsigned* a = V.coarse + 6 * (size_t)c;
+        const unsigned m0 = __ldg(a), M0 = __ldg(a + 3);
+        if (m0 <= M0) {
+          const float dx = fmaxf(fmaxf(ordered_to_float(m0) - qx, qx - ordered_to_float(M0)), 0.f);
+          const float dy = fmaxf(fmaxf(ordered_to_float(__ldg(a + 1)) - qy, qy - ordered_to_float(__ldg(a + 4))), 0.f);
+          const float dz = fmaxf(fmaxf(ordered_to_float(__ldg(a + 2)) - qz, qz - ordered_to_float(__ldg(a + 5))), 0.f);
+          lb = (dx * dx + dy * dy + dz * dz) * 0.9999f;  // never above the rounded distance of a point inside the box
+        }
+      }
+      unsigned mask = __ballot_sync(0xffffffffu, lb <= bound);
+      while (mask) {
+        const int src = __ffs(mask) - 1;
+        mask &= mask - 1;
+        const float lbc = __shfl_sync(0xffffffffu, lb, src);
+        if (lbc > bound) continue;  // the bound tightened meanwhile (warp-uniform)
+        const int cc = base + src;
+        const int bx = (cc % V.cdims[0]) << NN_COARSE_SHIFT, by = ((cc / V.cdims[0]) % V.cdims[1]) << NN_COARSE_SHIFT,
+                  bz = (cc / (V.cdims[0] * V.cdims[1])) << NN_COARSE_SHIFT;
+        for (int t = lane; t < 512; t += 32) {  // the block's 8x8x8 cells, 16 per lane
+          const int x = bx + (t & 7), y = by + ((t >> 3) & 7), z = bz + (t >> 6);
+          if (x >= g.dims[0] || y >= g.dims[1] || z >= g.dims[2]) continue;
+          const int cell = x + g.dims[0] * (y + g.dims[1] * z);
+          const uint2 w = __ldg(reinterpret_cast<const uint2*>(V.index + (cell >> 5)));
+          const unsigned bit = cell & 31;
+          if (!((w.x >> bit) & 1u)) continue;
+          const unsigned rk = w.y + __popc(w.x & ((1u << bit) - 1u));
+          const unsigned st = __ldg(V.cell_start + rk), en = __ldg(V.cell_start + rk + 1);
+          for (unsigned k = st; k < en; k++) {
+            const float4 tp = __ldg(V.sorted + k);
+            const float d2 = nn_dist2(qx, qy, qz, tp);
+            const int ti = __float_as_int(tp.w);
+            if (d2 < best || (d2 == best && (best_i < 0 || ti < best_i))) {
+              best = d2;
+              best_i = ti;
+            }
+          }
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {  // lexicographic (d2, index) minimum over the warp
+          const float od = __shfl_xor_sync(0xffffffffu, best, d);
+          const int oi = __shfl_xor_sync(0xffffffffu, best_i, d);
+          if (oi >= 0 && (od < best || (od == best && (best_i < 0 || oi < best_i)))) {
+            best = od;
+            best_i = oi;
+          }
+        }
+        if (best_i >= 0) bound = fminf(bound, best);
       }
     }
-    if ((threadIdx.x & 31) == 0) {
-      sd[threadIdx.x >> 5] = best;
-      si[threadIdx.x >> 5] = best_i;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      for (int w = 1; w < 8; w++)
-        if (si[w] >= 0 && (sd[w] < best || (sd[w] == best && (best_i < 0 || si[w] < best_i)))) {
-          best = sd[w];
-          best_i = si[w];
-        }
+    if (lane == 0) {
       out_idx[qi] = best_i;
       out_d2[qi] = best;
     }
-    __syncthreads();
   }
 }
 
@@ -278,6 +311,9 @@ NnView nn_view(const NnGrid& grid) {
   }
   V.g.h = grid.h;
   V.g.inv_h = grid.inv_h;
+  V.coarse = grid.coarse.ptr;
+  for (int a = 0; a < 3; a++) V.cdims[a] = grid.cdims[a];
+  V.n_coarse = grid.n_coarse;
   return V;
 }
 
@@ -317,6 +353,13 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s, const Bounds* kn
     n_cells *= dims[a];
   }
   n_words = (int)((n_cells + 31) / 32);
+  n_coarse = 1;
+  for (int a = 0; a < 3; a++) {
+    cdims[a] = (dims[a] + (1 << NN_COARSE_SHIFT) - 1) >> NN_COARSE_SHIFT;
+    n_coarse *= cdims[a];
+  }
+  coarse.ensure((size_t)n_coarse * 6);
+  nn_coarse_init_kernel<<<(n_coarse * 6 + 255) / 256, 256, 0, s>>>(coarse.ptr, n_coarse);
   // No host round trip below: the cell lists are sized by the upper bound min(points, cells) on the occupied cells; the
   // exclusive scan runs over that many counters (the tail past the occupied cells is zero, so cell_start[rank + 1] of
   // the last occupied cell is the total, as the queries expect).
@@ -338,7 +381,7 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s, const Bounds* kn
   g.h = h;
   g.inv_h = inv_h;
   const int blocks = (int)((n + 255) / 256);
-  nn_mark_kernel<<<blocks, 256, 0, s>>>(pts, n, g, index.ptr, cell_of_point.ptr);
+  nn_mark_kernel<<<blocks, 256, 0, s>>>(pts, n, g, index.ptr, cell_of_point.ptr, coarse.ptr, cdims[0], cdims[1]);
   rank_index_scan_async(index.ptr, n_words, scan_scratch, scan_scratch.total.ptr, s);
   nn_count_kernel<<<blocks, 256, 0, s>>>(n, cell_of_point.ptr, index.ptr, cell_start.ptr);
   {
@@ -349,7 +392,7 @@ void NnGrid::build(const float4* pts, size_t n, cudaStream_t s, const Bounds* kn
     if (n_tiles > 1) uscan_apply_kernel<<<n_tiles, USCAN_THREADS, 0, s>>>(cell_start.ptr, occ_max, scan_tmp.ptr);
   }
   nn_scatter_kernel<<<blocks, 256, 0, s>>>(pts, n, cell_of_point.ptr, index.ptr, cell_start.ptr, cursor.ptr, sorted.ptr);
-  launches += 9;
+  launches += 10;
   B200_CUDA(cudaGetLastError());
   n_cells_occupied = occ_max;  // upper bound; the exact count stays on the device (scan_scratch.total)
   valid = true;
@@ -370,7 +413,7 @@ void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float*
   B200_CUDA(cudaMemsetAsync(gm.unresolved_count.ptr, 0, sizeof(unsigned), s));
   const int blocks = (int)((n + 127) / 128);
   nn1_kernel<<<blocks, 128, 0, s>>>(P, queries, n, d_idx, d_d2, gm.unresolved_count.ptr, gm.unresolved.ptr);
-  nn1_bruteforce_kernel<<<148 * 4, 256, 0, s>>>(P, queries, gm.unresolved_count.ptr, gm.unresolved.ptr, d_idx, d_d2);
+  nn1_far_kernel<<<148 * 4, 256, 0, s>>>(P, queries, gm.unresolved_count.ptr, gm.unresolved.ptr, d_idx, d_d2);
   B200_CUDA(cudaGetLastError());
 }
 

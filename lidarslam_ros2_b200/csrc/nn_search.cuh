@@ -13,11 +13,18 @@ struct NnGeom {
   int dims[3];
 };
 
+constexpr int NN_COARSE_SHIFT = 3;  // a coarse cell = 8 x 8 x 8 grid cells
+
 struct NnView {
   const RankWord* index;
   const unsigned* cell_start;
   const float4* sorted;  // xyz + original index (int bits) in w
   NnGeom g;
+  // coarse level: tight bounding box of the points of every 8x8x8 block of cells (6 order-preserving uints: min xyz,
+  // max xyz; min > max = empty) — the far-query pass of nn_grid.cu prunes with it
+  const unsigned* coarse;
+  int cdims[3];
+  int n_coarse;
 };
 
 struct NnGrid;

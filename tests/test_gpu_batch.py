@@ -220,3 +220,30 @@ def test_voxelgrid_sparse_index_equals_dense(b200, oracle_mod):
             np.testing.assert_allclose(sparse, ref, atol=5e-5)
     finally:
         L.b200reg_debug_set_voxelgrid_dense_budget(4 << 20)
+
+
+def test_nn_far_queries_exact(b200):
+    """Exact 1-NN for queries the ring search cannot resolve (far outside the target's bounding box, or deep inside an empty
+    region): the coarse-level pass of nn_grid.cu must return the brute-force answer — same index (lower index on ties) and
+    the same un-fused float32 squared distance."""
+    from lidarslam_ros2_b200 import synth
+
+    _, tgt, _ = synth.registration_pair("small", 2.0)
+    tgt = np.ascontiguousarray(tgt[:, :3])
+    tgt[100] = tgt[7]  # an exact duplicate: the lower index must win
+    rng = np.random.default_rng(3)
+    lo, hi = tgt.min(axis=0), tgt.max(axis=0)
+    inside = rng.uniform(lo, hi, size=(300, 3))
+    inside[:, 2] += 25.0  # high above the scene: empty space, still inside the x/y extent
+    outside = rng.uniform(lo - 400.0, hi + 400.0, size=(700, 3))
+    near = tgt[rng.integers(0, len(tgt), 200)] + rng.normal(0, 0.05, size=(200, 3))
+    q = np.concatenate([inside, outside, near, tgt[7:8]]).astype(np.float32)
+    g = b200.NormalDistributionsTransform()
+    g.setInputTarget(tgt)
+    idx, d2 = g.nearest(q)
+    d = q[:, None, :] - tgt[None, :, :]                       # float32, un-fused like FLANN's L2_Simple
+    ref = (d[:, :, 0] * d[:, :, 0] + d[:, :, 1] * d[:, :, 1]) + d[:, :, 2] * d[:, :, 2]
+    ridx = ref.argmin(axis=1)                                 # first minimum = lowest index
+    np.testing.assert_array_equal(idx, ridx)
+    np.testing.assert_array_equal(d2, ref[np.arange(len(q)), ridx])
+    assert idx[-1] == 7
