@@ -299,6 +299,7 @@ int b200reg_create(int kind, int device, b200reg_t* out) {
     B200_CUDA(cudaEventCreate(&h->ev1));
     h->solver.init(device, h->stream);
     h->solver.timing_enabled = getenv("B200REG_TIMING") != nullptr;
+    h->solver.batch_profile = getenv("B200REG_BATCH_PROFILE") != nullptr;
     h->solver.scalar_controller = getenv("B200REG_SCALAR_CTL") != nullptr;
     h->solver.plain_launch = getenv("B200REG_PLAIN_LAUNCH") != nullptr;
     h->gicp_solver.device_bfgs = getenv("B200REG_GICP_HOST_BFGS") == nullptr;  // developer switch: host-driven BFGS

@@ -226,6 +226,7 @@ class NdtSolver {
   bool scalar_controller = false;  // developer switch (env B200REG_SCALAR_CTL=1)
   bool plain_launch = false;       // developer switch (env B200REG_PLAIN_LAUNCH=1): non-cooperative launch
   bool timing_enabled = false;  // developer instrumentation (env B200REG_TIMING=1)
+  bool batch_profile = false;   // developer instrumentation (env B200REG_BATCH_PROFILE=1): per-CTA wait / evaluate / reduce cycles
   void read_timing(unsigned long long* out48x8) const;
   void read_cta_eval_ns(unsigned* out, int n) const;
   void reset_barrier();

@@ -13,6 +13,10 @@
 #include <vector>
 
 #include "bfgs6.hpp"
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "gicp.hpp"
 #include "nn_search.cuh"
 
@@ -778,6 +782,17 @@ void GicpSolver::fdf(const float* T16, bool want_grad, double* f, double* g_t3, 
 
 GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, size_t n_target, const float4* source,
                               size_t n_source, const GicpConfig& cfg, const float* guess16, cudaStream_t s) {
+  // developer trace (env B200REG_GICP_TRACE=1): host wall clock per phase of one align, printed to stderr
+  static const bool trace = getenv("B200REG_GICP_TRACE") != nullptr;
+  auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double t_prev = trace ? now() : 0, t_cov = 0, t_nn = 0, t_inner = 0;
+  auto lap = [&](double& acc) {
+    if (!trace) return;
+    B200_CUDA(cudaStreamSynchronize(s));
+    const double t = now();
+    acc += t - t_prev;
+    t_prev = t;
+  };
   stream_ = s;
   target_ = target;
   n_target_ = n_target;
@@ -826,6 +841,7 @@ GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, s
   transform_kernel<<<blocks_pts, 256, 0, s>>>(source, (int)n_source, moved_.ptr, tbuf.ptr);
   launches += 1;
 
+  lap(t_cov);
   float transformation[16], previous[16];
   set_identity16(transformation);
   set_identity16(previous);
@@ -857,6 +873,7 @@ GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, s
     B200_CUDA(cudaStreamSynchronize(s));
     launches += 1;
     last_m_ = (int)m;
+    lap(t_nn);
     std::memcpy(previous, transformation, sizeof(previous));
     if (m < 4) break;  // NotEnoughPointsException → caught → break (:187-192, :494-498)
 
@@ -905,6 +922,7 @@ GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, s
         result = bfgs.testGradient(cfg.gradient_tol);
       } while (result == BFGS_Running && inner < cfg.max_inner_iterations);
     }
+    lap(t_inner);
     if (!(result == BFGS_NoProgress || result == BFGS_Success || inner == cfg.max_inner_iterations)) break;  // throws in the reference
     set_identity16(transformation);
     apply_state(transformation, x);
@@ -932,6 +950,10 @@ GicpOutcome GicpSolver::align(const NnGrid& target_grid, const float4* target, s
   out.converged = converged ? 1 : 0;
   out.iterations = nr_iterations;
   out.evaluations = evaluations_;
+  if (trace)
+    std::fprintf(stderr, "[gicp trace] source grid + covariances + transform %.3f ms, correspondences (NN + Mahalanobis) %.3f ms, "
+                         "inner BFGS launches %.3f ms (kernel events %.3f ms), %d outer iterations, %d evaluations\n",
+                 t_cov, t_nn, t_inner, inner_ms, nr_iterations, evaluations_);
   return out;
 }
 

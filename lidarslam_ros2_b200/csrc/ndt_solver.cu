@@ -58,7 +58,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 }
 #define B200_STAMP(cond, round, slot)                                                                  \
   do {                                                                                                 \
-    if (L.timing && (cond) && (round) < NDT_TIMING_ROUNDS) W->timing[round][slot] = globaltimer_ns(); \
+    if (L.timing && !L.jobs && (cond) && (round) < NDT_TIMING_ROUNDS) W->timing[round][slot] = globaltimer_ns(); \
   } while (0)
 
 // ---- TMA bulk copy helpers (cp.async.bulk → UBLKCP) -----------------------------------------------------
@@ -873,6 +873,8 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
   }
 
   const int all_ready = (1 << SOLVER_WARPS) - 2;
+  const bool prof = batch && L.timing && tid == 0;  // developer instrumentation: cycles waiting for rows / in the controller step
+  long long c_rows = 0, c_step = 0;
   for (int round = 0;; round++) {
     if (warp != 0) {
       // ---- warps 1..23: fixed-order reduction of the evaluators' partial rows --------------------------------------
@@ -953,6 +955,8 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
         }
       }
       __threadfence_block();
+      const long long t_rows = prof ? clock64() : 0;
+      if (prof) c_rows += t_rows - t0;
       B200_STAMP(lane == 0, round, 4);
       if (L.timing && lane == 0 && round < NDT_TIMING_ROUNDS) {
         unsigned long long tmax = 0, tmin = ~0ull;
@@ -1005,6 +1009,7 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
       }
       __syncwarp();
       publish(round + pub_shift);
+      if (prof) c_step += clock64() - t_rows;
       B200_STAMP(lane == 0, round, 6);
       if (lane == 0) cs.ready = 0;
     }
@@ -1012,6 +1017,10 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
     if (cs.done) break;
   }
   if (batch) {
+    if (prof) {
+      W->cta_eval_ns[n_eval_i + slot][0] = (unsigned)(c_rows >> 10);
+      W->cta_eval_ns[n_eval_i + slot][1] = (unsigned)(c_step >> 10);
+    }
     __threadfence_system();
     return;
   }
@@ -1135,6 +1144,10 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
     alive[k] = k < n_slots;
   }
   int n_alive = n_slots;
+  // developer instrumentation (L.timing in a batch launch): SM cycles this CTA spent waiting for control blocks,
+  // evaluating, and reducing — read back with b200reg_debug_cta_eval_ns (three counters per CTA, in kilocycles)
+  const bool prof = batch && L.timing && tid == 0;
+  long long c_wait = 0, c_eval = 0, c_red = 0, c_mark = prof ? clock64() : 0;
   for (int s = 0; n_alive > 0; s = (s + 1 >= n_slots) ? 0 : s + 1) {
     int round = 0;
     bool live = false;
@@ -1171,7 +1184,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
         payload = (unsigned)v;
       }
       reinterpret_cast<unsigned*>(&ctl_s[s])[tid] = payload;
-      if (round > 0) B200_STAMP(stamp0, round - 1, 7);
+      if (!batch && round > 0) B200_STAMP(stamp0, round - 1, 7);
     }
     __syncthreads();
     const NdtControl& ctl = ctl_s[s];
@@ -1182,8 +1195,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
       n_alive--;
       continue;
     }
-    B200_STAMP(stamp0, round, 0);
-    const unsigned long long t_round = (L.timing && tid == 0) ? globaltimer_ns() : 0ull;
+    if (prof) {
+      const long long t = clock64();
+      c_wait += t - c_mark;
+      c_mark = t;
+    }
+    if (!batch) B200_STAMP(stamp0, round, 0);
+    const unsigned long long t_round = (!batch && L.timing && tid == 0) ? globaltimer_ns() : 0ull;
 
     // ---- (0b) batch: a new registration on this slot — restage its points ----------------------------------------
     if (batch && ctl.job != slot_job[s]) {
@@ -1235,8 +1253,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
           }
         }
       }
-      B200_STAMP(stamp0, round, 1);
-      if (L.timing && tid == 0 && round == 2) {
+      if (prof) {
+        const long long t = clock64();
+        c_eval += t - c_mark;
+        c_mark = t;
+      }
+      if (!batch) B200_STAMP(stamp0, round, 1);
+      if (!batch && L.timing && tid == 0 && round == 2) {
         W->cta_eval_ns[my_rank][0] = (unsigned)t_round;
         W->cta_eval_ns[my_rank][1] = (unsigned)globaltimer_ns();
       }
@@ -1286,15 +1309,28 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
         const double sum = (sa + sb) + (sc2 + sd);
         st_relaxed_gpu_u64(reinterpret_cast<unsigned long long*>(&W->partials[s][round & 1][my_rank][tid]),
                            (unsigned long long)__double_as_longlong(sum));
-        if (L.timing && round == 2 && tid == 0) W->cta_eval_ns[my_rank][2] = (unsigned)globaltimer_ns();
+        if (!batch && L.timing && round == 2 && tid == 0) W->cta_eval_ns[my_rank][2] = (unsigned)globaltimer_ns();
       }
-      B200_STAMP(stamp0, round, 2);
-      B200_STAMP(stamp0, round, 3);
+      if (prof) {
+        const long long t = clock64();
+        c_red += t - c_mark;
+        c_mark = t;
+      }
+      if (!batch) {
+        B200_STAMP(stamp0, round, 2);
+        B200_STAMP(stamp0, round, 3);
+      }
     }
     skip_eval = false;
 #pragma unroll
     for (int k = 0; k < NDT_MAX_SLOTS; k++)
       if (k == s) rounds[k] = round + 1;
+  }
+  if (prof) {
+    W->cta_eval_ns[my_rank][0] = (unsigned)(c_wait >> 10);
+    W->cta_eval_ns[my_rank][1] = (unsigned)(c_eval >> 10);
+    W->cta_eval_ns[my_rank][2] = (unsigned)(c_red >> 10);
+    W->cta_eval_ns[my_rank][3] = (unsigned)((clock64() - c_mark) >> 10);
   }
 }
 
@@ -1423,7 +1459,10 @@ void NdtSolver::fill_common(NdtLaunch& L, const VoxelMap& map, const NdtConfig& 
   // CTAs overlay their own state on the same bytes
   const size_t index_bytes = ((size_t)map.geom.n_words * 8 + 127) & ~(size_t)127;
   L.index_in_smem = (map.geom.n_words > 0 && index_bytes <= (size_t)SOLVER_MAX_INDEX_SMEM) ? 1 : 0;
-  L.acc_offset = L.index_in_smem ? (int)index_bytes : 0;
+  // the index region is rounded up to 8 KB steps: consecutive targets of similar extent (the loop-closure sweep, the
+  // frontend's growing map) then launch with the SAME dynamic shared-memory size — a cooperative launch whose size differs
+  // from the previous one's costs the driver ~0.1 ms of extra work (measured on the loop-closure pairs)
+  L.acc_offset = L.index_in_smem ? (int)((index_bytes + 8191) & ~(size_t)8191) : 0;
   L.pts_offset = L.acc_offset + ACC_BYTES_PAD;
   // (a single registration stages one block of points: the shared-memory carve-out, and with it the L1 left for the
   // voxel-record gathers, stays what it was before batching existed)
@@ -1509,7 +1548,7 @@ void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n,
   size_t dyn_smem = 0;
   const int n_slots = std::max(1, std::min(std::min(slots, NDT_MAX_SLOTS), n));
   fill_common(L, map, cfg, NDT_MODE_ALIGN, n_slots, dyn_smem);
-  L.timing = 0;
+  L.timing = batch_profile ? 1 : 0;
   L.result_host = h_batch_results_;
   L.jobs = d_jobs_;
   L.n_jobs = n;

@@ -174,6 +174,33 @@ __global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4*
   nn_query_point(P, queries[i], qx, qy, qz);
   float best;
   int best_i;
+  {
+    // An outlier is recognised before any cell is probed: if the query's 8x8x8 block of cells and its 26 neighbours hold no
+    // point at all, nothing lies within NN_MAX_RINGS (< 8) rings — the ring search would probe 7^3 cells for nothing (a scan
+    // reaching far beyond a local map made this kernel wait for exactly those threads). Straight to the far-query pass.
+    const NnView& V = P.V;
+    const int bx = nn_cell_coord(qx, V.g.origin[0], V.g.inv_h, V.g.dims[0]) >> NN_COARSE_SHIFT;
+    const int by = nn_cell_coord(qy, V.g.origin[1], V.g.inv_h, V.g.dims[1]) >> NN_COARSE_SHIFT;
+    const int bz = nn_cell_coord(qz, V.g.origin[2], V.g.inv_h, V.g.dims[2]) >> NN_COARSE_SHIFT;
+    bool any = false;
+    for (int dz = -1; dz <= 1 && !any; dz++)
+      for (int dy = -1; dy <= 1 && !any; dy++)
+        for (int dx = -1; dx <= 1; dx++) {
+          const int x = bx + dx, y = by + dy, z = bz + dz;
+          if (x < 0 || y < 0 || z < 0 || x >= V.cdims[0] || y >= V.cdims[1] || z >= V.cdims[2]) continue;
+          const unsigned* a = V.coarse + 6 * (size_t)(x + V.cdims[0] * (y + V.cdims[1] * z));
+          if (__ldg(a) <= __ldg(a + 3)) {
+            any = true;
+            break;
+          }
+        }
+    if (!any) {
+      out_idx[i] = -1;
+      out_d2[i] = FLT_MAX;
+      unresolved_list[atomicAdd(unresolved_count, 1u)] = (int)i;
+      return;
+    }
+  }
   const bool resolved = nn1_search(P.V, qx, qy, qz, P.max_d2, NN_MAX_RINGS, best, best_i);
   out_idx[i] = best_i;
   out_d2[i] = best;
