@@ -5,6 +5,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
+#include <cstdio>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -147,8 +149,16 @@ void ensure_nn(b200reg_t h) {
   h->nn_valid = true;
 }
 
+// developer trace (env B200REG_TRACE=1): host wall clock of the phases of one NDT align, printed to stderr
+static const bool g_trace = getenv("B200REG_TRACE") != nullptr;
+static double trace_now() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+static thread_local double g_trace_t[4];
+
 // ---- NDT align: enqueue / complete ------------------------------------------------------------------------
 int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
+  if (g_trace) g_trace_t[0] = trace_now();
   h->converged = 0;
   set_identity(h->final_T);
   if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "align: no input target");
@@ -168,9 +178,11 @@ int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
     h->align_pending = false;
     return B200REG_OK;
   }
+  if (g_trace) g_trace_t[1] = trace_now();
   B200_CUDA(cudaEventRecord(h->ev0, h->stream));
   h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
   B200_CUDA(cudaEventRecord(h->ev1, h->stream));  // solve_ms brackets the kernel(s) on the stream, nothing host-side
+  if (g_trace) g_trace_t[2] = trace_now();
   h->align_pending = true;
   return B200REG_OK;
 }
@@ -201,6 +213,11 @@ int ndt_align_end(b200reg_t h) {
       return fail(h, B200REG_ERR_TIMEOUT, "NDT solver kernel watchdog fired (grid barrier timeout)");
     }
     B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
+    if (g_trace) {
+      const double t = trace_now();
+      std::fprintf(stderr, "[trace] align: prologue %.1f us, launch calls %.1f us, wait %.1f us (kernel events %.1f us)\n",
+                   g_trace_t[1] - g_trace_t[0], g_trace_t[2] - g_trace_t[1], t - g_trace_t[2], 1e3 * h->solve_ms);
+    }
     std::memcpy(h->final_T, r.final_T, sizeof(h->final_T));
     h->converged = r.converged;
     h->iterations = r.iterations;
