@@ -696,7 +696,8 @@ def main():
     pageable_scans = [np.ascontiguousarray(x).copy() for x in scans]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     poses_dev = torch.zeros((K, 16), dtype=torch.float32, device="cuda")
-    gathered = [torch.empty_like(poses_dev) for _ in range(world)]
+    poses_pin = torch.zeros((K, 16), dtype=torch.float32).pin_memory()
+    gathered = torch.empty((world * K, 16), dtype=torch.float32, device="cuda")
     ptrs = [d.data_ptr() for d in dev_scans]
     counts = [int(d.shape[0]) for d in dev_scans]
 
@@ -717,9 +718,10 @@ def main():
         barrier()
         e0.record()
         r = fn()
-        poses_dev.copy_(torch.from_numpy(np.ascontiguousarray(r["pose"].reshape(-1, 16)[:K])), non_blocking=False)
+        poses_pin.numpy()[:] = r["pose"].reshape(-1, 16)[:K]
+        poses_dev.copy_(poses_pin, non_blocking=True)
         if world > 1:  # the one collective of the replicated sweep: all-gather of the 4x4 poses (NCCL over NVLink)
-            dist.all_gather(gathered, poses_dev)
+            dist.all_gather_into_tensor(gathered, poses_dev)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -738,7 +740,7 @@ def main():
     ndt.alignBatch([p.numpy() for p in pinned_scans[:K]])  # full size: the staging / device buffers reach their final size here
     ndt.alignBatch(pageable_scans[:K])
     if world > 1:
-        dist.all_gather(gathered, poses_dev)
+        dist.all_gather_into_tensor(gathered, poses_dev)
 
     prev_aff = pin_host_thread(local_rank)
     sampler = ClockSampler(local_rank)

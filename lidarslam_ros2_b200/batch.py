@@ -143,8 +143,13 @@ class LoopSweep:
         if len(indices) == 0:
             return np.zeros((0, ROW), dtype=np.float32)
         r = self.ndt.sweep(sources, targets)
-        rows = [pack_row(i, r["pose"][k], r["fitness"][k], bool(r["converged"][k]), int(r["iterations"][k])) for k, i in enumerate(indices)]
-        return np.array(rows, dtype=np.float32).reshape(-1, ROW)
+        rows = np.zeros((len(indices), ROW), dtype=np.float32)
+        rows[:, :16] = r["pose"].reshape(-1, 16)
+        rows[:, 16] = r["fitness"]
+        rows[:, 17] = r["converged"] != 0
+        rows[:, 18] = r["iterations"]
+        rows[:, 19] = np.asarray(indices, dtype=np.float32)
+        return rows
 
     def run_sequential(self, sources, targets, indices) -> np.ndarray:
         """The same pairs one after the other through the public single-pair calls (reference for the parity test)."""

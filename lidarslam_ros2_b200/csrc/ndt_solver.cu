@@ -41,9 +41,13 @@ namespace {
 constexpr int SOLVER_THREADS = 768;
 constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
 constexpr int SOLVER_MIN_CTAS = 1;
-constexpr int SMEM_POINTS = 1024;  // source points of a CTA's chunk staged in shared memory for the whole solve
+#ifndef B200_SMEM_POINTS
+#define B200_SMEM_POINTS 1024  // developer switch for A/B builds
+#endif
+constexpr int SMEM_POINTS = B200_SMEM_POINTS;  // source points of a CTA's chunk staged in shared memory for the whole solve
 constexpr int ACC_SLOTS = 27;      // 6 gradient + 21 upper-triangular Hessian sums per thread (f32, in shared memory)
-constexpr int ACC_STRIDE = SOLVER_THREADS + 1;
+constexpr int ACC_STRIDE = SOLVER_THREADS + 4;  // rows start 16-byte aligned (the warp reduction reads them with LDS.128) and the
+                                                // 772-float pitch spreads the eight lanes of a quarter-warp over all 32 banks
 constexpr int ACC_BYTES = ACC_SLOTS * ACC_STRIDE * 4;
 constexpr int SOLVER_MAX_INDEX_SMEM = 64 * 1024;  // the rank index is staged in shared memory up to this size
 constexpr int PTS_BYTES = SMEM_POINTS * 16;  // per slot
@@ -1269,26 +1273,26 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
 #pragma unroll
         for (int k = 0; k < ACC_SLOTS; k++) acc_s[k][tid] = 0.f;
       }
-      double sc = acc.score, hc = (double)acc.hits;
+      double sc = acc.score;
 #pragma unroll
-      for (int d = 16; d > 0; d >>= 1) {
-        sc += __shfl_xor_sync(0xffffffffu, sc, d);
-        hc += __shfl_xor_sync(0xffffffffu, hc, d);
-      }
+      for (int d = 16; d > 0; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
+      const double hc = (double)__reduce_add_sync(0xffffffffu, acc.hits);
       __syncwarp();
       {
         double v = 0.0;
         if (lane >= SLOT_G && lane < SLOT_G + ACC_SLOTS) {
-          const float* row = &acc_s[lane - SLOT_G][warp * 32];
-          double v0 = 0.0, v1 = 0.0, v2 = 0.0, v3 = 0.0;  // four independent chains, fixed order
+          // 32 columns of this slot: eight 16-byte loads; the four values of a load (four neighbouring threads' sums, each of
+          // <= a few points) are added in f32, the eight results in f64, fixed order. (The reference adds every pair's f32
+          // contribution to an f64 accumulator; a 4-term f32 pre-sum adds ~1e-7 relative rounding to terms that already carry
+          // the f32 rounding of the per-pair products — and takes 100 of the 160 instructions out of this reduction.)
+          const float4* row4 = reinterpret_cast<const float4*>(&acc_s[lane - SLOT_G][warp * 32]);
+          double p[8];
 #pragma unroll
-          for (int t = 0; t < 32; t += 4) {
-            v0 += (double)row[t];
-            v1 += (double)row[t + 1];
-            v2 += (double)row[t + 2];
-            v3 += (double)row[t + 3];
+          for (int t = 0; t < 8; t++) {
+            const float4 q = row4[t];
+            p[t] = (double)__fadd_rn(__fadd_rn(q.x, q.y), __fadd_rn(q.z, q.w));
           }
-          v = (v0 + v1) + (v2 + v3);
+          v = ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
         } else if (lane == SLOT_SCORE) {
           v = sc;
         } else if (lane == SLOT_HITS) {

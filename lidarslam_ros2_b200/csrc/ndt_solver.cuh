@@ -9,7 +9,10 @@ constexpr int NDT_MAX_CTAS = 256;  // one CTA per SM
 // Registrations in flight inside one batch launch = controller CTAs. Every launch (single or batched) leaves this many
 // SMs to controllers, so that the evaluator count — and with it the point partition and the fixed summation order —
 // is the same for b200reg_align and for b200reg_ndt_align_batch: a batched result is bitwise the single-align result.
-constexpr int NDT_MAX_SLOTS = 3;
+#ifndef B200_NDT_MAX_SLOTS
+#define B200_NDT_MAX_SLOTS 3  // developer switch for A/B builds
+#endif
+constexpr int NDT_MAX_SLOTS = B200_NDT_MAX_SLOTS;
 
 enum EvalMode : int {
   EVAL_DERIV = 0,        // fused derivative pass (K1)

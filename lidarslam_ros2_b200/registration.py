@@ -193,16 +193,20 @@ class NormalDistributionsTransform(_Registration):
         return v.value
 
     # ---- batched registrations against the current target (one persistent launch, two in flight) ----
+    # b200reg_batch_result as a numpy record: the K results are unpacked with a handful of vectorised field reads
+    _BATCH_DTYPE = np.dtype([("final_T", np.float32, (16,)), ("trans_probability", np.float64), ("converged", np.int32),
+                             ("iterations", np.int32), ("evaluations", np.int32), ("status", np.int32), ("hits_total", np.int64)])
+
     def _batch_out(self, res, K):
-        T = np.stack([_from_colmajor(np.frombuffer(res[k].final_T, dtype=np.float32).copy()) for k in range(K)]) if K else \
-            np.zeros((0, 4, 4), dtype=np.float32)
-        return {"pose": T,
-                "converged": np.array([res[k].converged for k in range(K)], dtype=np.int32),
-                "iterations": np.array([res[k].iterations for k in range(K)], dtype=np.int32),
-                "evaluations": np.array([res[k].evaluations for k in range(K)], dtype=np.int32),
-                "trans_probability": np.array([res[k].trans_probability for k in range(K)]),
-                "hits_total": np.array([res[k].hits_total for k in range(K)], dtype=np.int64),
-                "status": np.array([res[k].status for k in range(K)], dtype=np.int32)}
+        assert self._BATCH_DTYPE.itemsize == C.sizeof(_capi.BatchResult)
+        if K == 0:
+            z = np.zeros(0, dtype=self._BATCH_DTYPE)
+            return {"pose": np.zeros((0, 4, 4), dtype=np.float32), **{k: z[k] for k in ("converged", "iterations", "evaluations",
+                                                                                       "trans_probability", "hits_total", "status")}}
+        a = np.frombuffer(res, dtype=self._BATCH_DTYPE, count=K)
+        return {"pose": a["final_T"].reshape(K, 4, 4).transpose(0, 2, 1).copy(),  # column-major -> row-major
+                "converged": a["converged"].copy(), "iterations": a["iterations"].copy(), "evaluations": a["evaluations"].copy(),
+                "trans_probability": a["trans_probability"].copy(), "hits_total": a["hits_total"].copy(), "status": a["status"].copy()}
 
     def alignBatch(self, clouds, guesses=None) -> dict:
         """K independent align() calls against the current target, sources in HOST memory (b200reg_ndt_align_batch).
@@ -248,12 +252,15 @@ class NormalDistributionsTransform(_Registration):
         res = (_capi.SweepResult * max(K, 1))()
         self._check(self._lib.b200reg_ndt_sweep(self._h, K, sp, sn, tp, tn, stride, _ptr(g) if g is not None else None,
                                                 float(fitness_max_range), res))
-        return {"pose": np.stack([_from_colmajor(np.frombuffer(res[k].final_T, dtype=np.float32).copy()) for k in range(K)]) if K
-                else np.zeros((0, 4, 4), np.float32),
-                "fitness": np.array([res[k].fitness for k in range(K)]),
-                "converged": np.array([res[k].converged for k in range(K)], dtype=np.int32),
-                "iterations": np.array([res[k].iterations for k in range(K)], dtype=np.int32),
-                "status": np.array([res[k].status for k in range(K)], dtype=np.int32)}
+        if K == 0:
+            return {"pose": np.zeros((0, 4, 4), np.float32), "fitness": np.zeros(0), "converged": np.zeros(0, np.int32),
+                    "iterations": np.zeros(0, np.int32), "status": np.zeros(0, np.int32)}
+        a = np.frombuffer(res, dtype=self._SWEEP_DTYPE, count=K)
+        return {"pose": a["final_T"].reshape(K, 4, 4).transpose(0, 2, 1).copy(), "fitness": a["fitness"].copy(),
+                "converged": a["converged"].copy(), "iterations": a["iterations"].copy(), "status": a["status"].copy()}
+
+    _SWEEP_DTYPE = np.dtype([("final_T", np.float32, (16,)), ("fitness", np.float64), ("trans_probability", np.float64),
+                             ("converged", np.int32), ("iterations", np.int32), ("status", np.int32), ("pad", np.int32)])
 
     def setBatchSlots(self, slots: int):
         self._check(self._lib.b200reg_ndt_set_batch_slots(self._h, int(slots)))
