@@ -7,6 +7,8 @@
 #include <atomic>
 #include <chrono>
 #include <cstdio>
+#include <dlfcn.h>
+#include <functional>
 #include <mutex>
 #include <string>
 #include <thread>
@@ -75,6 +77,9 @@ struct b200reg_engine {
   std::vector<NdtSolver::BatchItem> batch_items;
   int batch_slots = NDT_BATCH_SLOTS_DEFAULT;
   int sibling_launches_seen = 0;
+  cudaStream_t copy_stream = nullptr;    // streaming uploads of b200reg_ndt_align_batch
+  DeviceBuffer<unsigned> batch_ready;    // one "scan k has arrived" flag per registration of a batch
+  unsigned batch_tag = 0;                // value the flags take for the current call
   b200reg_engine* sibling = nullptr;  // second engine of b200reg_ndt_sweep (own stream and buffers), created on first use
 };
 
@@ -342,6 +347,7 @@ int b200reg_destroy(b200reg_t h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->sibling) b200reg_destroy(h->sibling);
+  if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStream_t s = h->stream;
   delete h;
   if (s) cudaStreamDestroy(s);
@@ -829,8 +835,31 @@ int b200reg_nn1(b200reg_t h, const float* base, size_t n, size_t stride_bytes, i
 
 // ---- batched NDT registration: K independent scans against the current target in ONE persistent launch --------------
 namespace {
-// items: device-resident sources + row-major guesses, already in h->batch_items
-int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results) {
+// cuStreamWriteValue32 (driver API), bound at run time: a 32-bit store into device memory performed by the stream when it
+// gets there — the copy stream marks "scan k has arrived" with it while the persistent solver kernel is already running
+using StreamWriteValue32 = int (*)(cudaStream_t, unsigned long long, unsigned, unsigned);
+StreamWriteValue32 stream_write_value32() {
+  static StreamWriteValue32 fn = []() -> StreamWriteValue32 {
+    if (getenv("B200REG_NO_STREAM_MEMOPS")) return nullptr;  // developer switch: upload everything first
+    void* lib = dlopen("libcuda.so.1", RTLD_NOW);
+    if (!lib) return nullptr;
+    void* p = dlsym(lib, "cuStreamWriteValue32_v2");
+    if (!p) p = dlsym(lib, "cuStreamWriteValue32");
+    return reinterpret_cast<StreamWriteValue32>(p);
+  }();
+  return fn;
+}
+
+bool batch_needs_sequential(b200reg_t h) {
+  // One launch cannot serve: an empty map (the reference returns the guess), or a configuration whose line search runs
+  // the More-Thuente inner loop (step_max <= step_min: it leaves the kernel for the f64 radius Hessian) — those take
+  // the single-registration path one by one.
+  return h->map.n_voxels == 0 || !((h->ndt.step_size - h->ndt.trans_eps / 2) > 0) || h->solver.timing_enabled;
+}
+
+// items: device-resident sources + row-major guesses, already in h->batch_items. after_launch (optional) runs on the host
+// right after the solver launch of a chunk has been enqueued (the streaming upload of b200reg_ndt_align_batch).
+int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const std::function<void()>& after_launch = nullptr) {
   if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "align_batch: no input target");
   ensure_map(h);
   std::vector<NdtSolver::BatchItem>& items = h->batch_items;
@@ -846,10 +875,7 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results) {
     r.hits_total = hits;
   };
   long long evals = 0, hits = 0;
-  // One launch cannot serve: an empty map (the reference returns the guess), or a configuration whose line search runs
-  // the More-Thuente inner loop (step_max <= step_min: it leaves the kernel for the f64 radius Hessian) — those take
-  // the single-registration path one by one.
-  const bool sequential = h->map.n_voxels == 0 || !((h->ndt.step_size - h->ndt.trans_eps / 2) > 0) || h->solver.timing_enabled;
+  const bool sequential = batch_needs_sequential(h);
   if (sequential) {
     int worst = B200REG_OK;
     float ms = 0;
@@ -882,6 +908,7 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results) {
     B200_CUDA(cudaEventRecord(h->ev0, h->stream));
     h->solver.launch_batch(h->map, items.data() + first, n, h->ndt, h->batch_slots);
     B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+    if (after_launch) after_launch();
     B200_CUDA(cudaStreamSynchronize(h->stream));
     float ms = 0;
     B200_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
@@ -931,8 +958,11 @@ int b200reg_ndt_align_batch_device(b200reg_t h, int count, const void* const* de
     for (int k = 0; k < count; k++) {
       if (!dev_sources[k] || n_points[k] == 0) return fail(h, B200REG_ERR_ARG, "align_batch: empty source cloud");
       NdtSolver::BatchItem& it = h->batch_items[k];
-      it.src = static_cast<const float4*>(dev_sources[k]);
+      it.src = dev_sources[k];
       it.n_src = n_points[k];
+      it.stride = 0;
+      it.ready = nullptr;
+      it.ready_tag = 0;
       if (guesses) col_to_row(guesses + 16 * k, it.T_rowmajor16);
       else set_identity(it.T_rowmajor16);
     }
@@ -945,30 +975,71 @@ int b200reg_ndt_align_batch(b200reg_t h, int count, const float* const* sources,
   if (!h || h->kind != B200REG_NDT || count < 0 || (count > 0 && (!sources || !n_points || !results))) return B200REG_ERR_ARG;
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
   return guarded(h, [&]() {
+    if (!h->have_target) return fail(h, B200REG_ERR_NO_TARGET, "align_batch: no input target");
+    ensure_map(h);
     size_t total = 0, raw_total = 0;
     bool pageable = false;
     std::vector<char> pinned((size_t)count);
+    std::vector<size_t> raw_off((size_t)count);
     for (int k = 0; k < count; k++) {
       if (!sources[k] || n_points[k] == 0) return fail(h, B200REG_ERR_ARG, "align_batch: empty source cloud");
       total += n_points[k];
+      raw_off[k] = raw_total;
       raw_total += (n_points[k] * stride_bytes + 255) & ~(size_t)255;
       pinned[k] = CloudUploader::is_pinned(sources[k]) ? 1 : 0;
       pageable = pageable || !pinned[k];
     }
-    h->d_batch.ensure(total);
     h->batch_uploader.reserve(raw_total, pageable);
     h->batch_items.resize((size_t)count);
-    size_t off = 0, raw_off = 0;
-    for (int k = 0; k < count; k++) {  // copies and unpack kernels stream back to back; nothing waits in between
-      h->batch_uploader.upload_at(sources[k], pinned[k] != 0, n_points[k], stride_bytes, -1, 1.0f, h->d_batch.ptr + off, raw_off,
-                                  h->stream);
+    for (int k = 0; k < count; k++) {
       NdtSolver::BatchItem& it = h->batch_items[k];
-      it.src = h->d_batch.ptr + off;
       it.n_src = n_points[k];
       if (guesses) col_to_row(guesses + 16 * k, it.T_rowmajor16);
       else set_identity(it.T_rowmajor16);
+      it.stride = 0;
+      it.ready = nullptr;
+      it.ready_tag = 0;
+    }
+    const int per_launch = std::max(1, NdtSolver::kMaxRoundsPerLaunch / (h->ndt.max_iterations + 4));
+    StreamWriteValue32 write_value = stream_write_value32();
+    if (write_value && !batch_needs_sequential(h) && count <= per_launch) {
+      // Streaming form: the solver kernel is launched FIRST and reads the caller's records as they are (no unpack pass);
+      // the scans follow on a second stream, each DMA trailed by a stream memory operation that raises the scan's ready
+      // flag. Registration k starts as soon as scan k is there, so the upload of the later scans (and, for pageable
+      // memory, the CPU staging copy) is hidden behind the registration of the earlier ones.
+      if (!h->copy_stream) B200_CUDA(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+      h->batch_ready.ensure((size_t)count);
+      const unsigned tag = ++h->batch_tag;
+      for (int k = 0; k < count; k++) {
+        NdtSolver::BatchItem& it = h->batch_items[k];
+        it.src = h->batch_uploader.raw.ptr + raw_off[k];
+        it.stride = (int)stride_bytes;
+        it.ready = h->batch_ready.ptr + k;
+        it.ready_tag = tag;
+      }
+      bool copy_failed = false;
+      auto upload = [&]() {
+        for (int k = 0; k < count && !copy_failed; k++) {
+          h->batch_uploader.copy_at(sources[k], pinned[k] != 0, n_points[k] * stride_bytes, raw_off[k], h->copy_stream);
+          if (write_value(h->copy_stream, (unsigned long long)(uintptr_t)(h->batch_ready.ptr + k), tag, 0) != 0) copy_failed = true;
+        }
+        if (copy_failed) {  // never leave the kernel waiting: raise the remaining flags from the host path
+          std::vector<unsigned> tags((size_t)count, tag);
+          cudaStreamSynchronize(h->copy_stream);
+          cudaMemcpyAsync(h->batch_ready.ptr, tags.data(), sizeof(unsigned) * count, cudaMemcpyHostToDevice, h->copy_stream);
+        }
+        B200_CUDA(cudaStreamSynchronize(h->copy_stream));  // the caller may reuse its buffers on return
+      };
+      return ndt_batch_run(h, count, results, upload);
+    }
+    // fallback: upload + unpack everything, then register
+    h->d_batch.ensure(total);
+    size_t off = 0;
+    for (int k = 0; k < count; k++) {  // copies and unpack kernels stream back to back; nothing waits in between
+      h->batch_uploader.upload_at(sources[k], pinned[k] != 0, n_points[k], stride_bytes, -1, 1.0f, h->d_batch.ptr + off, raw_off[k],
+                                  h->stream);
+      h->batch_items[k].src = h->d_batch.ptr + off;
       off += n_points[k];
-      raw_off += (n_points[k] * stride_bytes + 255) & ~(size_t)255;
     }
     h->other_launches += count;
     return ndt_batch_run(h, count, results);

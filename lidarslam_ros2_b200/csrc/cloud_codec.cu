@@ -146,6 +146,11 @@ bool CloudUploader::is_pinned(const void* host) {
   if (!pinned) cudaGetLastError();
   return pinned;
 }
+// host -> raw device buffer only (no unpack): the batch solver reads the records as they are
+void CloudUploader::copy_at(const void* host, bool pinned, size_t bytes, size_t byte_offset, cudaStream_t s) {
+  if (bytes == 0) return;
+  staged_h2d(raw.ptr + byte_offset, host, bytes, pinned, staging.ptr + byte_offset, s);
+}
 void CloudUploader::upload_at(const void* host, bool pinned, size_t n, size_t stride, long w_off, float w_default, float4* dst,
                               size_t byte_offset, cudaStream_t s) {
   if (n == 0) return;

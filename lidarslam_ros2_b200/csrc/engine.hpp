@@ -97,6 +97,7 @@ struct CloudUploader {
   static bool is_pinned(const void* host);
   void upload_at(const void* host, bool pinned, size_t n, size_t stride, long w_off, float w_default, float4* dst,
                  size_t byte_offset, cudaStream_t s);
+  void copy_at(const void* host, bool pinned, size_t bytes, size_t byte_offset, cudaStream_t s);
 };
 void upload_cloud(const float* base, size_t n, size_t stride_bytes, DeviceBuffer<float4>& dst, CloudUploader& up, cudaStream_t s);
 
@@ -203,9 +204,12 @@ class NdtSolver {
               const float* T_rowmajor16, const double* p6, int compute_hessian, int resume = 0);
   // one registration of a batch: device-resident source (float4) and the row-major 4x4 guess
   struct BatchItem {
-    const float4* src;
+    const void* src;       // device memory: float4 points (stride 0 or 16) or raw records of `stride` bytes (x, y, z first)
     size_t n_src;
     float T_rowmajor16[16];
+    int stride = 0;
+    const unsigned* ready = nullptr;  // device flag that reads ready_tag once the points have arrived (nullptr: they are there)
+    unsigned ready_tag = 0;
   };
   // enqueue ONE launch that performs n independent registrations against `map`, `slots` (<= NDT_MAX_SLOTS) in flight;
   // after the stream has drained batch_results()[k] holds registration k (error != 0: the kernel never finished it)

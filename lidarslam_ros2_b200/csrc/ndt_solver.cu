@@ -42,7 +42,7 @@ constexpr int SOLVER_THREADS = 768;
 constexpr int SOLVER_WARPS = SOLVER_THREADS / 32;
 constexpr int SOLVER_MIN_CTAS = 1;
 #ifndef B200_SMEM_POINTS
-#define B200_SMEM_POINTS 1024  // developer switch for A/B builds
+#define B200_SMEM_POINTS 768  // developer switch for A/B builds (768 measured 5 % faster than 1024: more L1 for the records)
 #endif
 constexpr int SMEM_POINTS = B200_SMEM_POINTS;  // source points of a CTA's chunk staged in shared memory for the whole solve
 constexpr int ACC_SLOTS = 27;      // 6 gradient + 21 upper-triangular Hessian sums per thread (f32, in shared memory)
@@ -620,6 +620,29 @@ __device__ __noinline__ void start_next_job(const NdtLaunch& L, CtlShared& cs, i
     return;
   }
   const NdtJob* J = L.jobs + job;
+  if (J->ready) {  // the scan may still be on its way to the device: wait for the tag the copy stream writes behind it
+    const unsigned tag = J->ready_tag;
+    const long long t0 = clock64();
+    bool ok = true;
+    if (lane == 0) {
+      while (ld_relaxed_gpu(J->ready) != tag) {
+        if (clock64() - t0 > 4 * SPIN_TIMEOUT_CYCLES) {
+          ok = false;
+          break;
+        }
+      }
+      fence_acq_rel_gpu();
+    }
+    ok = __shfl_sync(0xffffffffu, ok ? 1 : 0, 0) != 0;
+    if (!ok) {  // the upload never arrived: retire the slot, the host reports the unfinished registrations
+      if (lane == 0) {
+        cs.next.mode = EVAL_DONE;
+        cs.done = 3;
+      }
+      __syncwarp();
+      return;
+    }
+  }
   {
     const unsigned* src = reinterpret_cast<const unsigned*>(&J->init);
     unsigned* dst = reinterpret_cast<unsigned*>(&cs.next);
@@ -1079,11 +1102,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
   __shared__ __align__(16) NdtControl ctl_s[NDT_MAX_SLOTS];
   __shared__ int abort_flag;
   __shared__ __align__(8) unsigned long long tma_bar;
-  __shared__ const float4* slot_src[NDT_MAX_SLOTS];
-  __shared__ int slot_nsrc[NDT_MAX_SLOTS], slot_job[NDT_MAX_SLOTS];
+  __shared__ const unsigned char* slot_src[NDT_MAX_SLOTS];
+  __shared__ int slot_nsrc[NDT_MAX_SLOTS], slot_job[NDT_MAX_SLOTS], slot_stride[NDT_MAX_SLOTS];
   // dynamic shared memory: [rank index, L.acc_offset bytes][per-thread f32 accumulators][staged points, one block per slot]
   float (*acc_s)[ACC_STRIDE] = reinterpret_cast<float (*)[ACC_STRIDE]>(dyn_smem + L.acc_offset);
-  float4 (*pts_s)[SMEM_POINTS] = reinterpret_cast<float4 (*)[SMEM_POINTS]>(dyn_smem + L.pts_offset);
+  constexpr int PTS_ALLOC = SMEM_POINTS > 0 ? SMEM_POINTS : 1;
+  float4 (*pts_s)[PTS_ALLOC] = reinterpret_cast<float4 (*)[PTS_ALLOC]>(dyn_smem + L.pts_offset);
   const RankWord* idx = L.index_in_smem ? reinterpret_cast<const RankWord*>(dyn_smem) : L.index;
 
   // stage the voxel rank index into shared memory with TMA bulk copies (once per launch)
@@ -1109,7 +1133,14 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
   // mix of near and far rings, which evens out the per-CTA evaluation time (measured 2.3 .. 5.1 us with contiguous
   // chunks — the evaluation is issue-bound and the barrier waits for the slowest CTA).
   const int n_eval = n_eval_ctas;
-  auto stage_points = [&](int s, const float4* src, int n_src) {
+  // point gi of a cloud of `stride`-byte records (16: one aligned 16-byte load; anything else: three float loads)
+  auto load_point = [](const unsigned char* base, int stride, int gi) {
+    const unsigned char* p = base + (size_t)gi * (size_t)stride;
+    if (stride == 16) return *reinterpret_cast<const float4*>(p);
+    const float* f = reinterpret_cast<const float*>(p);
+    return make_float4(f[0], f[1], f[2], 1.0f);
+  };
+  auto stage_points = [&](int s, const unsigned char* src, int stride, int n_src) {
     const int n_rows = rows_for(n_src, n_eval);
     if (my_rank >= n_rows) return;
     const int n_units = (n_src + 31) >> 5;
@@ -1117,12 +1148,12 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
     const int n_staged = min(my_units * 32, SMEM_POINTS);
     for (int j = tid; j < n_staged; j += SOLVER_THREADS) {  // thread tid later reads exactly the slots it writes here
       const int gi = (((j >> 5) * n_rows + my_rank) << 5) + (j & 31);
-      pts_s[s][j] = (gi < n_src) ? src[gi] : make_float4(0.f, 0.f, 0.f, 0.f);  // padding slot of the ragged last unit
+      pts_s[s][j] = (gi < n_src) ? load_point(src, stride, gi) : make_float4(0.f, 0.f, 0.f, 0.f);  // padding slot of the ragged last unit
     }
   };
   if (tid < NDT_MAX_SLOTS) slot_job[tid] = -1;
   if (tid == 0) abort_flag = 0;
-  if (!batch) stage_points(0, L.src, L.n_src);
+  if (!batch) stage_points(0, reinterpret_cast<const unsigned char*>(L.src), 16, L.n_src);
 
   if (L.index_in_smem) {
     long long t0 = clock64();
@@ -1215,11 +1246,13 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
         slot_job[s] = ctl.job;
         slot_src[s] = J->src;
         slot_nsrc[s] = J->n_src;
+        slot_stride[s] = J->stride;
       }
       __syncthreads();
-      stage_points(s, slot_src[s], slot_nsrc[s]);
+      stage_points(s, slot_src[s], slot_stride[s], slot_nsrc[s]);
     }
-    const float4* __restrict__ src = batch ? slot_src[s] : L.src;
+    const unsigned char* __restrict__ src = batch ? slot_src[s] : reinterpret_cast<const unsigned char*>(L.src);
+    const int src_stride = batch ? slot_stride[s] : 16;
     const int n_src = batch ? slot_nsrc[s] : L.n_src;
     const int n_rows = rows_for(n_src, n_eval);
     const bool active = my_rank < n_rows;  // small scans are spread over fewer evaluators (rows_for)
@@ -1245,7 +1278,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
           }
           for (int j = SMEM_POINTS + tid; j < n_local; j += SOLVER_THREADS) {
             const int gi = global_index(j);
-            if (gi < n_src) process_point<METHOD, true>(L, ctl, idx, src[gi], gd2, acc);
+            if (gi < n_src) process_point<METHOD, true>(L, ctl, idx, load_point(src, src_stride, gi), gd2, acc);
           }
         } else {
           for (int j = tid; j < n_staged; j += SOLVER_THREADS) {
@@ -1253,7 +1286,7 @@ __global__ void __launch_bounds__(SOLVER_THREADS, SOLVER_MIN_CTAS) ndt_solver_ke
           }
           for (int j = SMEM_POINTS + tid; j < n_local; j += SOLVER_THREADS) {
             const int gi = global_index(j);
-            if (gi < n_src) process_point<METHOD, false>(L, ctl, idx, src[gi], gd2, acc);
+            if (gi < n_src) process_point<METHOD, false>(L, ctl, idx, load_point(src, src_stride, gi), gd2, acc);
           }
         }
       }
@@ -1539,8 +1572,11 @@ void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n,
   for (int k = 0; k < n; k++) {
     NdtJob& J = h_jobs_[k];
     std::memset(&J, 0, sizeof(J));
-    J.src = items[k].src;
+    J.src = reinterpret_cast<const unsigned char*>(items[k].src);
     J.n_src = (int)items[k].n_src;
+    J.stride = items[k].stride ? items[k].stride : 16;
+    J.ready = items[k].ready;
+    J.ready_tag = items[k].ready_tag;
     initial_pose(items[k].T_rowmajor16, nullptr, J.p0, J.init_final, J.init, 1);
     J.init.job = k;
     n_max = std::max(n_max, items[k].n_src);

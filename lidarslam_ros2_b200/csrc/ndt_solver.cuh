@@ -66,8 +66,17 @@ constexpr int NDT_MAX_ROUNDS = 60000;  // sequence numbers are epoch * 65536 + r
 
 // one registration of a batch launch (device array, filled by the host before the launch)
 struct NdtJob {
-  const float4* src;
+  // source points: records of `stride` bytes with x, y, z floats first — 16 for a float4 cloud resident in HBM, the
+  // caller's record size when the raw host records were copied straight in (no unpack pass: the evaluators read them
+  // once, when they stage the registration's points into shared memory)
+  const unsigned char* src;
   int n_src;
+  int stride;
+  // ready == nullptr: the points are there when the launch starts. Otherwise the controller waits, before it starts this
+  // registration, until *ready == ready_tag: the copy stream writes the tag behind the scan's DMA (cuStreamWriteValue32),
+  // so later scans of a batch are still being uploaded while earlier ones are already being registered.
+  const unsigned* ready;
+  unsigned ready_tag;
   int pad;
   double p0[6];         // initial pose parameters (ndt_omp_impl.hpp:103-111)
   float init_final[16]; // final_transformation_ = guess
