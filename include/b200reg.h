@@ -102,10 +102,9 @@ int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out);
 /* the `output` cloud of align(): source transformed by the final transformation; out has n_source points */
 int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes);
 
-/* Batched loop-closure sweep over independent handles (different targets; generalises gbs.cpp:187-233 from the
- * arg-min candidate to all candidates): every NDT solve is ENQUEUED on its handle's stream before the first one is
- * waited for, so the host-side launch / synchronise round trips overlap the device work of the other handles. The
- * solver kernels themselves occupy the whole GPU and run one after the other. guesses may be NULL (identity);
+/* align() on `count` independent handles (each with its own target and source already set), one after the other — a
+ * convenience loop: every solve is a persistent kernel that owns all SMs, so solves never overlap; what overlaps between
+ * pairs is done by b200reg_ndt_sweep below (uploads, map builds, fitness passes). guesses may be NULL (identity);
  * finals = 16*count floats. Results are those of b200reg_align on each handle. */
 int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, float* finals);
 

@@ -68,6 +68,7 @@ struct b200reg_engine {
   long long hits_last = 0, hits_total = 0;
   float solve_ms = 0, target_build_ms = 0;
   bool align_pending = false;
+  std::unique_lock<std::mutex> coop_lock;  // held from a solver launch until its completion (cooperative_launch_mutex)
   bool grid_overflow = false;  // the last voxel-map build hit the int32 guard (voxel_grid_covariance_omp_impl.hpp:79)
   int other_launches = 0;
 
@@ -76,11 +77,12 @@ struct b200reg_engine {
   CloudUploader batch_uploader;
   std::vector<NdtSolver::BatchItem> batch_items;
   int batch_slots = NDT_BATCH_SLOTS_DEFAULT;
-  int sibling_launches_seen = 0;
+  int sibling_launches_seen[3] = {0, 0, 0};
   cudaStream_t copy_stream = nullptr;    // streaming uploads of b200reg_ndt_align_batch
   DeviceBuffer<unsigned> batch_ready;    // one "scan k has arrived" flag per registration of a batch
   unsigned batch_tag = 0;                // value the flags take for the current call
-  b200reg_engine* sibling = nullptr;  // second engine of b200reg_ndt_sweep (own stream and buffers), created on first use
+  b200reg_engine* siblings[3] = {nullptr, nullptr, nullptr};  // further engines of b200reg_ndt_sweep (own stream and buffers each)
+  int sweep_engines = 4;  // engines (host threads) the sweep pipelines over (developer switch: B200REG_SWEEP_ENGINES)
 };
 
 namespace {
@@ -184,9 +186,15 @@ int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
     return B200REG_OK;
   }
   if (g_trace) g_trace_t[1] = trace_now();
-  B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-  h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
-  B200_CUDA(cudaEventRecord(h->ev1, h->stream));  // solve_ms brackets the kernel(s) on the stream, nothing host-side
+  h->coop_lock = std::unique_lock<std::mutex>(cooperative_launch_mutex(h->device));
+  try {
+    B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+    h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
+    B200_CUDA(cudaEventRecord(h->ev1, h->stream));  // solve_ms brackets the kernel(s) on the stream, nothing host-side
+  } catch (...) {
+    h->coop_lock.unlock();
+    throw;
+  }
   if (g_trace) g_trace_t[2] = trace_now();
   h->align_pending = true;
   return B200REG_OK;
@@ -195,6 +203,12 @@ int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
 int ndt_align_end(b200reg_t h) {
   if (!h->align_pending) return B200REG_OK;
   h->align_pending = false;
+  struct Release {  // the solver kernel(s) of this align are complete (or failed) whenever this function returns
+    std::unique_lock<std::mutex>& l;
+    ~Release() {
+      if (l.owns_lock()) l.unlock();
+    }
+  } release{h->coop_lock};
   for (int rounds = 0; rounds < 4096; rounds++) {
     B200_CUDA(cudaStreamSynchronize(h->stream));
     if (h->solver.result().error == 3) h->solver.fetch_result();
@@ -322,6 +336,7 @@ int b200reg_create(int kind, int device, b200reg_t* out) {
     h->solver.init(device, h->stream);
     h->solver.timing_enabled = getenv("B200REG_TIMING") != nullptr;
     h->solver.batch_profile = getenv("B200REG_BATCH_PROFILE") != nullptr;
+    if (const char* se = getenv("B200REG_SWEEP_ENGINES")) h->sweep_engines = std::max(1, std::min(4, atoi(se)));
     h->solver.scalar_controller = getenv("B200REG_SCALAR_CTL") != nullptr;
     h->solver.plain_launch = getenv("B200REG_PLAIN_LAUNCH") != nullptr;
     h->gicp_solver.device_bfgs = getenv("B200REG_GICP_HOST_BFGS") == nullptr;  // developer switch: host-driven BFGS
@@ -346,7 +361,8 @@ int b200reg_destroy(b200reg_t h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
-  if (h->sibling) b200reg_destroy(h->sibling);
+  for (b200reg_engine* sib : h->siblings)
+    if (sib) b200reg_destroy(sib);
   if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
   cudaStream_t s = h->stream;
   delete h;
@@ -482,22 +498,20 @@ int b200reg_align(b200reg_t h, const float* guess, float* final_out) {
 int b200reg_align_batch(b200reg_t* handles, int count, const float* guesses, float* finals) {
   if (!handles || count < 0) return B200REG_ERR_ARG;
   int worst = B200REG_OK;
-  std::vector<int> rc(count, B200REG_OK);
-  for (int i = 0; i < count; i++) {  // enqueue every NDT solve on its own stream before waiting for any
+  for (int i = 0; i < count; i++) {
+    // one handle after the other: every NDT / GICP solve is a persistent cooperative kernel that owns all SMs, and two
+    // such kernels must not be in flight at once (cooperative_launch_mutex) — the entry point is a convenience loop
     b200reg_t h = handles[i];
     if (!h) return B200REG_ERR_ARG;
-    if (h->kind != B200REG_NDT) continue;
-    rc[i] = guarded(h, [&]() { return ndt_align_begin(h, guesses ? guesses + 16 * i : nullptr); });
-  }
-  for (int i = 0; i < count; i++) {
-    b200reg_t h = handles[i];
-    if (h->kind == B200REG_NDT) {
-      if (rc[i] == B200REG_OK) rc[i] = guarded(h, [&]() { return ndt_align_end(h); });
-    } else {
-      rc[i] = guarded(h, [&]() { return gicp_align(h, guesses ? guesses + 16 * i : nullptr); });
-    }
+    const float* g = guesses ? guesses + 16 * i : nullptr;
+    const int rc = guarded(h, [&]() {
+      if (h->kind != B200REG_NDT) return gicp_align(h, g);
+      int r = ndt_align_begin(h, g);
+      if (r == B200REG_OK) r = ndt_align_end(h);
+      return r;
+    });
     if (finals) row_to_col(h->final_T, finals + 16 * i);
-    if (rc[i] != B200REG_OK) worst = rc[i];
+    if (rc != B200REG_OK) worst = rc;
   }
   return worst;
 }
@@ -665,10 +679,13 @@ int b200reg_ndt_derivatives(b200reg_t h, const float* T, const double* p6, int c
     }
     float Tr[16];
     col_to_row(T, Tr);
-    B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-    h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_DERIVATIVES, Tr, p6, compute_hessian, 0);
-    B200_CUDA(cudaEventRecord(h->ev1, h->stream));
-    B200_CUDA(cudaStreamSynchronize(h->stream));
+    {
+      std::lock_guard<std::mutex> coop(cooperative_launch_mutex(h->device));
+      B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+      h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_DERIVATIVES, Tr, p6, compute_hessian, 0);
+      B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+    }
     B200_CUDA(cudaEventElapsedTime(&h->solve_ms, h->ev0, h->ev1));
     if (h->solver.result().error == 3) h->solver.fetch_result();
     const NdtResult& r = h->solver.result();
@@ -905,11 +922,24 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const s
   float ms_total = 0;
   for (int first = 0; first < count; first += per_launch) {
     const int n = std::min(per_launch, count - first);
-    B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-    h->solver.launch_batch(h->map, items.data() + first, n, h->ndt, h->batch_slots);
-    B200_CUDA(cudaEventRecord(h->ev1, h->stream));
-    if (after_launch) after_launch();
-    B200_CUDA(cudaStreamSynchronize(h->stream));
+    const double tr0 = g_trace ? trace_now() : 0;
+    double tr1 = 0, tr2 = 0;
+    {
+      std::lock_guard<std::mutex> coop(cooperative_launch_mutex(h->device));
+      B200_CUDA(cudaEventRecord(h->ev0, h->stream));
+      h->solver.launch_batch(h->map, items.data() + first, n, h->ndt, h->batch_slots);
+      B200_CUDA(cudaEventRecord(h->ev1, h->stream));
+      if (g_trace) tr1 = trace_now();
+      if (after_launch) after_launch();
+      if (g_trace) tr2 = trace_now();
+      B200_CUDA(cudaStreamSynchronize(h->stream));
+    }
+    if (g_trace) {
+      float kms = 0;
+      cudaEventElapsedTime(&kms, h->ev0, h->ev1);
+      std::fprintf(stderr, "[trace] batch of %d: job table + launch calls %.1f us, uploads issued %.1f us, wait %.1f us (kernel events %.1f us)\n", n,
+                   tr1 - tr0, tr2 - tr1, trace_now() - tr2, 1e3 * kms);
+    }
     float ms = 0;
     B200_CUDA(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     ms_total += ms;
@@ -1094,22 +1124,24 @@ extern "C" int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sou
     return B200REG_ERR_ARG;
   if (stride_bytes < 12 || (stride_bytes % 4) != 0) return B200REG_ERR_ARG;
   if (count == 0) return B200REG_OK;
-  if (!h->sibling && count > 1) {
-    b200reg_t sib = nullptr;
-    const int rc = b200reg_create(B200REG_NDT, h->device, &sib);
-    if (rc != B200REG_OK) return rc;
-    h->sibling = sib;
+  const int n_eng = std::max(1, std::min(std::min(h->sweep_engines, 4), count));
+  b200reg_t eng[4] = {h, nullptr, nullptr, nullptr};
+  for (int e = 1; e < n_eng; e++) {
+    if (!h->siblings[e - 1]) {
+      b200reg_t sib = nullptr;
+      const int rc = b200reg_create(B200REG_NDT, h->device, &sib);
+      if (rc != B200REG_OK) return rc;
+      h->siblings[e - 1] = sib;
+    }
+    eng[e] = h->siblings[e - 1];
+    eng[e]->ndt = h->ndt;  // the further engines follow the first one's parameters
+    eng[e]->min_points_per_voxel = h->min_points_per_voxel;
+    eng[e]->min_covar_eigvalue_mult = h->min_covar_eigvalue_mult;
   }
-  b200reg_t eng[2] = {h, count > 1 ? h->sibling : nullptr};
-  if (eng[1]) {  // the second engine follows the first one's parameters
-    eng[1]->ndt = h->ndt;
-    eng[1]->min_points_per_voxel = h->min_points_per_voxel;
-    eng[1]->min_covar_eigvalue_mult = h->min_covar_eigvalue_mult;
-  }
-  // Two host threads, one engine (stream + buffers) each, take the pairs from a shared counter: the upload and voxel-map
-  // build of one pair overlap the solve and fitness pass of the other, and the host-side waits of the two overlap too.
-  // Every pair is computed exactly as the sequential calls would compute it (the result does not depend on which
-  // engine served it).
+  // A few host threads, one engine (stream + buffers) each, take the pairs from a shared counter: the upload and voxel-map
+  // build of one pair overlap the solve and fitness pass of another, and the host-side launch / wait overheads of the
+  // pairs overlap too (a pair is ~25 small launches and a handful of waits: more host time than device time). Every pair
+  // is computed exactly as the sequential calls would compute it (the result does not depend on which engine served it).
   std::atomic<int> next{0};
   std::atomic<int> worst{B200REG_OK};
   auto worker = [&](b200reg_t e) {
@@ -1122,14 +1154,14 @@ extern "C" int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sou
       if (rc != B200REG_OK) worst.store(rc);
     }
   };
-  if (eng[1]) {
-    std::thread t(worker, eng[1]);
-    worker(eng[0]);
-    t.join();
-    h->other_launches += eng[1]->solver.launches + eng[1]->map.launches + eng[1]->nn.launches + eng[1]->other_launches - h->sibling_launches_seen;
-    h->sibling_launches_seen = eng[1]->solver.launches + eng[1]->map.launches + eng[1]->nn.launches + eng[1]->other_launches;
-  } else {
-    worker(eng[0]);
+  std::vector<std::thread> threads;
+  for (int e = 1; e < n_eng; e++) threads.emplace_back(worker, eng[e]);
+  worker(eng[0]);
+  for (std::thread& t : threads) t.join();
+  for (int e = 1; e < n_eng; e++) {
+    const int seen = eng[e]->solver.launches + eng[e]->map.launches + eng[e]->nn.launches + eng[e]->other_launches;
+    h->other_launches += seen - h->sibling_launches_seen[e - 1];
+    h->sibling_launches_seen[e - 1] = seen;
   }
   return worst.load();
 }

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -11,6 +12,13 @@
 #include "ndt_math.cuh"
 
 namespace b200 {
+
+// Persistent cooperative kernels (NDT solver, GICP inner loop) need every CTA of their grid resident at once and spin on
+// one another. Two of them launched from different host threads / streams of one device must never be interleaved by
+// the block scheduler (each holding part of the SMs while waiting for the rest): whoever launches one holds this
+// per-device mutex from the launch until the kernel has completed. Uploads, map builds and NN passes of other handles
+// still overlap it.
+std::mutex& cooperative_launch_mutex(int device);
 
 // ---- RAII device / pinned buffers -------------------------------------------------------------------
 template <typename T>

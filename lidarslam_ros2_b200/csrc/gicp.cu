@@ -712,10 +712,13 @@ int GicpSolver::inner_loop_device(double* x, const GicpConfig& cfg, int* inner_i
     B200_CUDA(cudaEventCreate(&ev0_));
     B200_CUDA(cudaEventCreate(&ev1_));
   }
-  B200_CUDA(cudaEventRecord(ev0_, stream_));
-  B200_CUDA(cudaLaunchCooperativeKernel((const void*)gicp_inner_kernel, dim3(n_eval + 1), dim3(GI_THREADS), args, 0, stream_));
-  B200_CUDA(cudaEventRecord(ev1_, stream_));
-  B200_CUDA(cudaStreamSynchronize(stream_));
+  {
+    std::lock_guard<std::mutex> coop(cooperative_launch_mutex(device_));
+    B200_CUDA(cudaEventRecord(ev0_, stream_));
+    B200_CUDA(cudaLaunchCooperativeKernel((const void*)gicp_inner_kernel, dim3(n_eval + 1), dim3(GI_THREADS), args, 0, stream_));
+    B200_CUDA(cudaEventRecord(ev1_, stream_));
+    B200_CUDA(cudaStreamSynchronize(stream_));
+  }
   launches += 1;
   {  // roofline accounting of the persistent inner kernel (bench.py --workload c3)
     float ms = 0;

@@ -14,6 +14,11 @@
 
 namespace b200 {
 
+std::mutex& cooperative_launch_mutex(int device) {
+  static std::mutex m[64];
+  return m[(device >= 0 && device < 64) ? device : 0];
+}
+
 // =====================================================================================================
 // rank index
 // =====================================================================================================

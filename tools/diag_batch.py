@@ -6,6 +6,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import ctypes as C
 import numpy as np
+import torch
 import lidarslam_ros2_b200 as m
 from lidarslam_ros2_b200 import _capi, synth
 K = int(sys.argv[1]) if len(sys.argv) > 1 else 20
@@ -15,10 +16,13 @@ scans = [(src + rng.normal(0, 0.003, size=src.shape)).astype(np.float32) for _ i
 g = m.NormalDistributionsTransform(); g.setResolution(2.0); g.setTransformationEpsilon(0.01); g.setInputTarget(tgt)
 L = _capi.lib()
 L.b200reg_debug_cta_eval_ns.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+dev = [torch.from_numpy(np.concatenate([x, np.ones((len(x), 1), np.float32)], axis=1)).cuda() for x in scans]
+torch.cuda.synchronize()
+ptrs, cnts = [d.data_ptr() for d in dev], [d.shape[0] for d in dev]
 for slots in (3, 2, 1):
     g.setBatchSlots(slots)
-    g.alignBatch(scans)
-    r = g.alignBatch(scans)
+    g.alignBatchDevice(ptrs, cnts)
+    r = g.alignBatchDevice(ptrs, cnts)
     st = g.stats()
     buf = np.zeros((256, 4), dtype=np.uint32)
     L.b200reg_debug_cta_eval_ns(g._h, buf.ctypes.data, 256)

@@ -11,10 +11,12 @@ timeout 600 python bench.py --steps 20 --warmup 5 > $out/bench_$tag.json 2> $out
 for s in 2 1; do
   timeout 300 python bench.py --steps 20 --warmup 5 --slots $s --no-c4 --no-cpu-baseline > $out/bench_slots${s}_$tag.json 2> $out/bench_slots${s}_$tag.err
 done
-B200REG_LIB_VARIANT=libb200reg_noskip.so timeout 300 python bench.py --steps 20 --warmup 5 --no-c4 --no-cpu-baseline > $out/bench_noskip_$tag.json 2> $out/bench_noskip_$tag.err
+for w in c2 c1; do
+  timeout 300 python bench.py --steps 20 --warmup 5 --workload $w --no-c4 > $out/bench_${w}_$tag.json 2> $out/bench_${w}_$tag.err
+done
 python - <<PY
 import json
-for f in ["bench_$tag", "bench_slots2_$tag", "bench_slots1_$tag", "bench_noskip_$tag"]:
+for f in ["bench_$tag", "bench_slots2_$tag", "bench_slots1_$tag", "bench_c2_$tag", "bench_c1_$tag"]:
     try:
         l = json.loads(open("$out/" + f + ".json").read().strip().splitlines()[-1])
         print(f, "value %.0f  e2e %.0f  pageable %.0f  single %.0f  frac %.3f  us/eval %.2f" % (l["value"], l["e2e"]["value"], l["e2e"]["pageable"]["value"], l["single_align"]["value"], l["roofline"]["frac"], l["roofline"]["us_per_evaluation"]))
@@ -23,6 +25,7 @@ for f in ["bench_$tag", "bench_slots2_$tag", "bench_slots1_$tag", "bench_noskip_
 PY
 timeout 400 python bench.py --impl reference --steps 5 --warmup 2 > $out/bench_ref_$tag.json 2> $out/bench_ref_$tag.err; tail -c 300 $out/bench_ref_$tag.json
 timeout 300 python tools/diag_c4.py 8 > $out/diag_c4_$tag.log 2>&1; tail -6 $out/diag_c4_$tag.log
+timeout 300 python tools/diag_batch.py 20 > $out/diag_batch_$tag.log 2>&1; cat $out/diag_batch_$tag.log
 timeout 600 python bench.py --workload c3 > $out/bench_c3_$tag.json 2> $out/bench_c3_$tag.err; tail -c 1200 $out/bench_c3_$tag.json; tail -3 $out/bench_c3_$tag.err
 timeout 600 python bench.py --workload c5 --frames 120 > $out/bench_c5_$tag.json 2> $out/bench_c5_$tag.err; tail -c 700 $out/bench_c5_$tag.json; tail -3 $out/bench_c5_$tag.err
 # launch list of the profile command (cold-cache, serialised: compare shares, not absolutes)
