@@ -190,13 +190,14 @@ def cpu_info() -> dict:
     return info
 
 
-def ncu_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the solver kernel, from the committed ncu --set full
-    capture (profiles/r1_ndt_solver_traffic.json, same workload; bench.py itself never runs under a profiler)."""
+def ncu_traffic(n_registrations: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the solver kernel for a launch of n_registrations, from the committed
+    ncu --set full capture of the batched launch (profiles/r2_ndt_solver_traffic.json holds the bytes per registration of
+    that capture; bench.py itself never runs under a profiler)."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_ndt_solver_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_ndt_solver_traffic.json")) as f:
             t = json.load(f)
-        return float(t["dram_bytes_read_per_launch"] + t["dram_bytes_write_per_launch"])
+        return float(t["dram_bytes_per_registration"]) * n_registrations
     except Exception:
         return None
 
@@ -296,7 +297,8 @@ def run_reference(args, rank, world):
     hardware thread it can use (the reference itself needs PCL/Eigen/FLANN and cannot be built here: kind = port)."""
     if rank != 0:
         return
-    scans, tgt, res, desc = make_workload(args.workload, 0)
+    base, tgt, res, desc = make_workload(args.workload, 0)
+    scans = step_scans(base, max(args.steps, args.warmup, 1), 0)  # the very scans the GPU arm registers, step by step
     import oracle
 
     oracle.build()
@@ -320,7 +322,7 @@ def run_reference(args, rank, world):
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 pair math / f64 reduction",
         "data": "synthetic",
-        "config": workload_config(args.workload, scans, tgt),
+        "config": workload_config(args.workload, base, tgt),
         "cpu_baseline": {"value": v, "unit": "registrations/s", "cores": nt, "kind": "port",
                          "sample": f"{args.steps} full align() calls, {nt} OpenMP threads (fastest of {cand}), "
                                    f"host has {os.cpu_count()} cpus",
@@ -539,9 +541,8 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     sweep = batch.LoopSweep(m, device=local_rank, resolution=2.0, max_iterations=100)
     dev = torch.device("cuda", local_rank)
     comm = batch.RowComm(rank, world, local_rank) if world > 1 else None  # ncclAllGather issued by libb200reg.so (b200comm.h)
-    if mine:  # warm-up: allocations and first-launch costs (two pairs, twice)
-        for _ in range(2):
-            sweep.run([data[i][0] for i in mine[:2]], [data[i][1] for i in mine[:2]], mine[:2])
+    if mine:  # warm-up: one untimed pass over this rank's pairs — every engine of the sweep reaches its final buffer sizes
+        sweep.run([data[i][0] for i in mine], [data[i][1] for i in mine], mine)
     batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev, comm=comm)  # NCCL warm-up
     launches0 = sweep.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -566,6 +567,7 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     out = {
         "metric": "loop-closure candidate registrations/sec (64 scan<->submap pairs, sharded)", "value": args.pairs / (ms_max * 1e-3),
         "unit": "registrations/s", "n_gpus": world, "pairs": args.pairs, "ms_per_pair": ms_max / args.pairs, "ms_total": ms_max,
+        "warmup": "one untimed pass over the same pairs",
         "per_rank_ms": per_rank_ms, "scaling": "strong", "collective": "ONE ncclAllGather of 20-float result rows, issued from C (b200comm_all_gather_rows), inside the timed region",
         "workload": f"c4: {args.pairs} independent NDT pairs, 32-ring scan (~56k) vs 200k-pt submap, res 2.0, max_iter 100, DIRECT7, "
                     "setInputTarget+setInputSource+align+getFitnessScore per pair from host buffers; pair i -> rank i mod N",
@@ -748,7 +750,7 @@ def main():
     # ---- timed (value): K registrations of HBM-resident scans, ONE batched launch ---------------------------------
     launches0 = ndt.stats()["kernel_launches"]
     wall0 = time.perf_counter()
-    rb, total_ms_max, per_rank_ms = timed(lambda: ndt.alignBatchDevice(ptrs[:K], counts[:K]))
+    rb, total_ms_max, per_rank_ms = timed(ndt.prepareBatchDevice(ptrs[:K], counts[:K]))
     wall = time.perf_counter() - wall0
     st = ndt.stats()
     launches = st["kernel_launches"] - launches0
@@ -757,8 +759,8 @@ def main():
     n_pts = np.array(counts[:K], dtype=np.int64)
     alg_bytes = float(np.sum(evals * (n_pts * 16 + n_pts * 7 * 8 + 224)) + np.sum(hits) * 48)
     # ---- timed (e2e): the same K registrations from HOST buffers through the public call ---------------------------
-    re, e2e_ms_max, _ = timed(lambda: ndt.alignBatch([p.numpy() for p in pinned_scans[:K]]))
-    rp, e2e_pg_ms_max, _ = timed(lambda: ndt.alignBatch(pageable_scans[:K]))
+    re, e2e_ms_max, _ = timed(ndt.prepareBatch([p.numpy() for p in pinned_scans[:K]]))
+    rp, e2e_pg_ms_max, _ = timed(ndt.prepareBatch(pageable_scans[:K]))
     clocks = sampler.stop()
 
     # ---- single_align leg: one b200reg_align per step (latency-bound: round 1's headline), L2 flushed between steps ----
@@ -815,7 +817,7 @@ def main():
             "roofline": {"bound": "hbm", "kernel": f"ndt_solver_kernel<DIRECT7> (persistent: all evaluations of {K} registrations, "
                                                    f"{args.slots} in flight)",
                          "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "peak_source": which,
-                         "traffic": ncu_traffic(), "alg_bytes_per_launch": alg_bytes,
+                         "traffic": ncu_traffic(K), "alg_bytes_per_launch": alg_bytes,
                          "launch_ms": kernel_ms, "evaluations_per_launch": n_evals,
                          "us_per_evaluation": 1e3 * kernel_ms / max(1, n_evals),
                          "hits_per_point": float(np.sum(hits)) / max(1.0, float(np.sum(evals * n_pts)))},

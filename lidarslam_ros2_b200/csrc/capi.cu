@@ -858,6 +858,13 @@ using StreamWriteValue32 = int (*)(cudaStream_t, unsigned long long, unsigned, u
 StreamWriteValue32 stream_write_value32() {
   static StreamWriteValue32 fn = []() -> StreamWriteValue32 {
     if (getenv("B200REG_NO_STREAM_MEMOPS")) return nullptr;  // developer switch: upload everything first
+    // The streaming form lets the solver kernel wait for data another stream is still delivering. Tools that serialise
+    // the device (Nsight Compute replays one kernel at a time, compute-sanitizer, CUDA_LAUNCH_BLOCKING=1) would keep that
+    // kernel spinning until its watchdog fires: under them everything is uploaded before the launch.
+    const char* blocking = getenv("CUDA_LAUNCH_BLOCKING");
+    if ((blocking && blocking[0] && blocking[0] != '0') || getenv("CUDA_INJECTION64_PATH") || getenv("NV_NSIGHT_INJECTION_PORT_BASE") ||
+        getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR") || getenv("NVTX_INJECTION64_PATH"))
+      return nullptr;
     void* lib = dlopen("libcuda.so.1", RTLD_NOW);
     if (!lib) return nullptr;
     void* p = dlsym(lib, "cuStreamWriteValue32_v2");

@@ -30,10 +30,10 @@ timeout 600 python bench.py --workload c3 > $out/bench_c3_$tag.json 2> $out/benc
 timeout 600 python bench.py --workload c5 --frames 120 > $out/bench_c5_$tag.json 2> $out/bench_c5_$tag.err; tail -c 700 $out/bench_c5_$tag.json; tail -3 $out/bench_c5_$tag.err
 # launch list of the profile command (cold-cache, serialised: compare shares, not absolutes)
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $out/launches_$tag.csv \
-  python tools/profile_step.py headline 3 8 > $out/prof_step_$tag.log 2>&1
-# one full capture of the solver kernel: the last launch = the batched one (3 single + 2 batched launches)
+  python tools/profile_step.py headline 3 20 > $out/prof_step_$tag.log 2>&1
+# one full capture of the solver kernel: launch #5 = the second HBM-resident batched launch of 20 registrations (3 single + 3 batched launches)
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_solver_kernel -s 4 -c 1 \
-  -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 8 > $out/prof_full_$tag.log 2>&1
+  -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 20 > $out/prof_full_$tag.log 2>&1
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page raw --csv > $out/ndt_solver_raw_$tag.csv 2>/dev/null
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page details --csv > $out/ndt_solver_details_$tag.csv 2>/dev/null
 ls -la $out | tail -8
