@@ -36,4 +36,5 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:ndt_
   -o $out/prof_ndt_solver_$tag -f python tools/profile_step.py headline 3 20 > $out/prof_full_$tag.log 2>&1
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page raw --csv > $out/ndt_solver_raw_$tag.csv 2>/dev/null
 ncu -i $out/prof_ndt_solver_$tag.ncu-rep --page details --csv > $out/ndt_solver_details_$tag.csv 2>/dev/null
-ls -la $out | tail -8
+bash tools/profile_kernels.sh $tag > $out/profile_kernels_$tag.log 2>&1; tail -16 $out/profile_kernels_$tag.log
+ls -la $out | tail -4
