@@ -538,6 +538,7 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     from lidarslam_ros2_b200 import batch, synth
 
     mine = batch.shard_pairs(args.pairs, rank, world)
+    prev_aff = pin_host_thread(local_rank)  # the sweep's host threads inherit the mask (cores of the GPU's NUMA node)
     sweep = batch.LoopSweep(m, device=local_rank, resolution=2.0, max_iterations=100)
     dev = torch.device("cuda", local_rank)
     comm = batch.RowComm(rank, world, local_rank) if world > 1 else None  # ncclAllGather issued by libb200reg.so (b200comm.h)
@@ -561,6 +562,8 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
         dist.all_gather(allms, t)
     per_rank_ms = [float(x.item()) for x in allms] if world > 1 else [ms]
     ms_max = max(per_rank_ms)
+    if prev_aff:
+        os.sched_setaffinity(0, prev_aff)  # the CPU leg below gets every core back
     if rank != 0:
         return None
     errs = [synth.pose_error(res["pose"][k], data[int(i)][2]) for k, i in enumerate(res["index"]) if int(i) in data]
@@ -663,13 +666,10 @@ def main():
             dist.destroy_process_group()
         return
     if args.workload == "c4":
-        prev = pin_host_thread(local_rank)
         sampler = ClockSampler(local_rank)
         sampler.start()
         c4 = c4_sweep(args, rank, local_rank, world, m, c4_data, with_cpu=False)
         clocks = sampler.stop()
-        if prev:
-            os.sched_setaffinity(0, prev)
         if rank == 0:
             c4["clocks"] = clocks
             print(json.dumps(c4), flush=True)

@@ -33,15 +33,17 @@ __global__ void __launch_bounds__(256) nn_mark_kernel(const float4* __restrict__
     int iy = nn_cell_coord(p.y, g.origin[1], g.inv_h, g.dims[1]);
     int iz = nn_cell_coord(p.z, g.origin[2], g.inv_h, g.dims[2]);
     cell = ix + g.dims[0] * (iy + g.dims[1] * iz);
-    atomicOr(&table[cell >> 5].bits, 1u << (cell & 31));
-    // tight bounding box of the 8x8x8 block of cells this point falls into (far-query pruning)
+    if (!((__ldcg(&table[cell >> 5].bits) >> (cell & 31)) & 1u)) atomicOr(&table[cell >> 5].bits, 1u << (cell & 31));
+    // tight bounding box of the 8x8x8 block of cells this point falls into (far-query pruning). ~10^2 points share a
+    // block: look before each atomic — a stale (looser) bound can only cause a redundant atomic, never a missing one
     unsigned* a = coarse + 6 * (size_t)((ix >> NN_COARSE_SHIFT) + cd0 * ((iy >> NN_COARSE_SHIFT) + cd1 * (iz >> NN_COARSE_SHIFT)));
-    atomicMin(a + 0, float_to_ordered(p.x));
-    atomicMin(a + 1, float_to_ordered(p.y));
-    atomicMin(a + 2, float_to_ordered(p.z));
-    atomicMax(a + 3, float_to_ordered(p.x));
-    atomicMax(a + 4, float_to_ordered(p.y));
-    atomicMax(a + 5, float_to_ordered(p.z));
+    const unsigned ox = float_to_ordered(p.x), oy = float_to_ordered(p.y), oz = float_to_ordered(p.z);
+    if (ox < __ldcg(a + 0)) atomicMin(a + 0, ox);
+    if (oy < __ldcg(a + 1)) atomicMin(a + 1, oy);
+    if (oz < __ldcg(a + 2)) atomicMin(a + 2, oz);
+    if (ox > __ldcg(a + 3)) atomicMax(a + 3, ox);
+    if (oy > __ldcg(a + 4)) atomicMax(a + 4, oy);
+    if (oz > __ldcg(a + 5)) atomicMax(a + 5, oz);
   }
   cell_of_point[i] = cell;
 }
@@ -166,14 +168,20 @@ __device__ __forceinline__ void nn_query_point(const NnQueryParams& P, float4 q4
   }
 }
 
+constexpr int NN_GROUP = 4;  // lanes per query in the ring phase
+
 __global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4* __restrict__ queries, size_t n, int* out_idx,
                                                   float* out_d2, unsigned* unresolved_count, int* unresolved_list) {
-  size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  const size_t i = tid / NN_GROUP;
+  const int sub = (int)(threadIdx.x & (NN_GROUP - 1));
+  // (whole groups fall out together: n queries occupy n * NN_GROUP consecutive threads, warps are never split mid-group)
+  if (i >= n) return;  // (a whole group: its NN_GROUP lanes share i)
   float qx, qy, qz;
   nn_query_point(P, queries[i], qx, qy, qz);
-  float best;
-  int best_i;
+  float best = FLT_MAX;
+  int best_i = -1;
+  bool resolved = false;
   {
     // An outlier is recognised before any cell is probed: if the query's 8x8x8 block of cells and its 26 neighbours hold no
     // point at all, nothing lies within NN_MAX_RINGS (< 8) rings — the ring search would probe 7^3 cells for nothing (a scan
@@ -194,14 +202,10 @@ __global__ void __launch_bounds__(128) nn1_kernel(NnQueryParams P, const float4*
             break;
           }
         }
-    if (!any) {
-      out_idx[i] = -1;
-      out_d2[i] = FLT_MAX;
-      unresolved_list[atomicAdd(unresolved_count, 1u)] = (int)i;
-      return;
-    }
+    // the ring walk, shared by the NN_GROUP lanes of this query (the decision above is the same in all of them)
+    if (any) resolved = nn1_search<NN_GROUP>(P.V, qx, qy, qz, P.max_d2, NN_MAX_RINGS, best, best_i);
   }
-  const bool resolved = nn1_search(P.V, qx, qy, qz, P.max_d2, NN_MAX_RINGS, best, best_i);
+  if (sub != 0) return;
   out_idx[i] = best_i;
   out_d2[i] = best;
   if (!resolved) unresolved_list[atomicAdd(unresolved_count, 1u)] = (int)i;
@@ -438,7 +442,7 @@ void nn1_query(const NnGrid& grid, const float4* queries, size_t n, const float*
   gm.unresolved.ensure(n + 1);
   gm.unresolved_count.ensure(1);
   B200_CUDA(cudaMemsetAsync(gm.unresolved_count.ptr, 0, sizeof(unsigned), s));
-  const int blocks = (int)((n + 127) / 128);
+  const int blocks = (int)((n * NN_GROUP + 127) / 128);
   nn1_kernel<<<blocks, 128, 0, s>>>(P, queries, n, d_idx, d_d2, gm.unresolved_count.ptr, gm.unresolved.ptr);
   nn1_far_kernel<<<148 * 4, 256, 0, s>>>(P, queries, gm.unresolved_count.ptr, gm.unresolved.ptr, d_idx, d_d2);
   B200_CUDA(cudaGetLastError());

@@ -41,10 +41,12 @@ __device__ __forceinline__ float nn_dist2(float qx, float qy, float qz, float4 t
   return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
 }
 
-// visits every point of the Chebyshev ring r around cell (cx, cy, cz); f(float4 point)
+// visits every point of the Chebyshev ring r around cell (cx, cy, cz); f(float4 point).
+// (sub, nsub): a query may be shared by nsub lanes — lane `sub` then takes every nsub-th cell of the ring.
 template <typename F>
-__device__ __forceinline__ void nn_visit_ring(const NnView& V, int cx, int cy, int cz, int r, F&& f) {
+__device__ __forceinline__ void nn_visit_ring(const NnView& V, int cx, int cy, int cz, int r, F&& f, int sub = 0, int nsub = 1) {
   const NnGeom& g = V.g;
+  int turn = 0;
   const int z0 = max(cz - r, 0), z1 = min(cz + r, g.dims[2] - 1);
   const int y0 = max(cy - r, 0), y1 = min(cy + r, g.dims[1] - 1);
   for (int z = z0; z <= z1; z++) {
@@ -54,6 +56,11 @@ __device__ __forceinline__ void nn_visit_ring(const NnView& V, int cx, int cy, i
       const int step = (zface || yface || r == 0) ? 1 : 2 * r;  // interior rows: only the two x faces
       for (int x = cx - r; x <= cx + r; x += step) {
         if (x < 0 || x >= g.dims[0]) continue;
+        if (nsub > 1) {
+          const int mine = turn == sub;
+          turn = (turn + 1 == nsub) ? 0 : turn + 1;
+          if (!mine) continue;
+        }
         const int cell = x + g.dims[0] * (y + g.dims[1] * z);
         const uint2 w = __ldg(reinterpret_cast<const uint2*>(V.index + (cell >> 5)));
         const unsigned bit = cell & 31;
@@ -70,6 +77,10 @@ __device__ __forceinline__ void nn_visit_ring(const NnView& V, int cx, int cy, i
 // (the caller then tests best < max_d2 itself). The ring expansion is capped at `max_rings`: a query whose
 // neighbourhood is still unresolved then (an outlier far from every target point) returns false and is finished by
 // the brute-force pass of nn_grid.cu — ring volumes grow with r^3, a linear scan of the cloud does not.
+// GROUP (1, 2 or 4) consecutive lanes share the query: each walks its share of every ring's cells and the lexicographic
+// (d2, index) minimum is combined inside the group after each ring (all lanes of the group return the same answer). The
+// ring walk is a chain of dependent loads; four lanes per query cut that chain to a quarter.
+template <int GROUP = 1>
 __device__ __forceinline__ bool nn1_search(const NnView& V, float qx, float qy, float qz, float max_d2, int max_rings,
                                            float& best, int& best_i) {
   const NnGeom& g = V.g;
@@ -83,11 +94,24 @@ __device__ __forceinline__ bool nn1_search(const NnView& V, float qx, float qy, 
     nn_visit_ring(V, cx, cy, cz, r, [&](float4 t) {
       const float d2 = nn_dist2(qx, qy, qz, t);
       const int ti = __float_as_int(t.w);
-      if (d2 < best || (d2 == best && ti < best_i)) {
+      if (d2 < best || (d2 == best && (best_i < 0 || ti < best_i))) {
         best = d2;
         best_i = ti;
       }
-    });
+    }, (int)(threadIdx.x & (GROUP - 1)), GROUP);
+    if (GROUP > 1) {
+      // only the lanes of this group take part: other groups of the warp are in other rings, or done
+      const unsigned gmask = ((1u << GROUP) - 1u) << ((threadIdx.x & 31) & ~(GROUP - 1));
+#pragma unroll
+      for (int d = 1; d < GROUP; d <<= 1) {
+        const float od = __shfl_xor_sync(gmask, best, d);
+        const int oi = __shfl_xor_sync(gmask, best_i, d);
+        if (oi >= 0 && (od < best || (od == best && (best_i < 0 || oi < best_i)))) {
+          best = od;
+          best_i = oi;
+        }
+      }
+    }
     // after ring r every unvisited point is >= r*h away from the query
     const float bound = (float)r * g.h;
     const float b2 = bound * bound * 0.99999f;

@@ -29,7 +29,7 @@ __global__ void __launch_bounds__(256) vg_mark_kernel(const float4* __restrict__
     if (cell < 0 || cell >= g.n_cells) cell = -1;
   }
   cell_of_point[i] = cell;
-  if (cell >= 0) atomicOr(&table[cell >> 5].bits, 1u << (cell & 31));
+  if (cell >= 0 && !((__ldcg(&table[cell >> 5].bits) >> (cell & 31)) & 1u)) atomicOr(&table[cell >> 5].bits, 1u << (cell & 31));
 }
 
 __global__ void __launch_bounds__(256) vg_accumulate_kernel(const float4* __restrict__ pts, size_t n,
@@ -81,7 +81,7 @@ __global__ void __launch_bounds__(256) vg2_mark_pages_kernel(const float4* __res
   cell_of_point[i] = cell;
   if (cell >= 0) {
     const int page = cell >> PAGE_SHIFT;
-    atomicOr(&l1[page >> 5].bits, 1u << (page & 31));
+    if (!((__ldcg(&l1[page >> 5].bits) >> (page & 31)) & 1u)) atomicOr(&l1[page >> 5].bits, 1u << (page & 31));
   }
 }
 
@@ -93,7 +93,8 @@ __global__ void __launch_bounds__(256) vg2_mark_cells_kernel(size_t n, const int
   if (cell < 0) return;
   const unsigned rp = rank_of(l1, cell >> PAGE_SHIFT);
   const int in_page = cell & ((1 << PAGE_SHIFT) - 1);
-  atomicOr(&l2[(size_t)rp * PAGE_WORDS + (in_page >> 5)].bits, 1u << (in_page & 31));
+  unsigned* word = &l2[(size_t)rp * PAGE_WORDS + (in_page >> 5)].bits;
+  if (!((__ldcg(word) >> (in_page & 31)) & 1u)) atomicOr(word, 1u << (in_page & 31));
 }
 
 __device__ __forceinline__ unsigned rank_of2(const RankWord* __restrict__ l1, const RankWord* __restrict__ l2, int cell) {
