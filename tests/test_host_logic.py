@@ -237,3 +237,36 @@ def test_recorded_bench_line_follows_the_contract():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < line["value"]
     assert line["gpu_launches"] >= line["steps"]
     assert line["clocks"]["sm_mhz"] and not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+
+
+def test_recorded_round2_bench_line_follows_the_contract():
+    """profiles/r2_bench_lines.jsonl, first line = `python bench.py --steps 20 --warmup 5` on a B200: every key of the bench
+    contract, a roofline fraction consistent with its own fields, an e2e leg that moved bytes, one solver launch for the K
+    steps, and the loop-closure sweep object."""
+    import json
+
+    with open(os.path.join(ROOT, "profiles", "r2_bench_lines.jsonl")) as f:
+        line = json.loads(f.readline())
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in line, key
+    assert line["higher_is_better"] is True and line["vs_baseline"] is None and line["n_gpus"] == 1
+    assert abs(line["value"] - line["n_gpus"] * 1e3 / line["ms_per_step"]) < 1e-6 * line["value"]
+    r = line["roofline"]
+    assert r["bound"] == "hbm" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert abs(r["achieved"] - r["alg_bytes_per_launch"] / (r["launch_ms"] * 1e-3) / 1e9) < 1e-6 * r["achieved"]
+    assert r["frac"] >= 0.40  # north_star: the fused derivative kernel at >= 40 % of the HBM roofline
+    assert line["gpu_launches"] == 1 and line["details"]["batch_bitwise_equals_single_align"] is True
+    e = line["e2e"]
+    assert e["h2d_bytes_per_step"] > 1_000_000 and e["d2h_bytes_per_step"] > 0 and e["value"] > 0 and e["pageable"]["value"] > 0
+    assert set(line["config"]) >= {"workload", "n_source", "n_target", "l2"}
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    c = line["cpu_baseline"]
+    assert c["kind"] == "port" and c["value"] > 0 and line["e2e"]["value"] / c["value"] >= 50  # north_star: >= 50x
+    assert c["pose_parity_max"]["dt_m"] < 1e-3 and c["pose_parity_max"]["dr_rad"] < 1e-3
+    c4 = line["c4"]
+    assert c4["pairs"] == 64 and c4["converged"] == 64 and "ncclAllGather" in c4["collective"]
+    # the reference arm of the same round prints the same config keys
+    with open(os.path.join(ROOT, "profiles", "r2_bench_lines.jsonl")) as f:
+        ref = [json.loads(x) for x in f][1]
+    assert ref["impl"] == "reference" and ref["config"] == line["config"]
