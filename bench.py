@@ -212,6 +212,25 @@ def hbm_peak():
     return 6650.0, "fallback"
 
 
+def synchronized_start(world: int, device):
+    """Barrier, then a common wall-clock deadline: the ranks of ONE node share CLOCK_MONOTONIC, so rank 0 announces
+    'now + 3 ms' and every rank spins until then — the start skew of the timed region drops from the barrier's exit skew
+    (tens of microseconds, paid again as waiting time inside the closing all-gather) to about a microsecond."""
+    import torch
+    import torch.distributed as dist
+
+    if world <= 1:
+        torch.cuda.synchronize()
+        return
+    dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.monotonic() + 0.003], dtype=torch.float64, device=device)
+    dist.broadcast(t, src=0)
+    deadline = float(t.item())
+    while time.monotonic() < deadline:
+        pass
+
+
 def host_threads() -> int:
     """Hardware threads the CPU legs may use (torchrun exports OMP_NUM_THREADS=1, which is not a property of the box)."""
     try:
@@ -547,9 +566,7 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev, comm=comm)  # NCCL warm-up
     launches0 = sweep.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
+    synchronized_start(world, dev)
     e0.record()
     rows = sweep.run([data[i][0] for i in mine], [data[i][1] for i in mine], mine)
     res = batch.gather_rows(rows, args.pairs, rank, world, device=dev, comm=comm)  # the one collective: ncclAllGather of the rows
@@ -722,7 +739,7 @@ def main():
         """barrier + sync, CUDA events around fn() (synchronous engine call) + the pose all-gather, sync; max over ranks"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush()
-        barrier()
+        synchronized_start(world, torch.device("cuda", local_rank))
         e0.record()
         r = fn()
         poses_pin.numpy()[:] = r["pose"].reshape(-1, 16)[:K]

@@ -40,6 +40,7 @@ struct b200reg_engine {
   GicpConfig gicp;
 
   DeviceBuffer<float4> d_target, d_source, d_aligned;
+  const float4* src_view = nullptr;  // the source cloud the solves read: d_source, or a caller-owned device buffer (b200reg_adopt_source_device)
   PinnedBuffer<float4> staging;
   CloudUploader uploader;
   size_t n_target = 0, n_source = 0;
@@ -189,7 +190,7 @@ int ndt_align_begin(b200reg_t h, const float* guess_colmajor) {
   h->coop_lock = std::unique_lock<std::mutex>(cooperative_launch_mutex(h->device));
   try {
     B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-    h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
+    h->solver.launch(h->map, h->src_view, h->n_source, h->ndt, NDT_MODE_ALIGN, T, nullptr, 1, 0);
     B200_CUDA(cudaEventRecord(h->ev1, h->stream));  // solve_ms brackets the kernel(s) on the stream, nothing host-side
   } catch (...) {
     h->coop_lock.unlock();
@@ -216,13 +217,13 @@ int ndt_align_end(b200reg_t h) {
     if (r.error == 100) {
       // the More-Thuente loop ran (only when step_max <= step_min): f64 radius Hessian (K2), then resume
       h->scratch_d.ensure(64);
-      ndt_hessian_radius(h->map, h->d_source.ptr, h->n_source, h->ndt, h->solver.control_T(), h->solver.state_jd(),
+      ndt_hessian_radius(h->map, h->src_view, h->n_source, h->ndt, h->solver.control_T(), h->solver.state_jd(),
                          h->solver.state_hd(), h->scratch_d.ptr, h->stream);
       ndt_hessian_into_state(h->scratch_d.ptr, h->solver.work(), h->stream);
       h->other_launches += 2;
       float dummyT[16];
       set_identity(dummyT);
-      h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_ALIGN, dummyT, nullptr, 1, 1);
+      h->solver.launch(h->map, h->src_view, h->n_source, h->ndt, NDT_MODE_ALIGN, dummyT, nullptr, 1, 1);
       B200_CUDA(cudaEventRecord(h->ev1, h->stream));
       continue;
     }
@@ -260,7 +261,7 @@ int gicp_align(b200reg_t h, const float* guess_colmajor) {
   else set_identity(T);
   h->gicp.corr_dist = h->corr_dist;
   B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-  GicpOutcome out = h->gicp_solver.align(h->nn, h->d_target.ptr, h->n_target, h->d_source.ptr, h->n_source, h->gicp, T,
+  GicpOutcome out = h->gicp_solver.align(h->nn, h->d_target.ptr, h->n_target, h->src_view, h->n_source, h->gicp, T,
                                          h->stream);
   B200_CUDA(cudaEventRecord(h->ev1, h->stream));
   B200_CUDA(cudaEventSynchronize(h->ev1));
@@ -308,6 +309,7 @@ int set_cloud(b200reg_t h, bool target, const float* base, size_t n, size_t stri
   } else {
     h->n_source = n;
     h->have_source = true;
+    h->src_view = h->d_source.ptr;
     h->gicp_solver.invalidate_source();
   }
   return B200REG_OK;
@@ -479,6 +481,16 @@ int b200reg_set_input_target_device(b200reg_t h, const void* dev, size_t n) {
 int b200reg_set_input_source_device(b200reg_t h, const void* dev, size_t n) {
   return guarded(h, [&]() { return set_cloud(h, false, nullptr, n, 16, dev); });
 }
+// Library-internal (not in include/b200reg.h): the frontend session hands over its voxel-filtered scan WITHOUT a copy — the
+// buffer stays valid and untouched until the session's next frame, and the session has synchronised its own stream.
+int b200reg_adopt_source_device(b200reg_t h, const void* dev, size_t n) {
+  if (!h || !dev || n == 0) return B200REG_ERR_ARG;
+  h->src_view = static_cast<const float4*>(dev);
+  h->n_source = n;
+  h->have_source = true;
+  h->gicp_solver.invalidate_source();
+  return B200REG_OK;
+}
 
 // ---- align -----------------------------------------------------------------------------------------------
 int b200reg_align(b200reg_t h, const float* guess, float* final_out) {
@@ -543,7 +555,7 @@ int b200reg_get_fitness_score(b200reg_t h, double max_range, double* out) {
     h->nn_d2.ensure(h->n_source);
     // points farther than max_range do not contribute: let the search stop there
     const float bound = (max_range < 3.0e38) ? (float)max_range * 1.0001f + 1e-30f : 3.402823466e+38f;
-    nn1_query(h->nn, h->d_source.ptr, h->n_source, h->final_T, h->nn_idx.ptr, h->nn_d2.ptr, h->stream, bound);
+    nn1_query(h->nn, h->src_view, h->n_source, h->final_T, h->nn_idx.ptr, h->nn_d2.ptr, h->stream, bound);
     double sum = 0;
     long long cnt = 0;
     fitness_reduce(h->nn_d2.ptr, h->nn_idx.ptr, h->n_source, max_range, h->scratch_d.ptr, &sum, &cnt, h->stream);
@@ -559,7 +571,7 @@ int b200reg_get_aligned(b200reg_t h, float* out, size_t stride_bytes) {
     if (!h->have_source) return fail(h, B200REG_ERR_NO_SOURCE, "no input source");
     h->d_aligned.ensure(h->n_source);
     B200_CUDA(cudaMemcpyAsync(h->scratch_f.ptr, h->final_T, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    transform_cloud_device(h->d_source.ptr, h->n_source, h->d_aligned.ptr, h->scratch_f.ptr, h->stream);
+    transform_cloud_device(h->src_view, h->n_source, h->d_aligned.ptr, h->scratch_f.ptr, h->stream);
     h->other_launches += 1;
     h->staging.ensure(h->n_source);
     B200_CUDA(cudaMemcpyAsync(h->staging.ptr, h->d_aligned.ptr, h->n_source * sizeof(float4), cudaMemcpyDeviceToHost,
@@ -682,7 +694,7 @@ int b200reg_ndt_derivatives(b200reg_t h, const float* T, const double* p6, int c
     {
       std::lock_guard<std::mutex> coop(cooperative_launch_mutex(h->device));
       B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-      h->solver.launch(h->map, h->d_source.ptr, h->n_source, h->ndt, NDT_MODE_DERIVATIVES, Tr, p6, compute_hessian, 0);
+      h->solver.launch(h->map, h->src_view, h->n_source, h->ndt, NDT_MODE_DERIVATIVES, Tr, p6, compute_hessian, 0);
       B200_CUDA(cudaEventRecord(h->ev1, h->stream));
       B200_CUDA(cudaStreamSynchronize(h->stream));
     }
@@ -719,7 +731,7 @@ int b200reg_ndt_hessian_radius(b200reg_t h, const float* T, const double* p6, do
     h->scratch_d.ensure(128);
     B200_CUDA(cudaMemcpyAsync(h->scratch_d.ptr + 32, tabs, sizeof(tabs), cudaMemcpyHostToDevice, h->stream));
     B200_CUDA(cudaMemcpyAsync(h->scratch_f.ptr, Tr, 12 * sizeof(float), cudaMemcpyHostToDevice, h->stream));
-    ndt_hessian_radius(h->map, h->d_source.ptr, h->n_source, h->ndt, h->scratch_f.ptr, h->scratch_d.ptr + 32,
+    ndt_hessian_radius(h->map, h->src_view, h->n_source, h->ndt, h->scratch_f.ptr, h->scratch_d.ptr + 32,
                        h->scratch_d.ptr + 56, h->scratch_d.ptr, h->stream);
     h->other_launches += 1;
     double up[21];
@@ -906,6 +918,7 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const s
     for (int k = 0; k < count; k++) {
       h->d_source.ensure(items[k].n_src);
       B200_CUDA(cudaMemcpyAsync(h->d_source.ptr, items[k].src, items[k].n_src * sizeof(float4), cudaMemcpyDeviceToDevice, h->stream));
+      h->src_view = h->d_source.ptr;
       h->n_source = items[k].n_src;
       h->have_source = true;
       float Tc[16];
@@ -1112,7 +1125,7 @@ int sweep_one(b200reg_t e, const float* src, size_t n_src, const float* tgt, siz
       e->nn_idx.ensure(e->n_source);
       e->nn_d2.ensure(e->n_source);
       const float bound = (max_range < 3.0e38) ? (float)max_range * 1.0001f + 1e-30f : 3.402823466e+38f;
-      nn1_query(e->nn, e->d_source.ptr, e->n_source, e->final_T, e->nn_idx.ptr, e->nn_d2.ptr, e->stream, bound);
+      nn1_query(e->nn, e->src_view, e->n_source, e->final_T, e->nn_idx.ptr, e->nn_d2.ptr, e->stream, bound);
       double sum = 0;
       long long cnt = 0;
       fitness_reduce(e->nn_d2.ptr, e->nn_idx.ptr, e->n_source, max_range, e->scratch_d.ptr, &sum, &cnt, e->stream);

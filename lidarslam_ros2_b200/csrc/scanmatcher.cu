@@ -113,6 +113,8 @@ struct Submap {
 
 using namespace b200;
 
+extern "C" int b200reg_adopt_source_device(b200reg_t h, const void* dev, size_t n);  // capi.cu (library-internal)
+
 struct b200sm_session {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -130,6 +132,8 @@ struct b200sm_session {
   CloudUploader uploader;
   DeviceBuffer<unsigned> counter;
   VoxelGridFilter vg_input, vg_map, vg_target;
+  Bounds scan_bounds{};            // min/max of d_scan when it is the uploaded cloud itself (no de-skew, no range filter)
+  bool scan_bounds_valid = false;
   size_t n_filtered = 0;
   const float4* d_filtered = nullptr;  // VoxelGrid(vg_size_for_input) of the scan — the scan itself when the grid would overflow
   SubmapArena arena;
@@ -217,12 +221,16 @@ void matrix_to_quat_d(const double* R /* row-major 9 */, double* q /* x y z w */
 
 void upload_frame(b200sm_t s, const float* points, size_t n, size_t stride, long intensity_off) {
   s->upload.ensure(n);
-  s->uploader.upload(points, n, stride, intensity_off, 0.0f, s->upload.ptr, s->stream);  // one H2D copy per frame
+  // one H2D copy per frame; the unpack pass also measures the scan's min/max (both VoxelGrids of the frame are sized from it)
+  s->uploader.upload_with_bounds(points, n, stride, intensity_off, 0.0f, s->upload.ptr, s->stream);
   s->launches += 1;
   s->d_scan = s->upload.ptr;
   s->n_scan = n;
+  s->scan_bounds_valid = false;
+  bool deskewed = false;
   if (s->deskew_armed && n > 0) {  // cloud_callback: adjustDistortion before the range filter (sm.cpp:205-209)
     s->deskew_armed = false;
+    deskewed = true;
     const char* b = reinterpret_cast<const char*>(points);
     const int before = s->imu.launches;
     s->imu.adjust_distortion(s->upload.ptr, n, reinterpret_cast<const float*>(b), reinterpret_cast<const float*>(b + (n - 1) * stride),
@@ -242,13 +250,18 @@ void upload_frame(b200sm_t s, const float* points, size_t n, size_t stride, long
     s->d_scan = s->scan.ptr;
     s->n_scan = kept;
     s->launches += 1;
+  } else if (!deskewed) {  // the uploaded cloud IS the scan: its bounds are those measured during the upload
+    B200_CUDA(cudaStreamSynchronize(s->stream));
+    s->scan_bounds = s->uploader.finish_bounds();
+    s->scan_bounds_valid = true;
   }
 }
 
 // VoxelGrid on the device; a grid overflow returns the input unchanged like PCL
-const float4* filter_on_device(b200sm_t s, VoxelGridFilter& F, const float4* d_in, size_t n, float leaf, size_t* m) {
+const float4* filter_on_device(b200sm_t s, VoxelGridFilter& F, const float4* d_in, size_t n, float leaf, size_t* m,
+                               const Bounds* known_bounds = nullptr) {
   const int before = F.launches;
-  long long cnt = F.filter_device(d_in, n, leaf, s->stream);
+  long long cnt = F.filter_device(d_in, n, leaf, s->stream, known_bounds);
   s->launches += F.launches - before;
   if (cnt < 0) {
     *m = n;
@@ -260,12 +273,14 @@ const float4* filter_on_device(b200sm_t s, VoxelGridFilter& F, const float4* d_i
 
 int set_source_from_scan(b200sm_t s, b200reg_t reg) {
   size_t m = 0;
-  const float4* f = filter_on_device(s, s->vg_input, s->d_scan, s->n_scan, s->vg_size_for_input, &m);
+  const float4* f = filter_on_device(s, s->vg_input, s->d_scan, s->n_scan, s->vg_size_for_input, &m,
+                                     s->scan_bounds_valid ? &s->scan_bounds : nullptr);
   s->n_filtered = m;
   s->d_filtered = f;
   if (m == 0) return sm_fail(s, B200REG_ERR_ARG, "scan is empty after filtering");
-  B200_CUDA(cudaStreamSynchronize(s->stream));  // the engine copies on its own stream
-  const int rc = b200reg_set_input_source_device(reg, f, m);
+  // (the filter's read-back of the point count has synchronised this stream; the filtered scan lives in this session until
+  // the next frame, so the engine reads it in place: no copy, no second synchronisation)
+  const int rc = b200reg_adopt_source_device(reg, f, m);
   if (rc != B200REG_OK) s->err = std::string("setInputSource: ") + b200reg_last_error(reg);
   return rc;
 }
@@ -274,7 +289,8 @@ int set_source_from_scan(b200sm_t s, b200reg_t reg) {
 int update_map(b200sm_t s, const float* final_T, const double* position, const double* quat) {
   if (s->n_scan == 0) return sm_fail(s, B200REG_ERR_NO_SOURCE, "update_map: no scan");
   size_t m = 0;
-  const float4* filtered = filter_on_device(s, s->vg_map, s->d_scan, s->n_scan, s->vg_size_for_map, &m);
+  const float4* filtered = filter_on_device(s, s->vg_map, s->d_scan, s->n_scan, s->vg_size_for_map, &m,
+                                            s->scan_bounds_valid ? &s->scan_bounds : nullptr);
   // targeted_cloud_ = T(filtered) + the last num_targeted_cloud-1 submaps, newest first, each through its pose (double)
   const int n_sub = (int)s->submaps.size();
   size_t total = m;
