@@ -78,7 +78,7 @@ class ClockSampler:
     LIB = os.path.join(ROOT, "tools", "libclocksampler.so")
 
     def __init__(self, gpu_index: int, period_us: int = 250):
-        self.gpu, self.period_us = gpu_index, period_us
+        self.gpu, self.period_us = gpu_index, int(os.environ.get("BENCH_CLK_PERIOD_US", period_us))
         self.native = None
         self.nvml = None
         self.sm, self.mask, self.mx = [], 0, None
@@ -545,7 +545,7 @@ def _c4_pair(arg):
     return src, tgt, T_rel
 
 
-def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
+def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool, comm=None):
     """BASELINE config 4 inside the default line: the loop-closure candidate sweep — args.pairs independent scan<->submap
     registrations (32-ring scan ~56k pts vs 200k-pt local map, NDT res 2.0, max_iter 100 as graph_based_slam_component.
     cpp:66), the SAME pairs at every N, pair i -> rank i mod N, per pair the node's sequence setInputTarget +
@@ -560,10 +560,12 @@ def c4_sweep(args, rank, local_rank, world, m, data, with_cpu: bool):
     prev_aff = pin_host_thread(local_rank)  # the sweep's host threads inherit the mask (cores of the GPU's NUMA node)
     sweep = batch.LoopSweep(m, device=local_rank, resolution=2.0, max_iterations=100)
     dev = torch.device("cuda", local_rank)
-    comm = batch.RowComm(rank, world, local_rank) if world > 1 else None  # ncclAllGather issued by libb200reg.so (b200comm.h)
+    if comm is None and world > 1:
+        comm = batch.RowComm(rank, world, local_rank)  # ncclAllGather issued by libb200reg.so (b200comm.h)
     if mine:  # warm-up: one untimed pass over this rank's pairs — every engine of the sweep reaches its final buffer sizes
         sweep.run([data[i][0] for i in mine], [data[i][1] for i in mine], mine)
-    batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev, comm=comm)  # NCCL warm-up
+    for _ in range(8):  # NCCL warm-up (its channels come up lazily over the first few calls)
+        batch.gather_rows(np.full((len(mine), batch.ROW), -1.0, dtype=np.float32), args.pairs, rank, world, device=dev, comm=comm)
     launches0 = sweep.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     synchronized_start(world, dev)
@@ -719,9 +721,8 @@ def main():
     pinned_scans = [torch.from_numpy(np.ascontiguousarray(x)).pin_memory() for x in scans]
     pageable_scans = [np.ascontiguousarray(x).copy() for x in scans]
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
-    poses_dev = torch.zeros((K, 16), dtype=torch.float32, device="cuda")
-    poses_pin = torch.zeros((K, 16), dtype=torch.float32).pin_memory()
-    gathered = torch.empty((world * K, 16), dtype=torch.float32, device="cuda")
+    from lidarslam_ros2_b200 import batch as _b
+    comm = _b.RowComm(rank, world, local_rank) if world > 1 else None  # the collective is issued by libb200reg.so (b200comm.h)
     ptrs = [d.data_ptr() for d in dev_scans]
     counts = [int(d.shape[0]) for d in dev_scans]
 
@@ -741,20 +742,23 @@ def main():
         flush()
         synchronized_start(world, torch.device("cuda", local_rank))
         e0.record()
+        w0 = time.perf_counter()
         r = fn()
-        poses_pin.numpy()[:] = r["pose"].reshape(-1, 16)[:K]
-        poses_dev.copy_(poses_pin, non_blocking=True)
-        if world > 1:  # the one collective of the replicated sweep: all-gather of the 4x4 poses (NCCL over NVLink)
-            dist.all_gather_into_tensor(gathered, poses_dev)
+        w1 = time.perf_counter()
+        if world > 1:  # the one collective of the replicated sweep: ncclAllGather of the 4x4 poses (NCCL over NVLink), from C
+            comm.all_gather_rows(r["pose"].reshape(-1, 16)[:K])
         e1.record()
+        e1.synchronize()
+        w2 = time.perf_counter()
         barrier()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, 1e3 * (w1 - w0), 1e3 * (w2 - w1)], dtype=torch.float64, device="cuda")
         allt = [t.clone() for _ in range(world)]
         if world > 1:
             dist.all_gather(allt, t)
-        per = [float(x.item()) for x in allt] if world > 1 else [ms]
-        return r, max(per), per
+        rows = [[float(v) for v in x.tolist()] for x in allt] if world > 1 else [[float(v) for v in t.tolist()]]
+        per = [{"step_ms_sum": x[0], "engine_call_ms": x[1], "pose_gather_ms": x[2]} for x in rows]
+        return r, max(x[0] for x in rows), per
 
     # ---- warm-up: W single aligns, one batch of W from HBM, one from host --------------------------------------
     for k in range(W):
@@ -764,7 +768,8 @@ def main():
     ndt.alignBatch([p.numpy() for p in pinned_scans[:K]])  # full size: the staging / device buffers reach their final size here
     ndt.alignBatch(pageable_scans[:K])
     if world > 1:
-        dist.all_gather_into_tensor(gathered, poses_dev)
+        for _ in range(8):  # NCCL sets its channels up lazily over the first few calls (measured: 195, 123, 118, 42, 38 us ...)
+            comm.all_gather_rows(np.zeros((K, 16), dtype=np.float32))
 
     prev_aff = pin_host_thread(local_rank)
     sampler = ClockSampler(local_rank)
@@ -806,7 +811,7 @@ def main():
     # ---- the loop-closure sweep (BASELINE config 4) rides in the same line ---------------------------------------
     c4 = None
     if c4_data is not None:
-        c4 = c4_sweep(args, rank, local_rank, world, m, c4_data, with_cpu=not args.no_cpu_baseline)
+        c4 = c4_sweep(args, rank, local_rank, world, m, c4_data, with_cpu=not args.no_cpu_baseline, comm=comm)
 
     if rank == 0:
         peak, which = hbm_peak()
@@ -821,7 +826,7 @@ def main():
                         "index_in_smem": st["index_in_smem"], "slots_in_flight": args.slots,
                         "step": "the K steps are K independent registrations (own scan buffer each) issued as ONE "
                                 f"b200reg_ndt_align_batch_device call = one persistent launch, {args.slots} registrations in flight",
-                        "parallelism": f"replicas x{world} + 1 NCCL all-gather of the poses inside the timed region" if world > 1 else "1 GPU",
+                        "parallelism": f"replicas x{world} + ONE ncclAllGather of the poses (b200comm_all_gather_rows) inside the timed region" if world > 1 else "1 GPU",
                         "batch_bitwise_equals_single_align": bool(bitwise),
                         "mean_iterations": float(rb["iterations"].mean()), "converged": int(rb["converged"].sum())},
             "e2e": {"value": world * K / (e2e_ms_max * 1e-3), "unit": "registrations/s",
@@ -834,7 +839,7 @@ def main():
                              "note": "one b200reg_align per step (setInputSourceDevice + align, L2 flushed between steps): the "
                                      "latency of ONE registration; rank 0's own time"},
             "gpu_launches": int(launches),
-            "per_rank": [{"step_ms_sum": x} for x in per_rank_ms],
+            "per_rank": per_rank_ms,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": f"ndt_solver_kernel<DIRECT7> (persistent: all evaluations of {K} registrations, "
                                                    f"{args.slots} in flight)",
