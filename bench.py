@@ -69,7 +69,8 @@ def step_scans(base, n_steps: int, rank: int):
 
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe) by a NATIVE thread
-    (tools/clock_sampler.c: NVML through dlopen, one sample every 250 us plus one before and one after the region).
+    (tools/clock_sampler.c: NVML through dlopen; one sample before the region, one 400 us into it — while the batched kernel runs
+    and the host only waits — then at a backing-off period, one after the region: NVML queries contend with CUDA / NCCL calls).
     Round 1 polled NVML from a Python thread: eight such pollers fighting eight launch loops for their GILs cost one
     rank 6.5 ms inside a 3.8 ms timed region on the 8-GPU box. If the native sampler is unavailable the clocks are
     read once before and once after the region through nvidia_ml_py (never from a polling Python thread)."""
@@ -77,11 +78,12 @@ class ClockSampler:
     REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
     LIB = os.path.join(ROOT, "tools", "libclocksampler.so")
 
-    def __init__(self, gpu_index: int, period_us: int = 250):
+    def __init__(self, gpu_index: int, period_us: int = 400):
         self.gpu, self.period_us = gpu_index, int(os.environ.get("BENCH_CLK_PERIOD_US", period_us))
         self.native = None
         self.nvml = None
         self.sm, self.mask, self.mx = [], 0, None
+        self.acc_sm, self.acc_mask, self.acc_mx, self.used_native = [], 0, None, False
 
     def _uuid(self):
         try:
@@ -116,6 +118,7 @@ class ClockSampler:
             L = C.CDLL(self.LIB)
             L.b200clk_start.argtypes = [C.c_char_p, C.c_int, C.c_int]
             L.b200clk_stop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+            L.b200clk_arm.restype = None
             u = self._uuid()
             if L.b200clk_start(u.encode() if u else None, self.gpu, self.period_us) == 0:
                 self.native = L
@@ -124,7 +127,12 @@ class ClockSampler:
             self.native = None
         self._one_shot()
 
-    def stop(self) -> dict:
+    def arm(self):
+        if self.native is not None:
+            self.native.b200clk_arm()
+
+    def pause(self):
+        """End of one timed region: collect its samples; start() may be called again for the next region."""
         import ctypes as C
         if self.native is not None:
             cap = 65536
@@ -132,15 +140,25 @@ class ClockSampler:
             rs = (C.c_ulonglong * cap)()
             mx = C.c_uint(0)
             n = self.native.b200clk_stop(sm, rs, cap, C.byref(mx))
-            vals = [float(sm[i]) for i in range(n)]
-            mask = 0
+            self.acc_sm += [float(sm[i]) for i in range(n)]
             for i in range(n):
-                mask |= int(rs[i])
+                self.acc_mask |= int(rs[i])
+            self.acc_mx = float(mx.value) or self.acc_mx
+            self.native = None
+            self.used_native = True
+        else:
+            self._one_shot()
+
+    def stop(self) -> dict:
+        if self.native is not None or not getattr(self, "used_native", False):
+            self.pause()
+        if getattr(self, "used_native", False):
+            vals, mask, n = self.acc_sm, self.acc_mask, len(self.acc_sm)
+            mx = type("M", (), {"value": self.acc_mx or 0.0})()
             return {"sm_mhz": float(np.median(vals)) if vals else None, "sm_max_mhz": float(mx.value) or None, "samples": n,
                     "reasons": sorted(name for bit, name in self.REASONS if mask & bit),
-                    "source": f"nvml from a native thread inside the timed region: every {self.period_us} us for the first 16 samples, "
-                              "then 2 ms, then 20 ms (+1 sample before, +1 after)"}
-        self._one_shot()
+                    "source": f"nvml from a native thread: one sample before the timed region, one {self.period_us} us into it, then every "
+                              "4 / 8 / 16 / 20 ms, one after it"}
         return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
                 "reasons": sorted(name for bit, name in self.REASONS if self.mask & bit),
                 "source": "nvml, one sample before and one after the timed region (native sampler unavailable)"}
@@ -224,6 +242,8 @@ def synchronized_start(world: int, device):
         return
     dist.barrier()
     torch.cuda.synchronize()
+    if os.environ.get("BENCH_SYNC_START") == "0":  # developer switch: barrier only
+        return
     t = torch.tensor([time.monotonic() + 0.003], dtype=torch.float64, device=device)
     dist.broadcast(t, src=0)
     deadline = float(t.item())
@@ -373,6 +393,7 @@ def run_c5(args, rank, local_rank, world, m):
         warm.receiveCloud(scan)
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.arm()
     passes = []
     for rep in range(3):  # three passes over the stream, each on a fresh session; the MEDIAN pass is reported
         sm = ScanMatcher(device=local_rank, **kw)
@@ -463,6 +484,7 @@ def run_c3(args, rank, local_rank, world, m):
     g.align()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    sampler.arm()
     launches0 = g.stats()["kernel_launches"]
     e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     poses, inner_ms, pair_evals, its, evs = [], 0.0, 0.0, [], []
@@ -687,6 +709,7 @@ def main():
     if args.workload == "c4":
         sampler = ClockSampler(local_rank)
         sampler.start()
+        sampler.arm()
         c4 = c4_sweep(args, rank, local_rank, world, m, c4_data, with_cpu=False)
         clocks = sampler.stop()
         if rank == 0:
@@ -723,6 +746,15 @@ def main():
     flush_buf = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
     from lidarslam_ros2_b200 import batch as _b
     comm = _b.RowComm(rank, world, local_rank) if world > 1 else None  # the collective is issued by libb200reg.so (b200comm.h)
+    # N > 1: the poses of the sharded batch are exchanged by the solver kernel itself (pose board: peer-memory stores over
+    # NVLink as each registration converges, include/b200comm.h); BENCH_POSE_EXCHANGE=nccl keeps round 1's form — one
+    # ncclAllGather behind the batch call — and is also the fallback when the boards cannot be mapped (said in the line).
+    board, board_why = None, None
+    if world > 1 and os.environ.get("BENCH_POSE_EXCHANGE", "board") == "board":
+        try:
+            board = comm.create_board(max(K, 1))
+        except Exception as e:  # collective: fails on every rank or on none
+            board_why = str(e)
     ptrs = [d.data_ptr() for d in dev_scans]
     counts = [int(d.shape[0]) for d in dev_scans]
 
@@ -740,24 +772,33 @@ def main():
         """barrier + sync, CUDA events around fn() (synchronous engine call) + the pose all-gather, sync; max over ranks"""
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         flush()
+        sampler.start()  # one sample now (before the region); the sampling thread parks until arm()
         synchronized_start(world, torch.device("cuda", local_rank))
+        sampler.arm()  # the next sample comes 400 us from here
         e0.record()
         w0 = time.perf_counter()
         r = fn()
         w1 = time.perf_counter()
-        if world > 1:  # the one collective of the replicated sweep: ncclAllGather of the 4x4 poses (NCCL over NVLink), from C
-            comm.all_gather_rows(r["pose"].reshape(-1, 16)[:K])
+        if board is not None:  # all ranks' poses arrived with the call (stored by the peers' kernels): r["gathered"]
+            assert r["gathered"].shape[0] == world
+        elif world > 1:  # fallback: ncclAllGather of the 4x4 poses behind the call, from C
+            r["gathered"] = comm.all_gather_rows(r["pose"].reshape(-1, 16)[:K]).reshape(world, -1, 4, 4)
+        w1b = time.perf_counter()
         e1.record()
+        w1c = time.perf_counter()
         e1.synchronize()
         w2 = time.perf_counter()
+        sampler.pause()
         barrier()
         ms = e0.elapsed_time(e1)
-        t = torch.tensor([ms, 1e3 * (w1 - w0), 1e3 * (w2 - w1)], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms, 1e3 * (w1 - w0), 1e3 * (w2 - w1), 1e3 * (w1b - w1), 1e3 * (w1c - w1b), 1e3 * (w2 - w1c)], dtype=torch.float64,
+                         device="cuda")
         allt = [t.clone() for _ in range(world)]
         if world > 1:
             dist.all_gather(allt, t)
         rows = [[float(v) for v in x.tolist()] for x in allt] if world > 1 else [[float(v) for v in t.tolist()]]
-        per = [{"step_ms_sum": x[0], "engine_call_ms": x[1], "pose_gather_ms": x[2]} for x in rows]
+        per = [{"step_ms_sum": x[0], "engine_call_ms": x[1], "pose_gather_ms": x[2],
+                "tail_ms": {"poses_out": x[3], "event_record": x[4], "event_sync": x[5]}} for x in rows]
         return r, max(x[0] for x in rows), per
 
     # ---- warm-up: W single aligns, one batch of W from HBM, one from host --------------------------------------
@@ -767,13 +808,21 @@ def main():
     ndt.alignBatchDevice(ptrs[:W], counts[:W])
     ndt.alignBatch([p.numpy() for p in pinned_scans[:K]])  # full size: the staging / device buffers reach their final size here
     ndt.alignBatch(pageable_scans[:K])
+    if board is not None:
+        ndt.attachPoseBoard(board)
+        for _ in range(2):
+            ndt.alignBatchDevice(ptrs[:K], counts[:K])
+            ndt.alignBatch([p.numpy() for p in pinned_scans[:K]])
+            ndt.gatheredPoses()
+        wb = ndt.prepareBatchDevice(ptrs[:W], counts[:W])
+        for _ in range(3):
+            wb()
     if world > 1:
         for _ in range(8):  # NCCL sets its channels up lazily over the first few calls (measured: 195, 123, 118, 42, 38 us ...)
             comm.all_gather_rows(np.zeros((K, 16), dtype=np.float32))
 
     prev_aff = pin_host_thread(local_rank)
     sampler = ClockSampler(local_rank)
-    sampler.start()
     # ---- timed (value): K registrations of HBM-resident scans, ONE batched launch ---------------------------------
     launches0 = ndt.stats()["kernel_launches"]
     wall0 = time.perf_counter()
@@ -789,6 +838,14 @@ def main():
     re, e2e_ms_max, _ = timed(ndt.prepareBatch([p.numpy() for p in pinned_scans[:K]]))
     rp, e2e_pg_ms_max, _ = timed(ndt.prepareBatch(pageable_scans[:K]))
     clocks = sampler.stop()
+    exchange_checked = None
+    if world > 1:  # outside the timing: what the timed region gathered == an ncclAllGather of the ranks' own results
+        exchange_checked = True
+        for res_k in (rb, re, rp):
+            ref = comm.all_gather_rows(res_k["pose"].reshape(-1, 16)[:K]).reshape(world, K, 4, 4)
+            exchange_checked = exchange_checked and bool(np.array_equal(np.asarray(res_k["gathered"])[:, :K], ref))
+    if board is not None:
+        ndt.attachPoseBoard(None)
 
     # ---- single_align leg: one b200reg_align per step (latency-bound: round 1's headline), L2 flushed between steps ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
@@ -826,7 +883,14 @@ def main():
                         "index_in_smem": st["index_in_smem"], "slots_in_flight": args.slots,
                         "step": "the K steps are K independent registrations (own scan buffer each) issued as ONE "
                                 f"b200reg_ndt_align_batch_device call = one persistent launch, {args.slots} registrations in flight",
-                        "parallelism": f"replicas x{world} + ONE ncclAllGather of the poses (b200comm_all_gather_rows) inside the timed region" if world > 1 else "1 GPU",
+                        "parallelism": ("1 GPU" if world == 1 else
+                                        f"replicas x{world}, poses exchanged inside the timed region by the solver kernel itself: "
+                                        "peer-memory stores into every rank's pose board over NVLink as each registration converges "
+                                        "(b200reg_ndt_attach_pose_board)" if board is not None else
+                                        f"replicas x{world} + ONE ncclAllGather of the poses (b200comm_all_gather_rows) inside the "
+                                        f"timed region (pose board not used: {board_why or 'BENCH_POSE_EXCHANGE=nccl'})"),
+                        "pose_exchange": None if world == 1 else ("pose_board" if board is not None else "nccl_all_gather"),
+                        "pose_exchange_equals_nccl_all_gather": exchange_checked,
                         "batch_bitwise_equals_single_align": bool(bitwise),
                         "mean_iterations": float(rb["iterations"].mean()), "converged": int(rb["converged"].sum())},
             "e2e": {"value": world * K / (e2e_ms_max * 1e-3), "unit": "registrations/s",

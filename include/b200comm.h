@@ -25,6 +25,20 @@ int b200comm_destroy(b200comm_t c);
  * ncclAllGather on the communicator's own stream, one D2H copy; returns when rows_all is complete.                  */
 int b200comm_all_gather_rows(b200comm_t c, const float* rows_local, int rows_per_rank, int row_floats, float* rows_all);
 int b200comm_rank(b200comm_t c, int* rank, int* world);
+
+/* Pose board — the exchange fused INTO the registration kernel. For the sharded batch of one map (every rank registers
+ * its own scans against the same submap: b200reg_ndt_align_batch[_device]) the 4x4 poses do not need a collective call
+ * at all: each rank owns a small board in HBM, all ranks map all boards (CUDA IPC over NVLink / NVSwitch peer memory),
+ * and the solver kernel's controller CTAs store every finished pose straight into all boards, tagged word by word
+ * with the launch number. The transfer overlaps the remaining registrations of the launch; when the call returns,
+ * b200reg_ndt_gathered_poses (b200reg.h) has every rank's poses. Creation is collective over the communicator (one
+ * all-gather of the 64-byte IPC handles); max_rows = the largest batch a rank will register in one call. While a
+ * board is attached to a handle (b200reg_ndt_attach_pose_board), that handle's batch calls are collective: every rank
+ * of the board must make the same sequence of them.                                                                 */
+typedef struct b200comm_board* b200comm_board_t;
+int b200comm_board_create(b200comm_t c, int max_rows, b200comm_board_t* out);
+int b200comm_board_destroy(b200comm_board_t b);
+int b200comm_board_info(b200comm_board_t b, int* rank, int* world, int* max_rows);
 const char* b200comm_last_error(void);
 
 #ifdef __cplusplus

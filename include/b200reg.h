@@ -147,6 +147,16 @@ typedef struct b200reg_sweep_result {
 int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sources, const size_t* n_src,
                       const float* const* targets, const size_t* n_tgt, size_t stride_bytes, const float* guesses,
                       double fitness_max_range, b200reg_sweep_result* results);
+/* Multi-GPU form of the batch calls (the shards are independent, the only exchange is the 4x4 poses):
+ * attach a pose board (include/b200comm.h, b200comm_board_create) and every b200reg_ndt_align_batch[_device] call on this
+ * handle also publishes its poses to all ranks FROM INSIDE the solver kernel — peer-memory stores over NVLink as each
+ * registration converges — and returns when all ranks' poses of the call have arrived here. Such calls are collective:
+ * all ranks of the board make the same sequence of them (counts may differ; 1 <= count <= the board's max_rows).
+ * b200reg_ndt_gathered_poses then copies them out: poses[(r * max_rows + k) * 16 ..] = column-major pose of rank r's
+ * registration k, counts[r] = how many rank r registered. board = NULL detaches. */
+struct b200comm_board;
+int b200reg_ndt_attach_pose_board(b200reg_t h, struct b200comm_board* board);
+int b200reg_ndt_gathered_poses(b200reg_t h, float* poses, int* counts, int max_rows);
 /* registrations in flight per batch launch (1..3; default 3). Developer / measurement switch. */
 int b200reg_ndt_set_batch_slots(b200reg_t h, int slots);
 

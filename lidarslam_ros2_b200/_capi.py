@@ -31,6 +31,7 @@ SYMBOLS = [
     "b200reg_align", "b200reg_get_final_transformation", "b200reg_has_converged",
     "b200reg_get_fitness_score", "b200reg_get_aligned", "b200reg_align_batch",
     "b200reg_ndt_align_batch", "b200reg_ndt_align_batch_device", "b200reg_ndt_set_batch_slots", "b200reg_ndt_sweep",
+    "b200reg_ndt_attach_pose_board", "b200reg_ndt_gathered_poses",
     "b200reg_voxelgrid", "b200reg_get_stats", "b200reg_ndt_derivatives", "b200reg_ndt_hessian_radius",
     "b200reg_ndt_num_voxels", "b200reg_ndt_get_voxels", "b200reg_nn1",
     "b200reg_gicp_get_covariances", "b200reg_gicp_num_correspondences", "b200reg_get_kind",
@@ -41,6 +42,7 @@ SYMBOLS = [
     "b200sm_imu_get_state", "b200sm_imu_get_sample",
     # include/b200comm.h
     "b200comm_unique_id", "b200comm_create", "b200comm_destroy", "b200comm_all_gather_rows", "b200comm_rank", "b200comm_last_error",
+    "b200comm_board_create", "b200comm_board_destroy", "b200comm_board_info",
 ]
 
 
@@ -130,6 +132,8 @@ def lib() -> C.CDLL:
     L.b200reg_ndt_align_batch.argtypes = [vp, i, vp, vp, sz, vp, vp]
     L.b200reg_ndt_align_batch_device.argtypes = [vp, i, vp, vp, vp, vp]
     L.b200reg_ndt_set_batch_slots.argtypes = [vp, i]
+    L.b200reg_ndt_attach_pose_board.argtypes = [vp, vp]
+    L.b200reg_ndt_gathered_poses.argtypes = [vp, vp, vp, i]
     L.b200reg_ndt_sweep.argtypes = [vp, i, vp, vp, vp, vp, sz, vp, d, vp]
     L.b200reg_voxelgrid.argtypes = [i, vp, sz, sz, C.c_long, f, vp, sz, C.POINTER(sz)]
     L.b200reg_get_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -170,6 +174,9 @@ def lib() -> C.CDLL:
     L.b200comm_destroy.argtypes = [vp]
     L.b200comm_all_gather_rows.argtypes = [vp, vp, i, i, vp]
     L.b200comm_rank.argtypes = [vp, C.POINTER(i), C.POINTER(i)]
+    L.b200comm_board_create.argtypes = [vp, i, C.POINTER(vp)]
+    L.b200comm_board_destroy.argtypes = [vp]
+    L.b200comm_board_info.argtypes = [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.b200comm_last_error.argtypes = []
     L.b200comm_last_error.restype = C.c_char_p
     for name in SYMBOLS:

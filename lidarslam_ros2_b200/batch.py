@@ -61,9 +61,10 @@ class RowComm:
             rc = self._lib.b200comm_unique_id(ident)
             if rc != 0:
                 raise RuntimeError("b200comm_unique_id: " + self._lib.b200comm_last_error().decode())
-        t = torch.tensor(list(ident), dtype=torch.uint8, device=torch.device("cuda", device) if dist.get_backend() == "nccl" else None)
-        dist.broadcast(t, src=0)
-        ident = (C.c_ubyte * 128)(*[int(v) for v in t.cpu().tolist()])
+        if world > 1:
+            t = torch.tensor(list(ident), dtype=torch.uint8, device=torch.device("cuda", device) if dist.get_backend() == "nccl" else None)
+            dist.broadcast(t, src=0)
+            ident = (C.c_ubyte * 128)(*[int(v) for v in t.cpu().tolist()])
         h = C.c_void_p()
         rc = self._lib.b200comm_create(ident, int(rank), int(world), int(device), C.byref(h))
         if rc != 0:
@@ -75,6 +76,10 @@ class RowComm:
             self._lib.b200comm_destroy(self._h)
             self._h = None
 
+    def create_board(self, max_rows: int) -> "PoseBoard":
+        """Collective: one pose board per rank, every rank maps all of them (b200comm_board_create)."""
+        return PoseBoard(self, max_rows)
+
     def all_gather_rows(self, rows: np.ndarray) -> np.ndarray:
         rows = np.ascontiguousarray(rows, dtype=np.float32)
         per, width = rows.shape
@@ -83,6 +88,28 @@ class RowComm:
         if rc != 0:
             raise RuntimeError("b200comm_all_gather_rows: " + self._lib.b200comm_last_error().decode())
         return out
+
+
+class PoseBoard:
+    """include/b200comm.h's pose board: attached to an NDT handle (NormalDistributionsTransform.attachPoseBoard) it makes
+    that handle's batch calls exchange their poses from inside the solver kernel (peer-memory stores over NVLink)."""
+
+    def __init__(self, comm: RowComm, max_rows: int):
+        C = comm._C
+        self._lib, self._comm = comm._lib, comm  # the communicator must outlive the board's creation only; kept for clarity
+        h = C.c_void_p()
+        rc = self._lib.b200comm_board_create(comm._h, int(max_rows), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("b200comm_board_create: " + self._lib.b200comm_last_error().decode())
+        self._h, self.rank, self.world, self.max_rows = h, comm.rank, comm.world, int(max_rows)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.b200comm_board_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
 
 
 def gather_rows(local_rows: np.ndarray, n_pairs: int, rank: int, world: int, device=None, comm: "RowComm | None" = None):

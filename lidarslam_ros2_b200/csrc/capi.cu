@@ -78,6 +78,8 @@ struct b200reg_engine {
   CloudUploader batch_uploader;
   std::vector<NdtSolver::BatchItem> batch_items;
   int batch_slots = NDT_BATCH_SLOTS_DEFAULT;
+  b200comm_board* board = nullptr;  // attached pose board (not owned): batch launches also publish their poses to the peers
+  int board_valid = 0;              // the last batch call filled board->h_rows
   int sibling_launches_seen[3] = {0, 0, 0};
   cudaStream_t copy_stream = nullptr;    // streaming uploads of b200reg_ndt_align_batch
   DeviceBuffer<unsigned> batch_ready;    // one "scan k has arrived" flag per registration of a batch
@@ -912,6 +914,8 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const s
   };
   long long evals = 0, hits = 0;
   const bool sequential = batch_needs_sequential(h);
+  if (sequential && h->board)
+    return fail(h, B200REG_ERR_ARG, "align_batch with a pose board attached needs the one-launch path (non-empty map, step_size > transformation_epsilon / 2)");
   if (sequential) {
     int worst = B200REG_OK;
     float ms = 0;
@@ -940,6 +944,9 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const s
   const int per_launch = std::max(1, NdtSolver::kMaxRoundsPerLaunch / (h->ndt.max_iterations + 4));
   int worst = B200REG_OK;
   float ms_total = 0;
+  h->board_valid = 0;
+  if (h->board && (count > per_launch || count > h->board->view.rows || count == 0))
+    return fail(h, B200REG_ERR_ARG, "align_batch with a pose board attached: 1 .. min(board rows, one launch) registrations per call");
   for (int first = 0; first < count; first += per_launch) {
     const int n = std::min(per_launch, count - first);
     const double tr0 = g_trace ? trace_now() : 0;
@@ -947,11 +954,16 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const s
     {
       std::lock_guard<std::mutex> coop(cooperative_launch_mutex(h->device));
       B200_CUDA(cudaEventRecord(h->ev0, h->stream));
-      h->solver.launch_batch(h->map, items.data() + first, n, h->ndt, h->batch_slots);
+      if (h->board) h->board->view.tag += 1;  // every rank of the board makes the same sequence of batch calls
+      h->solver.launch_batch(h->map, items.data() + first, n, h->ndt, h->batch_slots, h->board);
       B200_CUDA(cudaEventRecord(h->ev1, h->stream));
       if (g_trace) tr1 = trace_now();
       if (after_launch) after_launch();
       if (g_trace) tr2 = trace_now();
+      // The collect kernel goes in behind ev1 (solve_ms stays the solver kernel's own time) and only AFTER the streaming
+      // uploads have been issued and drained: a launch parked behind the solver could otherwise sit in front of the
+      // copy stream's memory operations on a shared hardware queue while the solver still waits for exactly those.
+      if (h->board) h->solver.launch_board_collect(h->board);
       B200_CUDA(cudaStreamSynchronize(h->stream));
     }
     if (g_trace) {
@@ -982,6 +994,12 @@ int ndt_batch_run(b200reg_t h, int count, b200reg_batch_result* results, const s
       h->solver.reset_barrier();
       B200_CUDA(cudaStreamSynchronize(h->stream));
       worst = fail(h, B200REG_ERR_TIMEOUT, "NDT batch solver: a registration did not finish (device watchdog)");
+    }
+    if (h->board && !failed) {
+      if (h->board->h_counts[h->board->view.world] != 0)
+        worst = fail(h, B200REG_ERR_TIMEOUT, "pose board: a peer's poses did not arrive (did every rank make this batch call?)");
+      else
+        h->board_valid = 1;
     }
   }
   // the handle's "last align" state = the last registration of the batch
@@ -1094,6 +1112,27 @@ int b200reg_ndt_align_batch(b200reg_t h, int count, const float* const* sources,
     h->other_launches += count;
     return ndt_batch_run(h, count, results);
   });
+}
+
+int b200reg_ndt_attach_pose_board(b200reg_t h, b200comm_board* board) {
+  if (!h || h->kind != B200REG_NDT) return B200REG_ERR_ARG;
+  if (board && board->device != h->device) return fail(h, B200REG_ERR_ARG, "attach_pose_board: the board lives on another device");
+  h->board = board;
+  h->board_valid = 0;
+  return B200REG_OK;
+}
+
+int b200reg_ndt_gathered_poses(b200reg_t h, float* poses, int* counts, int max_rows) {
+  if (!h || h->kind != B200REG_NDT || !poses || !counts || max_rows < 0) return B200REG_ERR_ARG;
+  if (!h->board || !h->board_valid) return fail(h, B200REG_ERR_ARG, "gathered_poses: no finished batch call with a pose board attached");
+  const b200::PoseBoardView& B = h->board->view;
+  for (int r = 0; r < B.world; r++) {
+    const int n = h->board->h_counts[r];
+    counts[r] = n;
+    if (n > max_rows) return fail(h, B200REG_ERR_ARG, "gathered_poses: max_rows is smaller than a rank's count");
+    for (int k = 0; k < n; k++) row_to_col(h->board->h_rows + ((size_t)r * B.rows + k) * 16, poses + ((size_t)r * max_rows + k) * 16);
+  }
+  return B200REG_OK;
 }
 
 int b200reg_ndt_set_batch_slots(b200reg_t h, int slots) {

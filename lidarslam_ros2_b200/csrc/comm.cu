@@ -9,6 +9,7 @@
 
 #include "../../include/b200comm.h"
 #include "../../include/b200reg.h"
+#include "engine.hpp"
 
 namespace {
 
@@ -169,6 +170,106 @@ int b200comm_all_gather_rows(b200comm_t c, const float* rows_local, int rows_per
     return cuda_fail(e, "cudaMemcpyAsync D2H");
   if ((e = cudaStreamSynchronize(c->stream)) != cudaSuccess) return cuda_fail(e, "cudaStreamSynchronize");
   std::memcpy(rows_all, c->h_pinned, n * c->world * sizeof(float));
+  return B200REG_OK;
+}
+
+// ---- pose board (engine.hpp): one buffer per rank, mapped by every rank through CUDA IPC ---------------------------
+int b200comm_board_create(b200comm_t c, int max_rows, b200comm_board_t* out) {
+  if (!c || !out || max_rows < 1 || max_rows > (1 << 16)) return B200REG_ERR_ARG;
+  *out = nullptr;
+  if (c->world > b200::POSE_BOARD_MAX_PEERS) {
+    g_err = "pose board: at most 8 ranks (one NVSwitch domain)";
+    return B200REG_ERR_ARG;
+  }
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the handle travels as one row of 16 floats");
+  cudaError_t e = cudaSetDevice(c->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  b200comm_board* b = new b200comm_board();
+  b->device = c->device;
+  b->view.world = c->world;
+  b->view.rank = c->rank;
+  b->view.rows = max_rows;
+  b->view.tag = 0;
+  const size_t bytes = b200::pose_board_words(c->world, max_rows) * sizeof(unsigned long long);
+  int rc = B200REG_OK;
+  float handles[b200::POSE_BOARD_MAX_PEERS * 16];
+  cudaIpcMemHandle_t mine;
+  std::memset(&mine, 0, sizeof(mine));
+  // a failure on one rank must not leave the others inside the collective: every rank always performs both all-gathers
+  if ((e = cudaMalloc(&b->own, bytes)) != cudaSuccess) rc = cuda_fail(e, "cudaMalloc(pose board)");
+  if (rc == B200REG_OK && (e = cudaMemset(b->own, 0, bytes)) != cudaSuccess) rc = cuda_fail(e, "cudaMemset(pose board)");
+  if (rc == B200REG_OK && (e = cudaDeviceSynchronize()) != cudaSuccess) rc = cuda_fail(e, "cudaDeviceSynchronize");
+  if (rc == B200REG_OK && (e = cudaMallocHost(&b->h_rows, (size_t)c->world * max_rows * 16 * sizeof(float))) != cudaSuccess)
+    rc = cuda_fail(e, "cudaMallocHost");
+  if (rc == B200REG_OK && (e = cudaMallocHost(&b->h_counts, (size_t)(c->world + 1) * sizeof(int))) != cudaSuccess)
+    rc = cuda_fail(e, "cudaMallocHost");
+  if (rc == B200REG_OK && c->world > 1 && (e = cudaIpcGetMemHandle(&mine, b->own)) != cudaSuccess) rc = cuda_fail(e, "cudaIpcGetMemHandle");
+  float row[16];
+  std::memcpy(row, &mine, 64);  // bytes only: no float arithmetic touches them on the way
+  if (c->world > 1) {
+    const int g = b200comm_all_gather_rows(c, row, 1, 16, handles);
+    if (rc == B200REG_OK && g != B200REG_OK) rc = g;
+  }
+  b->view.peer[c->rank] = b->own;
+  for (int p = 0; p < c->world && rc == B200REG_OK; p++) {
+    if (p == c->rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handles + 16 * p, 64);
+    bool zero = true;
+    for (size_t i = 0; i < sizeof(h); i++) zero = zero && reinterpret_cast<const unsigned char*>(&h)[i] == 0;
+    if (zero) {
+      g_err = "pose board: rank " + std::to_string(p) + " could not export its board";
+      rc = B200REG_ERR_CUDA;
+      break;
+    }
+    if ((e = cudaIpcOpenMemHandle(&b->opened[p], h, cudaIpcMemLazyEnablePeerAccess)) != cudaSuccess) {
+      rc = cuda_fail(e, "cudaIpcOpenMemHandle");
+      break;
+    }
+    b->view.peer[p] = static_cast<unsigned long long*>(b->opened[p]);
+  }
+  // second round: did every rank map every board? (a board is usable only if all of them did)
+  float ok_row[16] = {rc == B200REG_OK ? 1.0f : 0.0f};
+  float ok_all[b200::POSE_BOARD_MAX_PEERS * 16];
+  if (c->world > 1) {
+    const std::string keep = rc == B200REG_OK ? std::string() : g_err;
+    const int g = b200comm_all_gather_rows(c, ok_row, 1, 16, ok_all);
+    if (!keep.empty()) g_err = keep;
+    if (rc == B200REG_OK && g != B200REG_OK) rc = g;
+    for (int p = 0; p < c->world && rc == B200REG_OK; p++)
+      if (ok_all[16 * p] != 1.0f) {
+        g_err = "pose board: rank " + std::to_string(p) + " could not map the peers' boards";
+        rc = B200REG_ERR_CUDA;
+      }
+  }
+  if (rc != B200REG_OK) {
+    const std::string keep = g_err;
+    b200comm_board_destroy(b);
+    g_err = keep;
+    return rc;
+  }
+  *out = b;
+  return B200REG_OK;
+}
+
+int b200comm_board_destroy(b200comm_board_t b) {
+  if (!b) return B200REG_ERR_ARG;
+  cudaSetDevice(b->device);
+  cudaDeviceSynchronize();
+  for (int p = 0; p < b200::POSE_BOARD_MAX_PEERS; p++)
+    if (b->opened[p]) cudaIpcCloseMemHandle(b->opened[p]);
+  if (b->own) cudaFree(b->own);
+  if (b->h_rows) cudaFreeHost(b->h_rows);
+  if (b->h_counts) cudaFreeHost(b->h_counts);
+  delete b;
+  return B200REG_OK;
+}
+
+int b200comm_board_info(b200comm_board_t b, int* rank, int* world, int* max_rows) {
+  if (!b) return B200REG_ERR_ARG;
+  if (rank) *rank = b->view.rank;
+  if (world) *world = b->view.world;
+  if (max_rows) *max_rows = b->view.rows;
   return B200REG_OK;
 }
 

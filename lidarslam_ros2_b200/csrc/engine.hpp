@@ -199,6 +199,39 @@ struct NdtConfig {
   int search_method = 2;  // DIRECT7
 };
 
+// ---- pose board: the poses of a sharded batch exchanged by the solver kernel itself over NVLink peer memory ----------
+// Every rank owns one board in its HBM; all ranks map all boards (CUDA IPC, include/b200comm.h). When a registration of
+// a batch launch finishes, its controller CTA stores the 4x4 pose into row [own rank][registration] of EVERY board —
+// sixteen 64-bit words {float bits, launch tag}, so a word is valid exactly when its tag is the current launch's (the
+// same flag-in-data convention as the kernel's internal signalling: no fence, no second message). The exchange rides
+// on the kernel's own progress: by the time the last registration converges all earlier poses have already crossed
+// NVSwitch. A small collect kernel behind the solver waits for the remaining words and copies the rows to mapped host
+// memory. Boards are double-buffered by tag parity: a rank can be at most one launch ahead of its slowest peer.
+constexpr int POSE_BOARD_MAX_PEERS = 8;
+struct PoseBoardView {
+  unsigned long long* peer[POSE_BOARD_MAX_PEERS];  // peer[r]: rank r's board as mapped on THIS device (peer[rank] = own)
+  int world, rank;
+  int rows;      // registrations per rank and launch the board has room for; row `rows` is the header {count, tag}
+  unsigned tag;  // this launch's sequence number (> 0; the same on every rank: attached batch calls are collective)
+};
+__host__ __device__ inline size_t pose_board_word(const PoseBoardView& b, unsigned tag, int src_rank, int row, int k) {
+  return ((((size_t)(tag & 1u) * (size_t)b.world + (size_t)src_rank) * (size_t)(b.rows + 1)) + (size_t)row) * 16 + (size_t)k;
+}
+inline size_t pose_board_words(int world, int rows) { return (size_t)2 * world * (rows + 1) * 16; }
+
+}  // namespace b200
+// the opaque object of include/b200comm.h (created by b200comm_board_create in comm.cu, consumed by capi.cu)
+struct b200comm_board {
+  b200::PoseBoardView view{};
+  unsigned long long* own = nullptr;
+  void* opened[b200::POSE_BOARD_MAX_PEERS] = {};
+  float* h_rows = nullptr;   // pinned + mapped: world x rows x 16 floats (row-major poses), written by the collect kernel
+  int* h_counts = nullptr;   // pinned + mapped: world counts, then [world] = error flag of the collect kernel
+  int device = 0;
+  double timeout_s = 5.0;
+};
+namespace b200 {
+
 enum NdtMode : int { NDT_MODE_ALIGN = 0, NDT_MODE_DERIVATIVES = 1, NDT_MODE_HESSIAN_RADIUS = 2, NDT_MODE_SCORE = 3 };
 
 class NdtSolver {
@@ -221,7 +254,11 @@ class NdtSolver {
   };
   // enqueue ONE launch that performs n independent registrations against `map`, `slots` (<= NDT_MAX_SLOTS) in flight;
   // after the stream has drained batch_results()[k] holds registration k (error != 0: the kernel never finished it)
-  void launch_batch(const VoxelMap& map, const BatchItem* items, int n, const NdtConfig& cfg, int slots);
+  // board (optional): the finished poses also go to every peer's pose board (board->view.tag = this launch's number);
+  // launch_board_collect() then enqueues the kernel that gathers all ranks' rows of the launch into board->h_rows / h_counts
+  void launch_batch(const VoxelMap& map, const BatchItem* items, int n, const NdtConfig& cfg, int slots,
+                    b200comm_board* board = nullptr);
+  void launch_board_collect(b200comm_board* board);
   const NdtResult* batch_results() const { return h_batch_results_; }
   // rounds one slot can run inside a launch (sequence numbers are 16 bits per launch)
   static constexpr int kMaxRoundsPerLaunch = 60000;

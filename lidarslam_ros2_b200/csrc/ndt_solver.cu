@@ -100,6 +100,15 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long* p, unsigned long long v) {
   asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// system scope: pose-board words live in a peer GPU's memory (NVLink) or are read while a peer writes them
+__device__ __forceinline__ void st_relaxed_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void ld_relaxed_gpu_v2(const double* p, unsigned long long& a, unsigned long long& b) {
   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
@@ -892,6 +901,9 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
   };
   if (batch) {  // first registration of this slot
     if (warp == 0) {
+      if (slot == 0 && L.board.world > 0 && lane < L.board.world)  // header of this rank's rows on every board: {count, tag}
+        st_relaxed_sys_u64(L.board.peer[lane] + pose_board_word(L.board, L.board.tag, L.board.rank, L.board.rows, 0),
+                           ((unsigned long long)L.board.tag << 32) | (unsigned)L.n_jobs);
       start_next_job(L, cs, lane, n_eval_i);
       publish(0);
     }
@@ -1023,6 +1035,12 @@ __device__ __noinline__ void controller_cta(const NdtLaunch& L, CtlShared& cs, d
           const int* src = reinterpret_cast<const int*>(&cs.result);
           int* dst = reinterpret_cast<int*>(L.result_host + cs.cur_job);
           for (int k = lane; k < (int)(sizeof(NdtResult) / 4); k += 32) dst[k] = src[k];
+          if (L.board.world > 0 && lane < 16) {
+            // ... and its pose to every rank's pose board over NVLink, word by word with the launch tag (engine.hpp)
+            const unsigned long long w = ((unsigned long long)L.board.tag << 32) | __float_as_uint(cs.result.final_T[lane]);
+            const size_t off = pose_board_word(L.board, L.board.tag, L.board.rank, cs.cur_job, lane);
+            for (int p = 0; p < L.board.world; p++) st_relaxed_sys_u64(L.board.peer[p] + off, w);
+          }
           __syncwarp();
           if (lane == 0) cs.job_done = 0;
           start_next_job(L, cs, lane, n_eval_i);
@@ -1549,10 +1567,47 @@ void NdtSolver::launch(const VoxelMap& map, const float4* src, size_t n_src, con
   launches += 1;
 }
 
+// Behind a batch launch with a pose board: wait until every rank's rows of this launch have arrived in OUR board and
+// copy them to mapped host memory. One thread per (rank, row, word); rows beyond a rank's count leave at once. The
+// peers' kernels make progress independently of this one, so the wait is bounded by their batch duration; the timeout
+// only guards against a peer that never launches (collective misuse / a crashed rank).
+__global__ void pose_board_collect_kernel(PoseBoardView B, float* __restrict__ rows_host, int* __restrict__ counts_host,
+                                          unsigned long long timeout_ns) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int k = t & 15, row = (t >> 4) % B.rows, src = (t >> 4) / B.rows;
+  if (src >= B.world) return;
+  const unsigned long long* own = B.peer[B.rank];
+  const unsigned long long t0 = globaltimer_ns();
+  auto wait_word = [&](const unsigned long long* p, unsigned& payload) {
+    for (;;) {
+      const unsigned long long w = ld_relaxed_sys_u64(p);
+      if ((unsigned)(w >> 32) == B.tag) {
+        payload = (unsigned)w;
+        return true;
+      }
+      if (globaltimer_ns() - t0 > timeout_ns) return false;
+      __nanosleep(200);
+    }
+  };
+  unsigned count = 0, bits = 0;
+  if (!wait_word(own + pose_board_word(B, B.tag, src, B.rows, 0), count)) {
+    counts_host[B.world] = 1;
+    return;
+  }
+  if (row == 0 && k == 0) counts_host[src] = (int)count;
+  if (row >= (int)count) return;
+  if (!wait_word(own + pose_board_word(B, B.tag, src, row, k), bits)) {
+    counts_host[B.world] = 1;
+    return;
+  }
+  rows_host[((size_t)src * B.rows + row) * 16 + k] = __uint_as_float(bits);
+}
+
 // K independent registrations against the same voxel map in ONE cooperative launch, NDT_MAX_SLOTS of them in flight:
 // while one registration's controller CTA reduces / solves / publishes, the evaluator CTAs work on the other one.
 // Results land in the mapped host array batch_results()[0..n) once the stream has drained.
-void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n, const NdtConfig& cfg, int slots) {
+void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n, const NdtConfig& cfg, int slots,
+                             b200comm_board* board) {
   if (n <= 0) return;
   if ((size_t)n > jobs_cap_) {
     if (d_jobs_) cudaFree(d_jobs_);
@@ -1594,12 +1649,25 @@ void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n,
   L.n_jobs = n;
   L.n_slots = n_slots;
   L.n_src = (int)n_max;
+  if (board) L.board = board->view;
   grid_ = eval_ctas_for(n_max) + L.n_slots;
   block_ = SOLVER_THREADS;
   KernelFn fn = kernel_for(cfg.search_method);
   void* args[] = {&L};
   B200_CUDA(cudaLaunchCooperativeKernel((const void*)fn, dim3(grid_), dim3(SOLVER_THREADS), args, dyn_smem, stream_));
   launches += 1;
+}
+
+void NdtSolver::launch_board_collect(b200comm_board* board) {
+  {
+    const PoseBoardView& B = board->view;
+    board->h_counts[B.world] = 0;
+    const int threads = B.world * B.rows * 16;
+    pose_board_collect_kernel<<<(threads + 255) / 256, 256, 0, stream_>>>(B, board->h_rows, board->h_counts,
+                                                                         (unsigned long long)(board->timeout_s * 1e9));
+    B200_CUDA(cudaGetLastError());
+    launches += 1;
+  }
 }
 
 }  // namespace b200

@@ -109,6 +109,7 @@ struct NdtLaunch {
   const NdtJob* jobs;
   int n_jobs;
   int n_slots;
+  PoseBoardView board;  // board.world > 0: finished poses are also stored into every peer's pose board (engine.hpp)
   GridGeom geom;
   int n_src;
   int n_voxels;

@@ -238,10 +238,12 @@ class NormalDistributionsTransform(_Registration):
         gp = _ptr(g) if g is not None else None
         res = (_capi.BatchResult * max(K, 1))()
 
+        gather = self._prepared_gather()
+
         def call():
             rc = self._lib.b200reg_ndt_align_batch_device(self._h, K, ptrs, ns, gp, res)
             self._check(rc, soft=(_capi.ERR_NO_TARGET,))
-            return self._batch_out(res, K)
+            return gather(self._batch_out(res, K))
 
         call.keepalive = (ptrs, ns, g, res)
         return call
@@ -260,10 +262,12 @@ class NormalDistributionsTransform(_Registration):
         gp = _ptr(g) if g is not None else None
         res = (_capi.BatchResult * max(K, 1))()
 
+        gather = self._prepared_gather()
+
         def call():
             rc = self._lib.b200reg_ndt_align_batch(self._h, K, ptrs, ns, stride, gp, res)
             self._check(rc, soft=(_capi.ERR_NO_TARGET,))
-            return self._batch_out(res, K)
+            return gather(self._batch_out(res, K))
 
         call.keepalive = (cs, ptrs, ns, g, res)
         return call
@@ -294,6 +298,46 @@ class NormalDistributionsTransform(_Registration):
 
     _SWEEP_DTYPE = np.dtype([("final_T", np.float32, (16,)), ("fitness", np.float64), ("trans_probability", np.float64),
                              ("converged", np.int32), ("iterations", np.int32), ("status", np.int32), ("pad", np.int32)])
+
+    def attachPoseBoard(self, board):
+        """Multi-GPU batch calls (b200reg_ndt_attach_pose_board): with a batch.PoseBoard attached, alignBatch /
+        alignBatchDevice become collective over the board's ranks and gatheredPoses() returns every rank's poses of the
+        last call. None detaches."""
+        self._check(self._lib.b200reg_ndt_attach_pose_board(self._h, board._h if board is not None else None))
+        self._board = board
+
+    def _prepared_gather(self):
+        """For the prepared batch calls: with a pose board attached (at preparation time) the call's result also carries
+        every rank's poses — "gathered" [world, max_rows, 4, 4] (a view into a buffer reused by the next call; rows beyond
+        "gathered_counts"[r] are stale) — copied out of the board by b200reg_ndt_gathered_poses into preallocated arrays."""
+        b = getattr(self, "_board", None)
+        if b is None:
+            return lambda out: out
+        counts = np.zeros(b.world, dtype=np.int32)
+        buf = np.zeros((b.world, b.max_rows, 16), dtype=np.float32)
+        view = buf.reshape(b.world, b.max_rows, 4, 4).transpose(0, 1, 3, 2)  # column-major -> row-major, no copy
+        pb, pc, fn, h, rows = buf.ctypes.data, counts.ctypes.data, self._lib.b200reg_ndt_gathered_poses, self._h, b.max_rows
+
+        def gather(out):
+            self._check(fn(h, pb, pc, rows))
+            out["gathered"], out["gathered_counts"] = view, counts
+            return out
+
+        return gather
+
+    def gatheredPoses(self):
+        """(poses [world, max_count, 4, 4] float32 — rows beyond a rank's count are identity — and counts [world])."""
+        b = getattr(self, "_board", None)
+        if b is None:
+            raise RuntimeError("gatheredPoses: no pose board attached")
+        counts = np.zeros(b.world, dtype=np.int32)
+        buf = np.zeros((b.world, b.max_rows, 16), dtype=np.float32)
+        self._check(self._lib.b200reg_ndt_gathered_poses(self._h, buf.ctypes.data, counts.ctypes.data, b.max_rows))
+        m = int(counts.max()) if b.world else 0
+        out = buf[:, :m].reshape(b.world, m, 4, 4).transpose(0, 1, 3, 2).copy()
+        for r in range(b.world):
+            out[r, counts[r]:] = np.eye(4, dtype=np.float32)
+        return out, counts
 
     def setBatchSlots(self, slots: int):
         self._check(self._lib.b200reg_ndt_set_batch_slots(self._h, int(slots)))

@@ -6,6 +6,8 @@
  * start() and stop(), keeping the samples in a fixed array. Measurement plumbing only; not part of the engine's C-ABI.
  *
  *   int  b200clk_start(const char* gpu_uuid_or_null, int index, int period_us);   0 on success
+ *   void b200clk_arm(void);     the timed region starts now: the in-region schedule counts from here (start() itself
+ *                               takes the "before" sample and may be called well ahead of the region)
  *   int  b200clk_stop(unsigned* sm_mhz, unsigned long long* reasons, int capacity, unsigned* sm_max_mhz);  -> #samples
  */
 #include <dlfcn.h>
@@ -30,6 +32,7 @@ static struct {
   nvmlDevice_t dev;
   pthread_t thread;
   atomic_int running;
+  atomic_int armed;
   int started;
   int period_us;
   int n;
@@ -50,19 +53,27 @@ static void sample_once(void) {
 
 static void* poll(void* arg) {
   (void)arg;
-  /* NVML queries take a driver lock the CUDA launch path also wants: a dense poll is affordable for the few
-   * milliseconds of the headline region, not for a region of hundreds of milliseconds with thousands of launches (the
-   * streaming workload slowed down 1.6x under a constant 250 us poll). So the period backs off: 250 us for the first 16
-   * samples, 2 ms up to 64, 20 ms afterwards. */
-  int k = 0;
-  while (atomic_load(&S.running)) {
-    sample_once();
-    k++;
-    long us = S.period_us;
-    if (k > 64) us = us < 20000 ? 20000 : us;
-    else if (k > 16) us = us < 2000 ? 2000 : us;
-    struct timespec ts = {us / 1000000L, (us % 1000000L) * 1000L};
+  /* NVML queries take a driver lock that CUDA's launch / copy / NCCL calls also want (measured: with a sample every 250 us the
+   * 40 us ncclAllGather that closes bench.py's timed region took 270 us; a streaming workload with thousands of launches ran
+   * 1.6x slower). The timed region of the default run is ONE ~1.4 ms kernel with the host merely waiting for it, so the
+   * sampler takes its first in-region sample `period_us` (default 400 us) after the start — while that kernel runs and no
+   * driver call is in flight — and then backs off: 4 ms, 8 ms, 16 ms, 20 ms ... */
+  long us = S.period_us;
+  while (atomic_load(&S.running) && !atomic_load(&S.armed)) { /* parked until the region starts */
+    struct timespec ts = {0, 20 * 1000L};
     nanosleep(&ts, NULL);
+  }
+  while (atomic_load(&S.running)) {
+    long left = us;
+    while (left > 0 && atomic_load(&S.running)) { /* sleep in <= 200 us slices so that stop() returns promptly */
+      const long slice = left < 200 ? left : 200;
+      struct timespec ts = {0, slice * 1000L};
+      nanosleep(&ts, NULL);
+      left -= slice;
+    }
+    if (!atomic_load(&S.running)) break;
+    sample_once();
+    us = us < 4000 ? 4000 : (us * 2 > 20000 ? 20000 : us * 2);
   }
   return NULL;
 }
@@ -86,8 +97,9 @@ int b200clk_start(const char* uuid, int index, int period_us) {
     if (ok != 0) return -4;
   }
   S.n = 0;
-  S.period_us = period_us > 0 ? period_us : 250;
+  S.period_us = period_us > 0 ? period_us : 400;
   sample_once(); /* one sample before the region starts */
+  atomic_store(&S.armed, 0);
   atomic_store(&S.running, 1);
   if (pthread_create(&S.thread, NULL, poll, NULL) != 0) {
     atomic_store(&S.running, 0);
@@ -96,6 +108,8 @@ int b200clk_start(const char* uuid, int index, int period_us) {
   S.started = 1;
   return 0;
 }
+
+void b200clk_arm(void) { atomic_store(&S.armed, 1); }
 
 int b200clk_stop(unsigned* sm_mhz, unsigned long long* reasons, int capacity, unsigned* sm_max_mhz) {
   if (!S.started) return 0;
