@@ -1,6 +1,8 @@
-# usage: r2x.sh N   — pose-board test + default bench at N ranks
+#!/bin/bash
+# usage (on an N-GPU box): gpurun --gpus N -- 'bash tools/multi_gpu_check.sh N'
+# the pose-board check under torchrun (bitwise against ncclAllGather) + the default bench line at N ranks → gpurun_out/
 N=$1; out=gpurun_out; mkdir -p $out
-[ "$N" = "2" ] && timeout 600 python -m pytest tests/test_gpu_pose_board.py -x -q 2>&1 | tail -3
+if [ "$N" = "2" ]; then timeout 600 python -m pytest tests/test_gpu_pose_board.py -x -q 2>&1 | tail -3; fi
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29521 tools/check_pose_board.py 2>&1 | grep -v "^W\|^\*\*\*\|OMP_NUM" | tail -4
 run() { # tag, env
   env $2 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $3 bench.py --gpus $N --steps 20 --warmup 5 --no-cpu-baseline > $out/bench_n${N}_$1.json 2> $out/bench_n${N}_$1.err
@@ -17,4 +19,4 @@ except Exception as e:
 PY
 }
 run board BENCH_X=1 29514
-[ "$N" = "2" ] && run board2 BENCH_X=1 29515
+if [ "$N" = "2" ]; then run board2 BENCH_X=1 29515; fi
