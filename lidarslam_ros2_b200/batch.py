@@ -166,7 +166,7 @@ class LoopSweep:
         return int(self.ndt.stats()["kernel_launches"])
 
     def run(self, sources, targets, indices) -> np.ndarray:
-        """b200reg_ndt_sweep: the pairs pipelined over two internal engines (two host threads, two streams)."""
+        """b200reg_ndt_sweep: the pairs dealt round-robin to up to four internal engines (one host thread and one stream each)."""
         if len(indices) == 0:
             return np.zeros((0, ROW), dtype=np.float32)
         r = self.ndt.sweep(sources, targets)

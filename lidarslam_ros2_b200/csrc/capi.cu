@@ -1197,25 +1197,26 @@ extern "C" int b200reg_ndt_sweep(b200reg_t h, int count, const float* const* sou
     eng[e]->min_points_per_voxel = h->min_points_per_voxel;
     eng[e]->min_covar_eigvalue_mult = h->min_covar_eigvalue_mult;
   }
-  // A few host threads, one engine (stream + buffers) each, take the pairs from a shared counter: the upload and voxel-map
-  // build of one pair overlap the solve and fitness pass of another, and the host-side launch / wait overheads of the
-  // pairs overlap too (a pair is ~25 small launches and a handful of waits: more host time than device time). Every pair
-  // is computed exactly as the sequential calls would compute it (the result does not depend on which engine served it).
-  std::atomic<int> next{0};
+  // A few host threads, one engine (stream + buffers) each: the upload and voxel-map build of one pair overlap the solve
+  // and fitness pass of another, and the host-side launch / wait overheads of the pairs overlap too (a pair is ~25 small
+  // launches and a handful of waits: more host time than device time). Every pair is computed exactly as the sequential
+  // calls would compute it (the result does not depend on which engine served it). Pairs are dealt round-robin — pair i to
+  // engine i mod n_eng — not taken from a shared counter: the pairs cost about the same, and a repeated sweep (the
+  // backend revisiting its candidates, a warmed-up benchmark pass) then shows every engine the targets it has already
+  // sized its bounding-box-dependent buffers for, instead of an occasional cudaFree + cudaMalloc (a device-wide
+  // synchronisation) in the middle of the pipeline.
   std::atomic<int> worst{B200REG_OK};
-  auto worker = [&](b200reg_t e) {
-    for (;;) {
-      const int i = next.fetch_add(1);
-      if (i >= count) break;
-      const int rc = sweep_one(e, sources[i], n_src[i], targets[i], n_tgt[i], stride_bytes, guesses ? guesses + 16 * i : nullptr,
+  auto worker = [&](int e) {
+    for (int i = e; i < count; i += n_eng) {
+      const int rc = sweep_one(eng[e], sources[i], n_src[i], targets[i], n_tgt[i], stride_bytes, guesses ? guesses + 16 * i : nullptr,
                                fitness_max_range, &results[i]);
       results[i].status = rc;
       if (rc != B200REG_OK) worst.store(rc);
     }
   };
   std::vector<std::thread> threads;
-  for (int e = 1; e < n_eng; e++) threads.emplace_back(worker, eng[e]);
-  worker(eng[0]);
+  for (int e = 1; e < n_eng; e++) threads.emplace_back(worker, e);
+  worker(0);
   for (std::thread& t : threads) t.join();
   for (int e = 1; e < n_eng; e++) {
     const int seen = eng[e]->solver.launches + eng[e]->map.launches + eng[e]->nn.launches + eng[e]->other_launches;

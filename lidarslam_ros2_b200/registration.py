@@ -274,7 +274,7 @@ class NormalDistributionsTransform(_Registration):
 
     def sweep(self, sources, targets, guesses=None, fitness_max_range: float = np.finfo(np.float64).max) -> dict:
         """The loop-closure candidate sweep on this GPU (b200reg_ndt_sweep): K independent (source, target) pairs through
-        setInputTarget + setInputSource + align + getFitnessScore, pipelined over two internal engines."""
+        setInputTarget + setInputSource + align + getFitnessScore, pipelined over up to four internal engines."""
         K = len(sources)
         ss = [_as_cloud(c) for c in sources]
         ts = [_as_cloud(c) for c in targets]

@@ -156,7 +156,7 @@ def test_get_aligned_matches_transformed_source(b200, oracle_mod, pair_small):
 
 
 def test_sweep_equals_sequential_pairs(b200):
-    """b200reg_ndt_sweep (two engines, two host threads) == the same pairs through setInputTarget + setInputSource + align +
+    """b200reg_ndt_sweep (up to four engines / host threads, pairs dealt round-robin) == the same pairs through setInputTarget + setInputSource + align +
     getFitnessScore one after the other, bitwise (each pair is computed by exactly the same kernels on the same inputs)."""
     from lidarslam_ros2_b200 import batch, synth
 

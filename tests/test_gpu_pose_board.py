@@ -78,7 +78,7 @@ def test_board_two_ranks_over_nvlink(b200):
     import torch
 
     if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs (run by tools/gpu_round.sh's --gpus 2 leg)")
+        pytest.skip("needs two GPUs (tools/multi_gpu_check.sh 2 runs it on a 2-GPU box)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29533", os.path.join(ROOT, "tools", "check_pose_board.py")]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
