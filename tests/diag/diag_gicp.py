@@ -3,7 +3,7 @@
 For each config: covariance agreement (source / target) with the eigen-gap of the mismatching points, then the pose after
 1, 2, 3, 5, 10, 30, 100 outer iterations (transformation_epsilon 1e-8 like the node, sm.cpp:119) on both sides."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import lidarslam_ros2_b200 as m
