@@ -1659,15 +1659,13 @@ void NdtSolver::launch_batch(const VoxelMap& map, const BatchItem* items, int n,
 }
 
 void NdtSolver::launch_board_collect(b200comm_board* board) {
-  {
-    const PoseBoardView& B = board->view;
-    board->h_counts[B.world] = 0;
-    const int threads = B.world * B.rows * 16;
-    pose_board_collect_kernel<<<(threads + 255) / 256, 256, 0, stream_>>>(B, board->h_rows, board->h_counts,
-                                                                         (unsigned long long)(board->timeout_s * 1e9));
-    B200_CUDA(cudaGetLastError());
-    launches += 1;
-  }
+  const PoseBoardView& B = board->view;
+  board->h_counts[B.world] = 0;  // the kernel's timeout flag
+  const int threads = B.world * B.rows * 16;
+  pose_board_collect_kernel<<<(threads + 255) / 256, 256, 0, stream_>>>(B, board->h_rows, board->h_counts,
+                                                                       (unsigned long long)(board->timeout_s * 1e9));
+  B200_CUDA(cudaGetLastError());
+  launches += 1;
 }
 
 }  // namespace b200
