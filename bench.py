@@ -844,8 +844,10 @@ def main():
         for res_k in (rb, re, rp):
             ref = comm.all_gather_rows(res_k["pose"].reshape(-1, 16)[:K]).reshape(world, K, 4, 4)
             exchange_checked = exchange_checked and bool(np.array_equal(np.asarray(res_k["gathered"])[:, :K], ref))
-    if board is not None:
+    if board is not None:  # every rank unmaps the peers' boards while all of them are still alive (rank 0 runs CPU legs later)
         ndt.attachPoseBoard(None)
+        barrier()
+        board.close()
 
     # ---- single_align leg: one b200reg_align per step (latency-bound: round 1's headline), L2 flushed between steps ----
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
