@@ -809,6 +809,7 @@ def main():
     ndt.alignBatch([p.numpy() for p in pinned_scans[:K]])  # full size: the staging / device buffers reach their final size here
     ndt.alignBatch(pageable_scans[:K])
     if board is not None:
+        barrier()  # attached batch calls are collective: enter the first one together
         ndt.attachPoseBoard(board)
         for _ in range(2):
             ndt.alignBatchDevice(ptrs[:K], counts[:K])

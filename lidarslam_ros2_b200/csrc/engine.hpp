@@ -228,7 +228,7 @@ struct b200comm_board {
   float* h_rows = nullptr;   // pinned + mapped: world x rows x 16 floats (row-major poses), written by the collect kernel
   int* h_counts = nullptr;   // pinned + mapped: world counts, then [world] = error flag of the collect kernel
   int device = 0;
-  double timeout_s = 5.0;
+  double timeout_s = 20.0;  // a peer that never makes the collective batch call is reported, not waited for for ever
 };
 namespace b200 {
 
